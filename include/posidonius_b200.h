@@ -1,0 +1,269 @@
+/*
+ * posidonius_b200.h — C ABI of the B200 ensemble integrator.
+ *
+ * This is the drop-in boundary for ONE path of marblestation/posidonius: the
+ * WHFast kick-drift-kick step with constant-time-lag tides, oblate-spheroid
+ * rotational flattening, general relativity (Kidder1995 / Anderson1975 /
+ * Newhall1983), the implicit-midpoint spin update and evolution-table
+ * interpolation, run over an ENSEMBLE of independent systems on one GPU.
+ *
+ * The reference has no FFI; its boundary is `trait Integrator`
+ * (src/integrator/mod.rs:16-26) implemented by `WHFast`
+ * (src/integrator/whfast.rs:169-318) over the serde image of the `WHFast`
+ * struct (src/integrator/whfast.rs:98-120).  Every entry point below names the
+ * reference item it replaces.  Plain pointers and sizes only; no exceptions
+ * cross this boundary; all functions return 0 on success or a negative
+ * PB200_E_* code (message via pb200_last_error()).
+ *
+ * Layout conventions
+ *   - pb200_case_t is the flattened image of one `WHFast` value (one system).
+ *   - Ensemble state moves as SoA: field-major, then body, then system:
+ *       a[(c * n_bodies + b) * n_systems + s]   for 3-vectors (c = x,y,z)
+ *       a[b * n_systems + s]                    for per-body scalars
+ *       a[s]                                    for per-system scalars
+ */
+#ifndef POSIDONIUS_B200_H
+#define POSIDONIUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_MAX_PARTICLES 10 /* src/constants.rs:3 */
+#define PB200_HISTORIC_RECORD_BYTES 156 /* src/integrator/output.rs:85-89 */
+
+/* error codes */
+#define PB200_OK 0
+#define PB200_E_INVALID (-1)      /* bad argument / inconsistent case */
+#define PB200_E_UNSUPPORTED (-2)  /* effect/integrator outside the hot path (Kaula, creep, disk, wind, IAS15, LeapFrog...) */
+#define PB200_E_CUDA (-3)         /* CUDA runtime failure */
+#define PB200_E_NOMEM (-4)
+
+/* CoordinatesType, enum tag order of src/integrator/whfast.rs:91-95 */
+#define PB200_COORD_JACOBI 0
+#define PB200_COORD_DEMOCRATIC_HELIOCENTRIC 1
+#define PB200_COORD_WHDS 2
+
+/* TidesEffect / RotationalFlatteningEffect / GeneralRelativityEffect tag order
+ * (tides/common.rs:89-93, rotational_flattening/common.rs:51-55, general_relativity.rs:48-52) */
+#define PB200_ROLE_CENTRAL 0
+#define PB200_ROLE_ORBITING 1
+#define PB200_ROLE_DISABLED 2
+
+/* GeneralRelativityImplementation tag order (general_relativity.rs:40-45) */
+#define PB200_GR_KIDDER1995 0
+#define PB200_GR_ANDERSON1975 1
+#define PB200_GR_NEWHALL1983 2
+#define PB200_GR_DISABLED 3
+
+/* EvolutionType tag order (effects/evolution.rs:9-17) */
+#define PB200_EVO_GALLETBOLMONT2017 0
+#define PB200_EVO_BOLMONTMATHIS2016 1
+#define PB200_EVO_BARAFFE2015 2
+#define PB200_EVO_LECONTE2011 3
+#define PB200_EVO_BARAFFE1998 4
+#define PB200_EVO_LECONTECHABRIER2013 5
+#define PB200_EVO_NONEVOLVING 6
+
+/* per-system status word (replaces the reference's panic!/warnings) */
+#define PB200_STATUS_OK 0
+#define PB200_STATUS_COMPLETED 1          /* t + dt > time_limit, whfast.rs:300 */
+#define PB200_STATUS_ROCHE_DESTROYED 2    /* universe.rs:225-228 */
+#define PB200_STATUS_COLLISION 3          /* universe.rs:230-233 */
+#define PB200_STATUS_EJECTED 4            /* universe.rs:234-237 */
+#define PB200_STATUS_ZERO_INERTIA 5       /* particles/common.rs:5-7 */
+/* warning bits, OR-ed into pb200 "warnings" word (do not stop the system) */
+#define PB200_WARN_MIDPOINT_NOT_CONVERGED 1u /* whfast.rs:389-391 */
+#define PB200_WARN_TIMESTEP_GT_PERIOD 2u     /* whfast.rs:702-707 */
+
+/* One body: the fields of `Particle` (src/particles/particle.rs:16-52) that the
+ * hot path reads or carries between steps.  Per-effect scratch that the
+ * reference recomputes before every use is not part of the image. */
+typedef struct pb200_body {
+    double mass;
+    double mass_g;
+    double radius;
+    double radius_of_gyration_2;
+    double moment_of_inertia;
+    double inertial_position[3];
+    double inertial_velocity[3];
+    double inertial_acceleration[3]; /* Newtonian acc. left by the last gravity evaluation; read by Anderson/Newhall GR */
+    double heliocentric_position[3];
+    double heliocentric_velocity[3]; /* host's value is read stale by universe.rs:335-337 */
+    double spin[3];                  /* spin of the previous evaluation feeds r.omega (universe.rs:429-430 order) */
+    double angular_momentum[3];
+    /* tides: ConstantTimeLagParameters (constant_time_lag.rs:12-18) + internal.scaled_dissipation_factor */
+    double tides_dissipation_factor;
+    double tides_dissipation_factor_scale;
+    double tides_love_number;
+    double tides_scaled_dissipation_factor;
+    double tides_lag_angle;
+    double tides_denergy_dt;
+    /* rotational flattening: OblateSpheroidParameters (oblate_spheroid.rs:8-10) */
+    double flattening_love_number;
+    /* general relativity: internal.factor (general_relativity.rs:16) */
+    double general_relativity_factor;
+    /* EvolutionType payload: stellar mass (f64 variants) or 0/1 (LeconteChabrier2013(bool)) */
+    double evolution_parameter;
+    int32_t tides_role;       /* PB200_ROLE_* */
+    int32_t flattening_role;  /* PB200_ROLE_* */
+    int32_t general_relativity_role; /* PB200_ROLE_* */
+    int32_t evolution_type;   /* PB200_EVO_* */
+    int32_t evolution_table;  /* index into the table pool, -1 when NonEvolving */
+    int32_t evolution_left_index; /* Evolver.left_index cursor (evolution.rs:27), carried for recovery images */
+    int32_t id;
+    int32_t reserved;
+} pb200_body_t;
+
+/* One system: flattened `WHFast` (whfast.rs:98-120) + `Universe` (universe.rs:50-63). */
+typedef struct pb200_case {
+    double time_step;
+    double half_time_step;
+    double initial_time;
+    double time_limit;
+    double current_time;
+    double recovery_snapshot_period;
+    double historic_snapshot_period;
+    double last_recovery_snapshot_time;
+    double last_historic_snapshot_time;
+    uint64_t current_iteration;
+    uint64_t n_historic_snapshots;
+    uint64_t timestep_warning;
+    int32_t coordinates_type;   /* PB200_COORD_* */
+    int32_t n_particles;
+    /* ConsiderEffects (universe.rs:40-47) */
+    int32_t consider_tides;
+    int32_t consider_rotational_flattening;
+    int32_t consider_general_relativity;
+    int32_t consider_disk;
+    int32_t consider_wind;
+    int32_t consider_evolution;
+    int32_t general_relativity_implementation; /* PB200_GR_* */
+    /* HostIndices (universe.rs:16-22); MAX_PARTICLES+1 when absent */
+    int32_t host_most_massive;
+    int32_t host_tides;
+    int32_t host_rotational_flattening;
+    int32_t host_general_relativity;
+    int32_t host_disk;
+    pb200_body_t bodies[PB200_MAX_PARTICLES];
+    double inertial_velocity_errors[PB200_MAX_PARTICLES][3];         /* whfast.rs:117 */
+    double particle_angular_momentum_errors[PB200_MAX_PARTICLES][3]; /* whfast.rs:119 */
+    double roche_radiuses[PB200_MAX_PARTICLES * PB200_MAX_PARTICLES]; /* universe.rs:62, row stride = n_particles */
+} pb200_case_t;
+
+/* One evolution table = the vectors of `Evolver` (evolution.rs:19-28). Columns
+ * that the EvolutionType does not use may be NULL. `time` is in days since
+ * initial_time, as stored in the JSON. */
+typedef struct pb200_table {
+    size_t n_rows;
+    const double* time;
+    const double* radius;
+    const double* radius_of_gyration_2;
+    const double* love_number;
+    const double* inverse_tidal_q_factor;
+} pb200_table_t;
+
+typedef struct pb200_ensemble pb200_ensemble_t;
+
+/* Library/version probes. */
+const char* pb200_version(void);
+const char* pb200_last_error(void);
+/* Number of CUDA devices visible; <0 on CUDA error. */
+int pb200_device_count(void);
+
+/* Validates one case against the hot-path scope. Returns PB200_OK,
+ * PB200_E_UNSUPPORTED or PB200_E_INVALID. Mirrors the trial deserialisation +
+ * checks of output::restore_snapshot (output.rs:206-231) and
+ * Universe::new (universe.rs:73-175) — no CPU fallback exists behind it. */
+int pb200_case_validate(const pb200_case_t* c, const pb200_table_t* tables, size_t n_tables);
+
+/* Replaces output::restore_snapshot + Universe ownership (output.rs:206-231):
+ * builds a device-resident ensemble of n_systems systems on `device`.
+ * n_cases must be 1 (the case is replicated) or n_systems. All cases must
+ * share structure (n_particles, coordinates, effects, roles, tables, dt). */
+int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_systems,
+                          const pb200_table_t* tables, size_t n_tables, int device,
+                          pb200_ensemble_t** out);
+void pb200_ensemble_destroy(pb200_ensemble_t* e);
+
+/* Integrator::get_n_particles / get_current_time / get_n_historic_snapshots (mod.rs:18-20). */
+int pb200_ensemble_n_particles(const pb200_ensemble_t* e);
+size_t pb200_ensemble_n_systems(const pb200_ensemble_t* e);
+/* Integrator::set_time_limit / set_snapshot_periods (whfast.rs:187-224); applied to every system. */
+int pb200_ensemble_set_time_limit(pb200_ensemble_t* e, double time_limit);
+int pb200_ensemble_set_snapshot_periods(pb200_ensemble_t* e, double historic_snapshot_period,
+                                        double recovery_snapshot_period);
+
+/* Integrator::initialize_physical_values (whfast.rs:226-233): spin = L/I, evolving
+ * quantities at t = 0, Roche radii. Fails with PB200_E_INVALID on a resumed ensemble
+ * (current_time != 0), like the reference's panic. */
+int pb200_ensemble_initialize_physical_values(pb200_ensemble_t* e);
+
+/* Integrator::iterate called n_steps times on every live system (whfast.rs:235-305).
+ * Systems stop individually when completed (t + dt > time_limit) or on a physical
+ * failure (status word). Historic snapshot records that fall due inside the call are
+ * appended to the ensemble's device-side history buffer (see pb200_ensemble_history_*).
+ * Asynchronous on the ensemble's stream; pb200_ensemble_synchronize() waits. */
+int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps);
+int pb200_ensemble_synchronize(pb200_ensemble_t* e);
+/* Duration in ms of the last pb200_ensemble_step kernel(s), measured with CUDA events
+ * on the ensemble's stream. Synchronizes. */
+int pb200_ensemble_last_step_ms(pb200_ensemble_t* e, float* ms);
+/* Kernel launches issued by this ensemble so far. */
+uint64_t pb200_ensemble_launch_count(const pb200_ensemble_t* e);
+
+/* Per-system status (PB200_STATUS_*), warning bits and the iteration index of the event. */
+int pb200_ensemble_status(pb200_ensemble_t* e, int32_t* status, uint32_t* warnings,
+                          uint64_t* iteration_of_event);
+
+/* SoA download/upload of the dynamic state (layout at top). Any pointer may be NULL.
+ *   position, velocity, acceleration, angular_momentum, spin, velocity_errors,
+ *   angular_momentum_errors : 3 * n_bodies * n_systems
+ *   radius, radius_of_gyration_2, moment_of_inertia : n_bodies * n_systems
+ *   current_time : n_systems */
+typedef struct pb200_state_view {
+    double* position;
+    double* velocity;
+    double* acceleration;
+    double* angular_momentum;
+    double* spin;
+    double* velocity_errors;
+    double* angular_momentum_errors;
+    double* radius;
+    double* radius_of_gyration_2;
+    double* moment_of_inertia;
+    double* current_time;
+} pb200_state_view_t;
+int pb200_ensemble_download(pb200_ensemble_t* e, const pb200_state_view_t* dst);
+int pb200_ensemble_upload(pb200_ensemble_t* e, const pb200_state_view_t* src);
+/* Full image of system `s` as a pb200_case_t (what write_recovery_snapshot serialises, whfast.rs:307-316). */
+int pb200_ensemble_get_case(pb200_ensemble_t* e, size_t s, pb200_case_t* out);
+
+/* Historic snapshots (output.rs:119-163; whfast.rs:237-261). Records are produced on
+ * the device in the reference's 156-byte little-endian layout, one per body per
+ * snapshot. `pb200_ensemble_history_pending` = snapshots (per system) buffered since
+ * the last drain; `pb200_ensemble_history_drain` copies them system-major:
+ * dst[((s * n_snapshots + k) * n_bodies + b) * 156 ...] and empties the buffer. */
+size_t pb200_ensemble_history_pending(pb200_ensemble_t* e);
+int pb200_ensemble_history_drain(pb200_ensemble_t* e, void* dst, size_t dst_bytes);
+
+/* Diagnostics with the formulas of Universe::compute_total_energy /
+ * compute_total_angular_momentum (universe.rs:625-658), evaluated on the device after
+ * a heliocentric refresh. energy / angular_momentum: n_systems each. */
+int pb200_ensemble_summary(pb200_ensemble_t* e, double* energy, double* angular_momentum);
+
+/* End-to-end convenience for benchmarking the boundary with HOST buffers: uploads the
+ * SoA state in `io`, advances n_steps, downloads the state back into `io`. */
+int pb200_ensemble_run_host(pb200_ensemble_t* e, const pb200_state_view_t* io, uint64_t n_steps);
+
+/* DFMA-chain microbenchmark used as the FP64 roofline denominator: returns the
+ * sustained fp64 FLOP/s (FMA = 2) measured over `ms_target` milliseconds. */
+int pb200_measure_fp64_peak(int device, double ms_target, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSIDONIUS_B200_H */
