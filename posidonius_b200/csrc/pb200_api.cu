@@ -1,0 +1,728 @@
+// pb200_api.cu — C ABI of the B200 ensemble integrator (include/posidonius_b200.h).
+// Host side: case validation (no CPU fallback: unsupported effects are rejected), SoA packing,
+// device residency, launches of the step kernel, status / state / history transfer.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "whfast_step.cuh"
+
+using namespace pb200;
+
+static thread_local std::string g_last_error;
+static int set_error(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                                         \
+    do {                                                                                                        \
+        cudaError_t _e = (expr);                                                                                \
+        if (_e != cudaSuccess) return set_error(PB200_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// small device kernels around the step kernel
+namespace pb200 {
+
+// Integrator::initialize_physical_values (whfast.rs:226-233): evolving quantities at t, spin = L/I
+// (universe.rs:305-316) and the Roche radii table (universe.rs:177-196).
+__global__ void init_physical_kernel(const __grid_constant__ KParams P) {
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ns = (size_t)P.n_sys;
+    if (gtid >= ns * (size_t)P.n_bodies) return;
+    const size_t sys = gtid % ns;
+    const int b = (int)(gtid / ns);
+    const size_t i = (size_t)b * ns + sys, cs = (size_t)P.n_bodies * ns;
+    Roles ro; ro.valid = true; ro.host = b == P.host; ro.planet = !ro.host; ro.t_on = ro.f_on = ro.g_on = false;
+    Lane q;
+    q.m = P.mass[i]; q.R = P.radius[i]; q.rg2 = P.rg2[i]; q.I = P.moi[i];
+    if (P.flags & FLAG_EVO) evolve_lane(P, ro, b, P.t[sys], q);
+    P.radius[i] = q.R; P.rg2[i] = q.rg2; P.moi[i] = q.I;
+    double invI = 1. / q.I;
+    P.spin[i] = P.L[i] * invI; P.spin[i + cs] = P.L[i + cs] * invI; P.spin[i + 2 * cs] = P.L[i + 2 * cs] * invI;
+    // Roche radii use the radii AFTER the evolution update (whfast.rs:231-232). Body j's evolved radius is recomputed
+    // here instead of read back, so no ordering between threads is needed (the update depends on t only).
+    double* roche = const_cast<double*>(P.roche);
+    for (int j = 0; j < P.n_bodies; j++) {
+        if (j == b) continue;
+        const size_t ij = (size_t)j * ns + sys;
+        Lane t; t.m = P.mass[ij]; t.R = P.radius[ij]; t.rg2 = 1.; t.I = 1.;
+        if (P.flags & FLAG_EVO) evolve_lane(P, ro, j, P.t[sys], t);
+        double rr;
+        if (q.m > t.m) rr = (t.R / 0.462) * cbrt(q.m / t.m);
+        else rr = (q.R / 0.462) * cbrt(t.m / q.m);
+        roche[((size_t)(b * P.n_bodies + j)) * ns + sys] = rr;
+    }
+}
+
+// Universe::compute_total_energy / compute_total_angular_momentum (universe.rs:625-658) after a heliocentric refresh.
+__global__ void summary_kernel(const __grid_constant__ KParams P, double* energy, double* angmom) {
+    const size_t sys = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ns = (size_t)P.n_sys;
+    if (sys >= ns) return;
+    const int n = P.n_bodies;
+    const size_t cs = (size_t)n * ns;
+    double hx[PB200_MAX_PARTICLES][3], hv[PB200_MAX_PARTICLES][3], m[PB200_MAX_PARTICLES], mg[PB200_MAX_PARTICLES];
+    const size_t ih = (size_t)P.host * ns + sys;
+    for (int b = 0; b < n; b++) {
+        size_t i = (size_t)b * ns + sys;
+        for (int c = 0; c < 3; c++) {
+            hx[b][c] = b == P.host ? 0. : P.pos[i + c * cs] - P.pos[ih + c * cs];
+            hv[b][c] = b == P.host ? 0. : P.vel[i + c * cs] - P.vel[ih + c * cs];
+        }
+        m[b] = P.mass[i]; mg[b] = P.mass_g[i];
+    }
+    double ekin = 0., epot = 0.;
+    for (int b = 0; b < n; b++) ekin += 0.5 * m[b] * (hv[b][0] * hv[b][0] + hv[b][1] * hv[b][1] + hv[b][2] * hv[b][2]);
+    for (int a = 0; a < n; a++)
+        for (int b = a + 1; b < n; b++) {
+            double dx = hx[a][0] - hx[b][0], dy = hx[a][1] - hx[b][1], dz = hx[a][2] - hx[b][2];
+            epot -= mg[b] * m[a] / sqrt(dx * dx + dy * dy + dz * dz);
+        }
+    energy[sys] = ekin + epot;
+    double lx = 0., ly = 0., lz = 0.;
+    for (int b = 0; b < n; b++) {
+        lx += m[b] * (hx[b][1] * hv[b][2] - hx[b][2] * hv[b][1]);
+        ly += m[b] * (hx[b][2] * hv[b][0] - hx[b][0] * hv[b][2]);
+        lz += m[b] * (hx[b][0] * hv[b][1] - hx[b][1] * hv[b][0]);
+    }
+    angmom[sys] = sqrt(lx * lx + ly * ly + lz * lz);
+}
+
+// SoA history planes -> the reference's 156-byte records (output.rs:119-163), system-major.
+// One thread per (system, snapshot, body); 4-byte stores because the doubles sit at offset 20 (unaligned).
+__global__ void pack_history_kernel(const __grid_constant__ KParams P, int n_snap, double dt, unsigned int* out) {
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ns = (size_t)P.n_sys;
+    const int n = P.n_bodies;
+    const size_t total = ns * (size_t)n_snap * (size_t)n;
+    if (gtid >= total) return;
+    const int b = (int)(gtid % n);
+    const int k = (int)((gtid / n) % n_snap);
+    const size_t sys = gtid / ((size_t)n * n_snap);
+    const size_t cs = (size_t)n * ns;
+    const double* h = P.hist + (size_t)k * PB_HIST_FIELDS * cs + (size_t)b * ns + sys;
+    unsigned int* w = out + gtid * (PB200_HISTORIC_RECORD_BYTES / 4);
+    auto put = [&](int word, double v) {
+        unsigned long long u = (unsigned long long)__double_as_longlong(v);
+        w[word] = (unsigned int)(u & 0xffffffffull); w[word + 1] = (unsigned int)(u >> 32);
+    };
+    put(0, h[0]);           // current_time
+    put(2, dt);             // time_step
+    w[4] = (unsigned int)b; // particle id (i32)
+    const bool have = k < P.hist_count[sys];  // systems that stopped early have fewer snapshots: zero records
+    for (int f = 0; f < 14; f++) put(5 + 2 * f, have ? h[(size_t)(1 + f) * cs] : 0.);  // pos, spin, vel, mass, radius, rg2, love, sigma
+    put(5 + 2 * 14, 0.);                                   // lag_angle (0 for the supported evolution types, evolution.rs:552-565)
+    put(5 + 2 * 15, have ? h[(size_t)15 * cs] : 0.);       // denergy_dt
+    put(5 + 2 * 16, 0.);                                   // disk migration_timescale (disk out of scope)
+    if (!have) { put(0, 0.); }
+}
+
+// DFMA chain microbenchmark: 8 independent chains per thread.
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace pb200
+
+// ---------------------------------------------------------------------------------------------
+struct pb200_ensemble {
+    int device = 0;
+    size_t n_sys = 0;
+    int n_bodies = 0;
+    KParams P{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    bool timing_pending = false;
+    uint64_t launches = 0;
+    std::vector<void*> allocations;
+    pb200_case_t tmpl{};                // structure + uniform scalars (system 0 image at creation)
+    std::vector<pb200_case_t> cases;    // per-system images when n_cases == n_systems (params may differ), else 1
+    int coord = 0, gr = PB200_GR_DISABLED;
+    // device arrays that are not part of KParams constness
+    double *d_mass = nullptr, *d_mass_g = nullptr, *d_sigma = nullptr, *d_k2t = nullptr, *d_k2f = nullptr, *d_roche = nullptr;
+    double *d_energy = nullptr, *d_angmom = nullptr;
+    unsigned int* d_records = nullptr;
+    size_t records_capacity = 0;
+    double recovery_snapshot_period = 0.;
+    // host mirror of the ensemble clock (exact snapshot counting without a device round trip)
+    bool uniform_clock = true;
+    double clock_t = 0., clock_last_hist = -1.;
+    size_t hist_pending_host = 0;
+};
+
+template <class T>
+static int dev_alloc(pb200_ensemble* e, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t err = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (err != cudaSuccess) return set_error(PB200_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(err));
+    err = cudaMemset(q, 0, count * sizeof(T) + 16);
+    if (err != cudaSuccess) return set_error(PB200_E_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(err));
+    e->allocations.push_back(q);
+    *p = (T*)q;
+    return PB200_OK;
+}
+
+static bool is_dynamical_tide_evolution(const pb200_body_t& b) {
+    return b.evolution_type == PB200_EVO_GALLETBOLMONT2017 || b.evolution_type == PB200_EVO_BOLMONTMATHIS2016 ||
+           (b.evolution_type == PB200_EVO_LECONTECHABRIER2013 && b.evolution_parameter != 0.);
+}
+
+template <int COORD>
+static cudaError_t launch_gr(pb200_ensemble* e, unsigned grid, unsigned long long n) {
+    switch (e->gr) {
+        case PB200_GR_KIDDER1995: whfast_steps_kernel<COORD, PB200_GR_KIDDER1995><<<grid, PB_BLOCK, 0, e->stream>>>(e->P, n); break;
+        case PB200_GR_ANDERSON1975: whfast_steps_kernel<COORD, PB200_GR_ANDERSON1975><<<grid, PB_BLOCK, 0, e->stream>>>(e->P, n); break;
+        case PB200_GR_NEWHALL1983: whfast_steps_kernel<COORD, PB200_GR_NEWHALL1983><<<grid, PB_BLOCK, 0, e->stream>>>(e->P, n); break;
+        default: whfast_steps_kernel<COORD, PB200_GR_DISABLED><<<grid, PB_BLOCK, 0, e->stream>>>(e->P, n); break;
+    }
+    return cudaGetLastError();
+}
+
+extern "C" {
+
+const char* pb200_version(void) { return "posidonius_b200 0.1.0 (sm_100a)"; }
+const char* pb200_last_error(void) { return g_last_error.c_str(); }
+
+int pb200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { set_error(PB200_E_CUDA, cudaGetErrorString(e)); return -1; }
+    return n;
+}
+
+int pb200_case_validate(const pb200_case_t* c, const pb200_table_t* tables, size_t n_tables) {
+    if (!c) return set_error(PB200_E_INVALID, "null case");
+    const int n = c->n_particles;
+    if (n < 2 || n > PB200_MAX_PARTICLES) return set_error(PB200_E_INVALID, "n_particles must be in [2, 10]");
+    if (c->coordinates_type < 0 || c->coordinates_type > 2) return set_error(PB200_E_INVALID, "unknown coordinates type");
+    if (!(c->time_step > 0.) || c->half_time_step != 0.5 * c->time_step) return set_error(PB200_E_INVALID, "time_step must be > 0 and half_time_step = time_step / 2");
+    if (c->consider_disk) return set_error(PB200_E_UNSUPPORTED, "disk interaction is outside the B200 hot path (no CPU fallback)");
+    if (c->consider_wind) return set_error(PB200_E_UNSUPPORTED, "stellar wind is outside the B200 hot path (no CPU fallback)");
+    const int h = c->host_most_massive;
+    if (h < 0 || h >= n) return set_error(PB200_E_INVALID, "host_most_massive out of range");
+    for (int i = 0; i < n; i++) {
+        if (i != h && !(c->bodies[i].mass <= c->bodies[h].mass)) return set_error(PB200_E_INVALID, "host_most_massive is not the most massive body");
+        if (!(c->bodies[i].moment_of_inertia > 0.)) return set_error(PB200_E_INVALID, "moment of inertia must be > 0 (particles/common.rs:5-7)");
+        if (!(c->bodies[i].mass > 0.)) return set_error(PB200_E_INVALID, "mass must be > 0");
+    }
+    if (c->consider_tides) {
+        if (c->host_tides != h) return set_error(PB200_E_UNSUPPORTED, "the tidal host must be the most massive body on the B200 path");
+        if (c->bodies[h].tides_role != PB200_ROLE_CENTRAL) return set_error(PB200_E_INVALID, "tides enabled without a CentralBody host");
+    }
+    if (c->consider_rotational_flattening) {
+        if (c->host_rotational_flattening != h) return set_error(PB200_E_UNSUPPORTED, "the rotational-flattening host must be the most massive body on the B200 path");
+        if (c->bodies[h].flattening_role != PB200_ROLE_CENTRAL) return set_error(PB200_E_INVALID, "rotational flattening enabled without a CentralBody host");
+    }
+    if (c->consider_general_relativity) {
+        if (c->host_general_relativity != h) return set_error(PB200_E_INVALID, "the central body for General Relativity should be the most massive one (universe.rs:925-927)");
+        if (c->bodies[h].general_relativity_role != PB200_ROLE_CENTRAL) return set_error(PB200_E_INVALID, "general relativity enabled without a CentralBody host");
+        int g = c->general_relativity_implementation;
+        if (g != PB200_GR_KIDDER1995 && g != PB200_GR_ANDERSON1975 && g != PB200_GR_NEWHALL1983)
+            return set_error(PB200_E_INVALID, "general relativity enabled with implementation Disabled");
+    }
+    for (int i = 0; i < n; i++) {
+        const pb200_body_t& b = c->bodies[i];
+        if (i != h) {
+            if (b.tides_role == PB200_ROLE_CENTRAL && c->consider_tides) return set_error(PB200_E_INVALID, "only one central body is allowed for tidal effects");
+            if (b.flattening_role == PB200_ROLE_CENTRAL && c->consider_rotational_flattening) return set_error(PB200_E_INVALID, "only one central body is allowed for rotational flattening effects");
+            if (b.general_relativity_role == PB200_ROLE_CENTRAL && c->consider_general_relativity) return set_error(PB200_E_INVALID, "only one central body is allowed for general relativity effects");
+        }
+        if (c->consider_evolution && b.evolution_type != PB200_EVO_NONEVOLVING) {
+            if (is_dynamical_tide_evolution(b))
+                return set_error(PB200_E_UNSUPPORTED, "evolution types with dynamical-tide (pair-dependent) dissipation are outside the B200 hot path");
+            if (b.evolution_table < 0 || (size_t)b.evolution_table >= n_tables || !tables)
+                return set_error(PB200_E_INVALID, "evolving body without an evolution table");
+            const pb200_table_t& t = tables[b.evolution_table];
+            if (t.n_rows < 1 || !t.time || !t.radius) return set_error(PB200_E_INVALID, "evolution table needs time and radius columns");
+            bool need_rg2 = b.evolution_type == PB200_EVO_BARAFFE2015 || b.evolution_type == PB200_EVO_LECONTE2011 ||
+                            b.evolution_type == PB200_EVO_LECONTECHABRIER2013;
+            if (need_rg2 && !t.radius_of_gyration_2) return set_error(PB200_E_INVALID, "evolution table needs a radius_of_gyration_2 column");
+        }
+    }
+    // Q4: universe.rs:335-337 reads the host's stale heliocentric velocity; the kernel takes it as zero.
+    const double* hv = c->bodies[h].heliocentric_velocity;
+    if (hv[0] != 0. || hv[1] != 0. || hv[2] != 0.)
+        return set_error(PB200_E_UNSUPPORTED, "the host's heliocentric velocity must be zero (stale-read quirk of universe.rs:335-337 is not reproduced)");
+    return PB200_OK;
+}
+
+static int same_structure(const pb200_case_t& a, const pb200_case_t& b) {
+    if (a.n_particles != b.n_particles || a.coordinates_type != b.coordinates_type || a.time_step != b.time_step ||
+        a.time_limit != b.time_limit || a.historic_snapshot_period != b.historic_snapshot_period ||
+        a.consider_tides != b.consider_tides || a.consider_rotational_flattening != b.consider_rotational_flattening ||
+        a.consider_general_relativity != b.consider_general_relativity || a.consider_evolution != b.consider_evolution ||
+        a.general_relativity_implementation != b.general_relativity_implementation || a.host_most_massive != b.host_most_massive)
+        return 0;
+    for (int i = 0; i < a.n_particles; i++) {
+        const pb200_body_t &x = a.bodies[i], &y = b.bodies[i];
+        if (x.tides_role != y.tides_role || x.flattening_role != y.flattening_role ||
+            x.general_relativity_role != y.general_relativity_role || x.evolution_type != y.evolution_type ||
+            x.evolution_table != y.evolution_table)
+            return 0;
+    }
+    return 1;
+}
+
+void pb200_ensemble_destroy(pb200_ensemble_t* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void* p : e->allocations) cudaFree(p);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_systems, const pb200_table_t* tables,
+                          size_t n_tables, int device, pb200_ensemble_t** out) {
+    if (!cases || !out || n_systems == 0) return set_error(PB200_E_INVALID, "null argument or empty ensemble");
+    if (n_cases != 1 && n_cases != n_systems) return set_error(PB200_E_INVALID, "n_cases must be 1 or n_systems");
+    if (n_tables > PB200_MAX_PARTICLES) return set_error(PB200_E_INVALID, "too many evolution tables");
+    int rc = pb200_case_validate(&cases[0], tables, n_tables);
+    if (rc != PB200_OK) return rc;
+    for (size_t s = 1; s < n_cases; s++) {
+        if (!same_structure(cases[0], cases[s])) return set_error(PB200_E_INVALID, "all cases of an ensemble must share structure (bodies, coordinates, effects, dt, limits)");
+        rc = pb200_case_validate(&cases[s], tables, n_tables);
+        if (rc != PB200_OK) return rc;
+    }
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return set_error(PB200_E_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    pb200_ensemble* e = new pb200_ensemble();
+    e->device = device;
+    e->n_sys = n_systems;
+    const pb200_case_t& c0 = cases[0];
+    const int n = c0.n_particles;
+    e->n_bodies = n;
+    e->tmpl = c0;
+    e->cases.assign(cases, cases + n_cases);
+    e->coord = c0.coordinates_type;
+    e->gr = c0.consider_general_relativity ? c0.general_relativity_implementation : PB200_GR_DISABLED;
+    e->recovery_snapshot_period = c0.recovery_snapshot_period;
+    e->clock_t = c0.current_time; e->clock_last_hist = c0.last_historic_snapshot_time;
+    for (size_t s = 1; s < n_cases; s++)
+        if (cases[s].current_time != c0.current_time || cases[s].last_historic_snapshot_time != c0.last_historic_snapshot_time) e->uniform_clock = false;
+    KParams& P = e->P;
+    P.n_sys = (int)n_systems; P.n_bodies = n;
+    int W = 2; while (W < n) W <<= 1;
+    P.W = W; P.shift = 0; while ((1 << P.shift) < W) P.shift++;
+    P.host = c0.host_most_massive;
+    P.flags = (c0.consider_tides ? FLAG_TIDES : 0) | (c0.consider_rotational_flattening ? FLAG_FLAT : 0) |
+              (c0.consider_general_relativity ? FLAG_GR : 0) | (c0.consider_evolution ? FLAG_EVO : 0);
+    P.spin_on = c0.consider_tides || c0.consider_rotational_flattening || c0.consider_evolution ||
+                (c0.consider_general_relativity && c0.general_relativity_implementation == PB200_GR_KIDDER1995);
+    P.dt = c0.time_step; P.half_dt = c0.half_time_step; P.time_limit = c0.time_limit; P.hist_period = c0.historic_snapshot_period;
+    P.tides_orbiting = P.flat_orbiting = P.gr_orbiting = P.gr_enabled = 0;
+    for (int i = 0; i < n; i++) {
+        const pb200_body_t& b = c0.bodies[i];
+        if (b.tides_role == PB200_ROLE_ORBITING) P.tides_orbiting |= 1u << i;
+        if (b.flattening_role == PB200_ROLE_ORBITING) P.flat_orbiting |= 1u << i;
+        if (b.general_relativity_role == PB200_ROLE_ORBITING) P.gr_orbiting |= 1u << i;
+        if (b.general_relativity_role != PB200_ROLE_DISABLED) P.gr_enabled |= 1u << i;
+        P.evo_table[i] = (c0.consider_evolution && b.evolution_type != PB200_EVO_NONEVOLVING) ? b.evolution_table : -1;
+    }
+    for (int i = n; i < PB200_MAX_PARTICLES; i++) P.evo_table[i] = -1;
+    P.tides_host_central = c0.bodies[P.host].tides_role == PB200_ROLE_CENTRAL;
+    P.flat_host_central = c0.bodies[P.host].flattening_role == PB200_ROLE_CENTRAL;
+
+#define TRY(x) do { int _r = (x); if (_r != PB200_OK) { pb200_ensemble_destroy(e); return _r; } } while (0)
+#define CUDA_TRY_E(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { pb200_ensemble_destroy(e); return set_error(PB200_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+    CUDA_TRY_E(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_TRY_E(cudaEventCreate(&e->ev0));
+    CUDA_TRY_E(cudaEventCreate(&e->ev1));
+    // evolution tables (replicated per GPU, read through the read-only path)
+    for (int i = 0; i < PB200_MAX_PARTICLES; i++) P.tables[i] = DevTable{nullptr, nullptr, nullptr, 0, 0, 0};
+    for (int i = 0; i < n; i++) {
+        int ti = P.evo_table[i];
+        if (ti < 0 || P.tables[ti].time) continue;
+        const pb200_table_t& t = tables[ti];
+        const pb200_body_t& b = c0.bodies[i];
+        double *dt_ = nullptr, *dr = nullptr, *dg = nullptr;
+        TRY(dev_alloc(e, &dt_, t.n_rows));
+        TRY(dev_alloc(e, &dr, t.n_rows));
+        CUDA_TRY_E(cudaMemcpy(dt_, t.time, t.n_rows * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY_E(cudaMemcpy(dr, t.radius, t.n_rows * sizeof(double), cudaMemcpyHostToDevice));
+        int need_rg2 = b.evolution_type == PB200_EVO_BARAFFE2015 || b.evolution_type == PB200_EVO_LECONTE2011 ||
+                       b.evolution_type == PB200_EVO_LECONTECHABRIER2013;
+        if (need_rg2) {
+            TRY(dev_alloc(e, &dg, t.n_rows));
+            CUDA_TRY_E(cudaMemcpy(dg, t.radius_of_gyration_2, t.n_rows * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        P.tables[ti] = DevTable{dt_, dr, dg, (int)t.n_rows, 1, need_rg2};
+    }
+    const size_t ns = n_systems, nb = (size_t)n;
+    TRY(dev_alloc(e, &P.pos, 3 * nb * ns)); TRY(dev_alloc(e, &P.vel, 3 * nb * ns)); TRY(dev_alloc(e, &P.acc, 3 * nb * ns));
+    TRY(dev_alloc(e, &P.L, 3 * nb * ns)); TRY(dev_alloc(e, &P.spin, 3 * nb * ns)); TRY(dev_alloc(e, &P.verr, 3 * nb * ns));
+    TRY(dev_alloc(e, &P.lerr, 3 * nb * ns));
+    TRY(dev_alloc(e, &P.radius, nb * ns)); TRY(dev_alloc(e, &P.rg2, nb * ns)); TRY(dev_alloc(e, &P.moi, nb * ns));
+    TRY(dev_alloc(e, &e->d_mass, nb * ns)); TRY(dev_alloc(e, &e->d_mass_g, nb * ns)); TRY(dev_alloc(e, &e->d_sigma, nb * ns));
+    TRY(dev_alloc(e, &e->d_k2t, nb * ns)); TRY(dev_alloc(e, &e->d_k2f, nb * ns)); TRY(dev_alloc(e, &e->d_roche, nb * nb * ns));
+    P.mass = e->d_mass; P.mass_g = e->d_mass_g; P.sigma = e->d_sigma; P.k2t = e->d_k2t; P.k2f = e->d_k2f; P.roche = e->d_roche;
+    TRY(dev_alloc(e, &P.t, ns)); TRY(dev_alloc(e, &P.last_hist, ns));
+    TRY(dev_alloc(e, &P.iteration, ns)); TRY(dev_alloc(e, &P.n_hist, ns)); TRY(dev_alloc(e, &P.event_iteration, ns));
+    TRY(dev_alloc(e, &P.tswarn, ns)); TRY(dev_alloc(e, &P.status, ns)); TRY(dev_alloc(e, &P.warnings, ns));
+    TRY(dev_alloc(e, &P.hist_count, ns));
+    TRY(dev_alloc(e, &P.tide_scratch, (size_t)PB_TIDE_SCRATCH * nb * ns));
+    TRY(dev_alloc(e, &e->d_energy, ns)); TRY(dev_alloc(e, &e->d_angmom, ns));
+    // history planes: keep the buffer below ~256 MB
+    {
+        size_t per_slot = (size_t)PB_HIST_FIELDS * nb * ns * sizeof(double);
+        size_t slots = (256ull << 20) / per_slot;
+        if (slots < 2) slots = 2;
+        if (slots > 64) slots = 64;
+        P.hist_capacity = (int)slots;
+        TRY(dev_alloc(e, &P.hist, (size_t)PB_HIST_FIELDS * nb * ns * slots));
+    }
+    // pack the SoA on the host and upload
+    {
+        std::vector<double> buf(3 * nb * ns);
+        auto up3 = [&](double* dst, auto get) -> int {
+            for (size_t s = 0; s < ns; s++) {
+                const pb200_case_t& cs_ = cases[n_cases == 1 ? 0 : s];
+                for (size_t b = 0; b < nb; b++) {
+                    const double* v = get(cs_, (int)b);
+                    for (int c = 0; c < 3; c++) buf[((size_t)c * nb + b) * ns + s] = v[c];
+                }
+            }
+            cudaError_t err = cudaMemcpy(dst, buf.data(), 3 * nb * ns * sizeof(double), cudaMemcpyHostToDevice);
+            return err == cudaSuccess ? PB200_OK : set_error(PB200_E_CUDA, cudaGetErrorString(err));
+        };
+        auto up1 = [&](double* dst, auto get) -> int {
+            for (size_t s = 0; s < ns; s++) {
+                const pb200_case_t& cs_ = cases[n_cases == 1 ? 0 : s];
+                for (size_t b = 0; b < nb; b++) buf[b * ns + s] = get(cs_, (int)b);
+            }
+            cudaError_t err = cudaMemcpy(dst, buf.data(), nb * ns * sizeof(double), cudaMemcpyHostToDevice);
+            return err == cudaSuccess ? PB200_OK : set_error(PB200_E_CUDA, cudaGetErrorString(err));
+        };
+        TRY(up3(P.pos, [](const pb200_case_t& c, int b) { return c.bodies[b].inertial_position; }));
+        TRY(up3(P.vel, [](const pb200_case_t& c, int b) { return c.bodies[b].inertial_velocity; }));
+        TRY(up3(P.acc, [](const pb200_case_t& c, int b) { return c.bodies[b].inertial_acceleration; }));
+        TRY(up3(P.L, [](const pb200_case_t& c, int b) { return c.bodies[b].angular_momentum; }));
+        TRY(up3(P.spin, [](const pb200_case_t& c, int b) { return c.bodies[b].spin; }));
+        TRY(up3(P.verr, [](const pb200_case_t& c, int b) { return (const double*)c.inertial_velocity_errors[b]; }));
+        TRY(up3(P.lerr, [](const pb200_case_t& c, int b) { return (const double*)c.particle_angular_momentum_errors[b]; }));
+        TRY(up1(P.radius, [](const pb200_case_t& c, int b) { return c.bodies[b].radius; }));
+        TRY(up1(P.rg2, [](const pb200_case_t& c, int b) { return c.bodies[b].radius_of_gyration_2; }));
+        TRY(up1(P.moi, [](const pb200_case_t& c, int b) { return c.bodies[b].moment_of_inertia; }));
+        TRY(up1(e->d_mass, [](const pb200_case_t& c, int b) { return c.bodies[b].mass; }));
+        TRY(up1(e->d_mass_g, [](const pb200_case_t& c, int b) { return c.bodies[b].mass_g; }));
+        TRY(up1(e->d_sigma, [](const pb200_case_t& c, int b) { return c.bodies[b].tides_scaled_dissipation_factor; }));
+        TRY(up1(e->d_k2t, [](const pb200_case_t& c, int b) { return c.bodies[b].tides_role != PB200_ROLE_DISABLED ? c.bodies[b].tides_love_number : 0.; }));
+        TRY(up1(e->d_k2f, [](const pb200_case_t& c, int b) { return c.bodies[b].flattening_role != PB200_ROLE_DISABLED ? c.bodies[b].flattening_love_number : 0.; }));
+        // roche [i][j][s]
+        {
+            std::vector<double> rb(nb * nb * ns);
+            for (size_t s = 0; s < ns; s++) {
+                const pb200_case_t& cs_ = cases[n_cases == 1 ? 0 : s];
+                for (size_t i = 0; i < nb * nb; i++) rb[i * ns + s] = cs_.roche_radiuses[i];
+            }
+            CUDA_TRY_E(cudaMemcpy(e->d_roche, rb.data(), rb.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        std::vector<double> t(ns), lh(ns);
+        std::vector<unsigned long long> it(ns), nh(ns), tw(ns);
+        for (size_t s = 0; s < ns; s++) {
+            const pb200_case_t& cs_ = cases[n_cases == 1 ? 0 : s];
+            t[s] = cs_.current_time; lh[s] = cs_.last_historic_snapshot_time; it[s] = cs_.current_iteration;
+            nh[s] = cs_.n_historic_snapshots; tw[s] = cs_.timestep_warning;
+        }
+        CUDA_TRY_E(cudaMemcpy(P.t, t.data(), ns * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY_E(cudaMemcpy(P.last_hist, lh.data(), ns * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY_E(cudaMemcpy(P.iteration, it.data(), ns * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        CUDA_TRY_E(cudaMemcpy(P.n_hist, nh.data(), ns * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        CUDA_TRY_E(cudaMemcpy(P.tswarn, tw.data(), ns * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+#undef TRY
+#undef CUDA_TRY_E
+    *out = e;
+    return PB200_OK;
+}
+
+int pb200_ensemble_n_particles(const pb200_ensemble_t* e) { return e ? e->n_bodies : 0; }
+size_t pb200_ensemble_n_systems(const pb200_ensemble_t* e) { return e ? e->n_sys : 0; }
+
+int pb200_ensemble_set_time_limit(pb200_ensemble_t* e, double time_limit) {
+    if (!e) return set_error(PB200_E_INVALID, "null ensemble");
+    // whfast.rs:187-208: ignored unless > 0 and different
+    if (time_limit > 0. && e->P.time_limit != time_limit) { e->P.time_limit = time_limit; e->tmpl.time_limit = time_limit; }
+    return PB200_OK;
+}
+int pb200_ensemble_set_snapshot_periods(pb200_ensemble_t* e, double historic, double recovery) {
+    if (!e) return set_error(PB200_E_INVALID, "null ensemble");
+    if (historic > 0. && e->P.hist_period != historic) { e->P.hist_period = historic; e->tmpl.historic_snapshot_period = historic; }
+    if (recovery > 0. && e->recovery_snapshot_period != recovery) { e->recovery_snapshot_period = recovery; e->tmpl.recovery_snapshot_period = recovery; }
+    return PB200_OK;
+}
+
+int pb200_ensemble_initialize_physical_values(pb200_ensemble_t* e) {
+    if (!e) return set_error(PB200_E_INVALID, "null ensemble");
+    CUDA_TRY(cudaSetDevice(e->device));
+    for (const auto& c : e->cases)
+        if (c.current_time != 0.) return set_error(PB200_E_INVALID, "Physical values cannot be initialized on a resumed simulation (whfast.rs:227-229)");
+    size_t total = e->n_sys * (size_t)e->n_bodies;
+    init_physical_kernel<<<(unsigned)((total + 127) / 128), 128, 0, e->stream>>>(e->P);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return PB200_OK;
+}
+
+int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
+    if (!e) return set_error(PB200_E_INVALID, "null ensemble");
+    if (n_steps == 0) return PB200_OK;
+    CUDA_TRY(cudaSetDevice(e->device));
+    const size_t threads = e->n_sys * (size_t)e->P.W;
+    const unsigned grid = (unsigned)((threads + PB_BLOCK - 1) / PB_BLOCK);
+    // The history planes hold hist_capacity snapshots; refuse a call that could overflow them (the caller drains and
+    // steps in smaller calls). The count is exact when the ensemble shares one clock, else a device query.
+    {
+        size_t upcoming;
+        if (e->uniform_clock) {
+            upcoming = 0;
+            double t = e->clock_t, lh = e->clock_last_hist;
+            for (uint64_t k = 0; k < n_steps; k++) {
+                bool first = lh < 0.;
+                if (first || lh + e->P.hist_period <= t) { upcoming++; if (!first) lh += e->P.hist_period; else lh = 0.; }
+                t += e->P.dt;
+                if (t + e->P.dt > e->P.time_limit) break;
+            }
+            if (e->hist_pending_host + upcoming > (size_t)e->P.hist_capacity)
+                return set_error(PB200_E_INVALID, "history buffer would overflow: call pb200_ensemble_history_drain and step in smaller calls");
+            // advance the host mirror of the clock
+            t = e->clock_t; lh = e->clock_last_hist;
+            for (uint64_t k = 0; k < n_steps; k++) {
+                bool first = lh < 0.;
+                if (first || lh + e->P.hist_period <= t) { if (!first) lh += e->P.hist_period; else lh = 0.; }
+                t += e->P.dt;
+                if (t + e->P.dt > e->P.time_limit) break;
+            }
+            e->clock_t = t; e->clock_last_hist = lh;
+            e->hist_pending_host += upcoming;
+        } else {
+            upcoming = (size_t)std::floor((double)n_steps * e->P.dt / e->P.hist_period) + 2;
+            if (pb200_ensemble_history_pending(e) + upcoming > (size_t)e->P.hist_capacity)
+                return set_error(PB200_E_INVALID, "history buffer would overflow: call pb200_ensemble_history_drain and step in smaller calls");
+        }
+    }
+    CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
+    {
+        cudaError_t err;
+        switch (e->coord) {
+            case PB200_COORD_JACOBI: err = launch_gr<PB200_COORD_JACOBI>(e, grid, n_steps); break;
+            case PB200_COORD_DEMOCRATIC_HELIOCENTRIC: err = launch_gr<PB200_COORD_DEMOCRATIC_HELIOCENTRIC>(e, grid, n_steps); break;
+            default: err = launch_gr<PB200_COORD_WHDS>(e, grid, n_steps); break;
+        }
+        e->launches++;
+        if (err != cudaSuccess) return set_error(PB200_E_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(err));
+    }
+    CUDA_TRY(cudaEventRecord(e->ev1, e->stream));
+    e->timing_pending = true;
+    return PB200_OK;
+}
+
+int pb200_ensemble_synchronize(pb200_ensemble_t* e) {
+    if (!e) return set_error(PB200_E_INVALID, "null ensemble");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PB200_OK;
+}
+
+int pb200_ensemble_last_step_ms(pb200_ensemble_t* e, float* ms) {
+    if (!e || !ms) return set_error(PB200_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (e->timing_pending) {
+        CUDA_TRY(cudaEventSynchronize(e->ev1));
+        CUDA_TRY(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+        e->timing_pending = false;
+    }
+    *ms = e->last_ms;
+    return PB200_OK;
+}
+
+uint64_t pb200_ensemble_launch_count(const pb200_ensemble_t* e) { return e ? e->launches : 0; }
+
+int pb200_ensemble_status(pb200_ensemble_t* e, int32_t* status, uint32_t* warnings, uint64_t* iteration_of_event) {
+    if (!e) return set_error(PB200_E_INVALID, "null ensemble");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (status) CUDA_TRY(cudaMemcpy(status, e->P.status, e->n_sys * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (warnings) CUDA_TRY(cudaMemcpy(warnings, e->P.warnings, e->n_sys * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (iteration_of_event) CUDA_TRY(cudaMemcpy(iteration_of_event, e->P.event_iteration, e->n_sys * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return PB200_OK;
+}
+
+static int copy_state(pb200_ensemble* e, const pb200_state_view_t* v, bool to_host) {
+    const size_t ns = e->n_sys, nb = (size_t)e->n_bodies;
+    struct Item { double* host; double* dev; size_t count; };
+    Item items[] = {
+        {v->position, e->P.pos, 3 * nb * ns}, {v->velocity, e->P.vel, 3 * nb * ns}, {v->acceleration, e->P.acc, 3 * nb * ns},
+        {v->angular_momentum, e->P.L, 3 * nb * ns}, {v->spin, e->P.spin, 3 * nb * ns}, {v->velocity_errors, e->P.verr, 3 * nb * ns},
+        {v->angular_momentum_errors, e->P.lerr, 3 * nb * ns}, {v->radius, e->P.radius, nb * ns},
+        {v->radius_of_gyration_2, e->P.rg2, nb * ns}, {v->moment_of_inertia, e->P.moi, nb * ns}, {v->current_time, e->P.t, ns},
+    };
+    for (const Item& it : items) {
+        if (!it.host) continue;
+        cudaError_t err = to_host ? cudaMemcpyAsync(it.host, it.dev, it.count * sizeof(double), cudaMemcpyDeviceToHost, e->stream)
+                                  : cudaMemcpyAsync(it.dev, it.host, it.count * sizeof(double), cudaMemcpyHostToDevice, e->stream);
+        if (err != cudaSuccess) return set_error(PB200_E_CUDA, std::string("state copy: ") + cudaGetErrorString(err));
+    }
+    return PB200_OK;
+}
+
+int pb200_ensemble_download(pb200_ensemble_t* e, const pb200_state_view_t* dst) {
+    if (!e || !dst) return set_error(PB200_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc = copy_state(e, dst, true);
+    if (rc != PB200_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PB200_OK;
+}
+
+int pb200_ensemble_upload(pb200_ensemble_t* e, const pb200_state_view_t* src) {
+    if (!e || !src) return set_error(PB200_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc = copy_state(e, src, false);
+    if (rc != PB200_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PB200_OK;
+}
+
+int pb200_ensemble_run_host(pb200_ensemble_t* e, const pb200_state_view_t* io, uint64_t n_steps) {
+    if (!e || !io) return set_error(PB200_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    int rc = copy_state(e, io, false);
+    if (rc != PB200_OK) return rc;
+    rc = pb200_ensemble_step(e, n_steps);
+    if (rc != PB200_OK) return rc;
+    rc = copy_state(e, io, true);
+    if (rc != PB200_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PB200_OK;
+}
+
+int pb200_ensemble_get_case(pb200_ensemble_t* e, size_t s, pb200_case_t* out) {
+    if (!e || !out || s >= e->n_sys) return set_error(PB200_E_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    *out = e->cases.size() == 1 ? e->cases[0] : e->cases[s];
+    out->time_limit = e->P.time_limit;
+    out->historic_snapshot_period = e->P.hist_period;
+    out->recovery_snapshot_period = e->recovery_snapshot_period;
+    const size_t ns = e->n_sys, nb = (size_t)e->n_bodies;
+    auto get = [&](const void* dev, size_t index, void* dst, size_t bytes) -> cudaError_t {
+        return cudaMemcpy(dst, (const char*)dev + index * bytes, bytes, cudaMemcpyDeviceToHost);
+    };
+    for (size_t b = 0; b < nb; b++) {
+        pb200_body_t& B = out->bodies[b];
+        for (int c = 0; c < 3; c++) {
+            size_t i = ((size_t)c * nb + b) * ns + s;
+            CUDA_TRY(get(e->P.pos, i, &B.inertial_position[c], 8)); CUDA_TRY(get(e->P.vel, i, &B.inertial_velocity[c], 8));
+            CUDA_TRY(get(e->P.acc, i, &B.inertial_acceleration[c], 8)); CUDA_TRY(get(e->P.L, i, &B.angular_momentum[c], 8));
+            CUDA_TRY(get(e->P.spin, i, &B.spin[c], 8));
+            CUDA_TRY(get(e->P.verr, i, &out->inertial_velocity_errors[b][c], 8));
+            CUDA_TRY(get(e->P.lerr, i, &out->particle_angular_momentum_errors[b][c], 8));
+        }
+        size_t i = b * ns + s;
+        CUDA_TRY(get(e->P.radius, i, &B.radius, 8)); CUDA_TRY(get(e->P.rg2, i, &B.radius_of_gyration_2, 8));
+        CUDA_TRY(get(e->P.moi, i, &B.moment_of_inertia, 8));
+    }
+    for (size_t i = 0; i < nb * nb; i++) CUDA_TRY(get(e->d_roche, i * ns + s, &out->roche_radiuses[i], 8));
+    unsigned long long u;
+    CUDA_TRY(get(e->P.t, s, &out->current_time, 8));
+    CUDA_TRY(get(e->P.last_hist, s, &out->last_historic_snapshot_time, 8));
+    CUDA_TRY(get(e->P.iteration, s, &u, 8)); out->current_iteration = u;
+    CUDA_TRY(get(e->P.n_hist, s, &u, 8)); out->n_historic_snapshots = u;
+    CUDA_TRY(get(e->P.tswarn, s, &u, 8)); out->timestep_warning = u;
+    return PB200_OK;
+}
+
+size_t pb200_ensemble_history_pending(pb200_ensemble_t* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    // all live systems snapshot in lock step; take the maximum
+    std::vector<int> hc(e->n_sys);
+    if (cudaMemcpy(hc.data(), e->P.hist_count, e->n_sys * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    int mx = 0;
+    for (int v : hc) if (v > mx) mx = v;
+    return (size_t)mx;
+}
+
+int pb200_ensemble_history_drain(pb200_ensemble_t* e, void* dst, size_t dst_bytes) {
+    if (!e) return set_error(PB200_E_INVALID, "null ensemble");
+    CUDA_TRY(cudaSetDevice(e->device));
+    size_t n_snap = pb200_ensemble_history_pending(e);
+    if (n_snap == 0) return PB200_OK;
+    const size_t nrec = e->n_sys * n_snap * (size_t)e->n_bodies;
+    const size_t bytes = nrec * PB200_HISTORIC_RECORD_BYTES;
+    if (!dst || dst_bytes < bytes) return set_error(PB200_E_INVALID, "history destination too small");
+    if (e->records_capacity < bytes) {
+        int rc = dev_alloc(e, &e->d_records, bytes / 4 + 1);
+        if (rc != PB200_OK) return rc;
+        e->records_capacity = bytes;
+    }
+    pack_history_kernel<<<(unsigned)((nrec + 127) / 128), 128, 0, e->stream>>>(e->P, (int)n_snap, e->P.dt, e->d_records);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(dst, e->d_records, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaMemsetAsync(e->P.hist_count, 0, e->n_sys * sizeof(int), e->stream));
+    e->hist_pending_host = 0;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PB200_OK;
+}
+
+int pb200_ensemble_summary(pb200_ensemble_t* e, double* energy, double* angular_momentum) {
+    if (!e) return set_error(PB200_E_INVALID, "null ensemble");
+    CUDA_TRY(cudaSetDevice(e->device));
+    summary_kernel<<<(unsigned)((e->n_sys + 127) / 128), 128, 0, e->stream>>>(e->P, e->d_energy, e->d_angmom);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (energy) CUDA_TRY(cudaMemcpyAsync(energy, e->d_energy, e->n_sys * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (angular_momentum) CUDA_TRY(cudaMemcpyAsync(angular_momentum, e->d_angmom, e->n_sys * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return PB200_OK;
+}
+
+int pb200_measure_fp64_peak(int device, double ms_target, double* flops_per_s) {
+    if (!flops_per_s) return set_error(PB200_E_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8;
+    double* out = nullptr;
+    CUDA_TRY(cudaMalloc(&out, (size_t)threads * blocks * sizeof(double)));
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreate(&a)); CUDA_TRY(cudaEventCreate(&b));
+    int iters = 256;
+    double best = 0.;
+    float ms = 0.f;
+    for (int rep = 0; rep < 12; rep++) {
+        CUDA_TRY(cudaEventRecord(a));
+        dfma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+        CUDA_TRY(cudaEventRecord(b));
+        CUDA_TRY(cudaEventSynchronize(b));
+        CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+        double flops = 2.0 * 8 * 16 * (double)iters * threads * blocks;
+        double rate = flops / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+        if (ms < ms_target && iters < (1 << 24)) iters *= 2;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    *flops_per_s = best;
+    return PB200_OK;
+}
+
+}  // extern "C"

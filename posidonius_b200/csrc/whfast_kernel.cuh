@@ -1,0 +1,443 @@
+// whfast_kernel.cuh — the ensemble WHFast step for sm_100a (fp64 vector pipe, no tensor cores).
+//
+// Mapping: one body per lane, one system per aligned group of W lanes (W = 2,4,8,16), 32/W systems
+// per warp. Dynamic state lives in registers for all n_steps of a launch; the host body's
+// quantities reach the other lanes with warp shuffles, the pairwise sums onto the host are
+// xor-butterfly reductions inside the group. HBM is touched only when a launch starts and ends
+// (coalesced SoA [field][body][system]) and when a historic snapshot falls due.
+//
+// Reference path restated here (file:line under /root/reference/src):
+//   WHFast::iterate                          integrator/whfast.rs:235-305
+//   integrate_velocity_dependent_forces      integrator/whfast.rs:322-466
+//   kepler_individual_step / stumpff         integrator/whfast.rs:676-876
+//   coordinate transforms, jump, kick        integrator/whfast.rs:495-672, 881-1155
+//   gravity_calculate_acceleration           particles/universe.rs:198-303
+//   inertial_to_heliocentric                 particles/universe.rs:318-351
+//   calculate_additional_effects             particles/universe.rs:428-614
+//   constant-time-lag tides                  effects/tides/{common,constant_time_lag}.rs
+//   oblate-spheroid flattening               effects/rotational_flattening/{common,oblate_spheroid}.rs
+//   GR Kidder1995/Anderson1975/Newhall1983   effects/general_relativity.rs:177-895
+//   evolution interpolation                  effects/evolution.rs:449-567, tools.rs:840-907
+//
+// Arithmetic: the WHFast core (transforms, Kepler drift, jump, kick, gravity, compensated v/L updates) is
+// strict IEEE in the reference's association order (strict.cuh) and reproduces the CPU oracle's roundings;
+// the perturbation forces use FMA contraction, reciprocal reuse, hoisted powers and butterfly reductions.
+// Parity is asserted against the CPU oracle at 1e-10 relative after 10^4 steps.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/posidonius_b200.h"
+#include "strict.cuh"
+
+namespace pb200 {
+
+// ---- constants (constants.rs), same expressions as the reference
+#define PB_HOUR 3600.
+#define PB_DAY (24. * PB_HOUR)
+#define PB_M_SUN 1.9818e30
+#define PB_G_SI 6.67428e-11
+#define PB_AU 1.49597870700e11
+__device__ constexpr double kG = PB_G_SI / (PB_AU * PB_AU * PB_AU) * PB_M_SUN * (PB_DAY * PB_DAY);
+__device__ constexpr double kK2 = kG;
+__device__ constexpr double kC = (2.99792458e8 / PB_AU) * PB_DAY;
+__device__ constexpr double kC2 = kC * kC;
+__device__ constexpr double kInvC2 = 1.0 / kC2;
+__device__ constexpr double kEps2 = 2.2204460492503131e-16 * 2.2204460492503131e-16;
+__device__ constexpr double kMaxDistance2 = 100. * 100.;
+__device__ constexpr double kPi = 3.14159265358979323846264338327950288;
+
+enum : int { FLAG_TIDES = 1, FLAG_FLAT = 2, FLAG_GR = 4, FLAG_EVO = 8 };
+
+// Device-side description of one evolution table (effects/evolution.rs:19-28).
+struct DevTable {
+    const double* time;
+    const double* radius;
+    const double* rg2;
+    int n_rows;
+    int interp_radius;  // 1 unless NonEvolving
+    int interp_rg2;     // Baraffe2015 / Leconte2011 / LeconteChabrier2013
+};
+
+// Kernel parameters: everything uniform across the ensemble + SoA pointers.
+struct KParams {
+    int n_sys, n_bodies, W, shift;
+    int host;      // index of the most massive body = host of every enabled effect
+    int flags;     // FLAG_*
+    int spin_on;   // integrate_spin (whfast.rs:270-275)
+    double dt, half_dt, time_limit, hist_period;
+    // per-body roles, uniform across systems (bit b set = body b is OrbitingBody for the effect)
+    uint32_t tides_orbiting, flat_orbiting, gr_orbiting, gr_enabled /* != Disabled */;
+    int tides_host_central, flat_host_central;
+    int evo_table[PB200_MAX_PARTICLES];  // -1 = NonEvolving
+    DevTable tables[PB200_MAX_PARTICLES];
+    // dynamic state, [c][b][s]
+    double *pos, *vel, *acc, *L, *spin, *verr, *lerr;
+    // per body per system, [b][s]
+    double *radius, *rg2, *moi;
+    const double *mass, *mass_g, *sigma, *k2t, *k2f;
+    const double* roche;  // [i][j][s], i,j < n_bodies
+    // per system
+    double *t, *last_hist;
+    unsigned long long *iteration, *n_hist, *event_iteration, *tswarn;
+    int* status;
+    unsigned int* warnings;
+    // historic snapshot planes: hist[slot][field(17)][b][s] doubles; slot = snapshots since launch start
+    double* hist;
+    int hist_capacity;          // slots available
+    int* hist_count;            // per system: slots used
+    // stale tidal internals for denergy_dt (tides/common.rs:263-279 reads the last evaluation), [k(13)][b][s]
+    double* tide_scratch;
+};
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
+__device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(FULL, v, m); }
+
+// all-reduce (sum) inside the aligned group of W lanes
+__device__ __forceinline__ double group_sum(double v, int W) {
+    for (int off = W >> 1; off > 0; off >>= 1) v += shfl_xor(v, off);
+    return v;
+}
+
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(double s, V3 a) { return v3(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ V3 shfl3(V3 a, int src) { return v3(shfl(a.x, src), shfl(a.y, src), shfl(a.z, src)); }
+__device__ __forceinline__ V3 group_sum3(V3 a, int W) { return v3(group_sum(a.x, W), group_sum(a.y, W), group_sum(a.z, W)); }
+__device__ __forceinline__ V3 sel(bool c, V3 a, V3 b) { return v3(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
+
+// ---------------------------------------------------------------------------------------------
+// Stumpff functions c0..c3 (whfast.rs:844-876) and Stiefel G-functions (whfast.rs:835-842), strict arithmetic
+__device__ __forceinline__ void stumpff_cs3(sd z, sd& c0, sd& c1, sd& c2, sd& c3) {
+    int n = 0;
+    while (fabs(z.v) > 0.1) { z = z / sd(4.); n++; }
+    sd c_odd = sd(1. / 6227020800.);   // 1/13!
+    sd c_even = sd(1. / 479001600.);   // 1/12!
+    c_odd = sd(1. / 39916800.) - z * c_odd;   c_even = sd(1. / 3628800.) - z * c_even;  // 11!, 10!
+    c_odd = sd(1. / 362880.) - z * c_odd;     c_even = sd(1. / 40320.) - z * c_even;    // 9!, 8!
+    c_odd = sd(1. / 5040.) - z * c_odd;       c_even = sd(1. / 720.) - z * c_even;      // 7!, 6!
+    c_odd = sd(1. / 120.) - z * c_odd;        c_even = sd(1. / 24.) - z * c_even;       // 5!, 4!
+    c_odd = sd(1. / 6.) - z * c_odd;          c_even = sd(1. / 2.) - z * c_even;        // 3!, 2!
+    c3 = c_odd; c2 = c_even;
+    c1 = sd(1.) - z * c_odd;
+    c0 = sd(1.) - z * c_even;
+    for (; n > 0; n--) {
+        c3 = (c2 + c0 * c3) * sd(0.25);
+        c2 = c1 * c1 * sd(0.5);
+        c1 = c0 * c1;
+        c0 = sd(2.) * c0 * c0 - sd(1.);
+    }
+}
+__device__ __forceinline__ void stiefel_gs3(sd beta, sd x, sd& g0, sd& g1, sd& g2, sd& g3) {
+    sd x2 = x * x;
+    stumpff_cs3(beta * x2, g0, g1, g2, g3);
+    g1 = g1 * x; g2 = g2 * x2; g3 = g3 * (x2 * x);
+}
+
+// Universal-variable Kepler drift of one body (whfast.rs:676-833), strict arithmetic in the reference's
+// association order. `work` lanes only; the warp iterates until every working lane has met the reference's
+// exit test (exact repetition of x).
+__device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu, sd dt, bool& tswarn, unsigned int& warnings) {
+    const S3 p1 = pos, v1 = vel;
+    const sd r0 = ssqrt(p1.x * p1.x + p1.y * p1.y + p1.z * p1.z);
+    const sd r0i = sd(1.) / r0;
+    const sd v2 = v1.x * v1.x + v1.y * v1.y + v1.z * v1.z;
+    const sd beta = sd(2.) * mu * r0i - v2;
+    const sd eta0 = p1.x * v1.x + p1.y * v1.y + p1.z * v1.z;
+    const sd zeta0 = mu - beta * r0;
+    sd x, g0, g1, g2, g3;
+    sd invperiod = sd(0.), x_per_period = sd(0.);
+    const bool elliptic = beta.v > 0.;
+    const sd two_pi = sd(2. * kPi);
+    if (elliptic) {
+        sd sqrt_beta = ssqrt(beta);
+        invperiod = sqrt_beta * beta / (two_pi * mu);
+        x_per_period = two_pi / sqrt_beta;
+        if (work && fabs(dt.v) * invperiod.v > 1. && !tswarn) { tswarn = true; warnings |= PB200_WARN_TIMESTEP_GT_PERIOD; }
+        sd dtr0i = dt * r0i;
+        x = dtr0i * (sd(1.) - dtr0i * eta0 * sd(0.5) * r0i);
+    } else {
+        x = sd(0.);
+    }
+    bool converged = false;
+    sd old_x = x;
+    stiefel_gs3(beta, x, g0, g1, g2, g3);
+    sd e1 = eta0 * g1 + zeta0 * g2;
+    sd ri = sd(1.) / (r0 + e1);
+    x = ri * (x * e1 - eta0 * g2 - zeta0 * g3 + dt);
+    const bool quartic = work && elliptic && fabs((x - old_x).v) > (sd(0.01) * x_per_period).v;
+    if (__any_sync(FULL, quartic)) {
+        // Laguerre-like quartic solver (whfast.rs:732-755), rare: large steps only.
+        if (quartic) {
+            x = beta * dt / mu;
+            double prev_x[64];
+            for (int k = 0; k < 64; k++) prev_x[k] = 0.;
+            for (int n_lag = 1; n_lag < 64; n_lag++) {
+                stiefel_gs3(beta, x, g0, g1, g2, g3);
+                sd f = r0 * x + eta0 * g2 + zeta0 * g3 - dt;
+                sd fp = r0 + eta0 * g1 + zeta0 * g2;
+                sd fpp = eta0 * g0 + zeta0 * g1;
+                sd denom = fp + ssqrt(sabs(sd(16.) * fp * fp - sd(20.) * f * fpp));
+                x = (x * denom - sd(5.) * f) / denom;
+                bool hit = false;
+                for (int k = 1; k < n_lag; k++) if (x.v == prev_x[k]) hit = true;
+                if (hit) { converged = true; break; }
+                prev_x[n_lag] = x.v;
+            }
+            ri = sd(1.) / (r0 + (eta0 * g1 + zeta0 * g2));
+        }
+    }
+    {
+        // Newton's method (whfast.rs:757-773): at most 31 passes, exit on x == old_x || x == old_x2.
+        bool active = work && !quartic;
+#pragma unroll 1
+        for (int k = 1; k < 32; k++) {
+            if (!__any_sync(FULL, active)) break;
+            sd h0, h1, h2, h3;
+            stiefel_gs3(beta, x, h0, h1, h2, h3);
+            sd e = eta0 * h1 + zeta0 * h2;
+            sd rin = sd(1.) / (r0 + e);
+            sd xn = rin * (x * e - eta0 * h2 - zeta0 * h3 + dt);
+            if (active) {
+                sd old_x2 = old_x;
+                old_x = x; x = xn; ri = rin; g0 = h0; g1 = h1; g2 = h2; g3 = h3;
+                if (x.v == old_x.v || x.v == old_x2.v) { converged = true; active = false; }
+            }
+        }
+    }
+    const bool bisect = work && !converged;
+    if (__any_sync(FULL, bisect)) {
+        if (bisect) {
+            sd x_min, x_max;
+            if (elliptic) {
+                x_min = x_per_period * sd(floor((dt * invperiod).v));
+                x_max = x_min + x_per_period;
+            } else {
+                sd h2 = r0 * r0 * v2 - eta0 * eta0;
+                sd q = h2 / mu / (sd(1.) + ssqrt(sd(1.) - h2 * beta / (mu * mu)));
+                sd vq = ssqrt(h2) / q;
+                x_min = sd(1.) / (vq + r0 / dt);
+                x_max = dt / q;
+            }
+            x = (x_max + x_min) / sd(2.);
+            for (int guard = 0; guard < 200; guard++) {   // the reference's `loop {}` never ends on NaN input
+                stiefel_gs3(beta, x, g0, g1, g2, g3);
+                sd s = r0 * x + eta0 * g2 + zeta0 * g3 - dt;
+                if (s.v >= 0.) x_max = x; else x_min = x;
+                x = (x_max + x_min) / sd(2.);
+                if ((sabs(x_max - x_min) / x_max).v <= 1e-15) break;
+            }
+            ri = sd(1.) / (r0 + (eta0 * g1 + zeta0 * g2));
+        }
+    }
+    if (isnan(ri.v)) { ri = sd(0.); g1 = sd(0.); g2 = sd(0.); g3 = sd(0.); }
+    sd f = -mu * g2 * r0i;
+    sd g = dt - mu * g3;
+    sd fd = -mu * g1 * r0i * ri;
+    sd gd = -mu * g2 * ri;
+    if (work) {
+        pos.x = pos.x + (f * p1.x + g * v1.x); pos.y = pos.y + (f * p1.y + g * v1.y); pos.z = pos.z + (f * p1.z + g * v1.z);
+        vel.x = vel.x + (fd * p1.x + gd * v1.x); vel.y = vel.y + (fd * p1.y + gd * v1.y); vel.z = vel.z + (fd * p1.z + gd * v1.z);
+    }
+}
+
+// upper-bound search + linear interpolation (tools.rs:840-907): first row with time > t
+__device__ __forceinline__ int table_upper(const double* __restrict__ time, int n, double t) {
+    int lo = 0, hi = n;  // first index with time[i] > t, n if none
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(time + mid) > t) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ double table_interp(const double* __restrict__ time, const double* __restrict__ y, int n, int i,
+                                               double t) {
+    if (i == 0) return __ldg(y);
+    if (i >= n) return __ldg(y + n - 1);
+    // strict, in the order of tools.rs:853-855
+    sd xl = sd(__ldg(time + i - 1)), xr = sd(__ldg(time + i));
+    sd pct = (sd(t) - xl) / (xr - xl);
+    return (sd(__ldg(y + i - 1)) * (sd(1.) - pct) + sd(__ldg(y + i)) * pct).v;
+}
+
+// Per-lane register state.
+struct Lane {
+    S3 r, v;            // inertial position / velocity (strict arithmetic only)
+    V3 L, s;            // angular momentum, spin (of the previous evaluation)
+    V3 ev, el;          // Kahan residuals (whfast.rs:117-119)
+    double m, mg, R, rg2, I;
+    double sigma, k2t, k2f;
+};
+__device__ __forceinline__ V3 plain(S3 a) { return v3(a.x.v, a.y.v, a.z.v); }
+__device__ __forceinline__ S3 strict(V3 a) { return s3(sd(a.x), sd(a.y), sd(a.z)); }
+__device__ __forceinline__ S3 shfl3(S3 a, int src) { return s3(sd(shfl(a.x.v, src)), sd(shfl(a.y.v, src)), sd(shfl(a.z.v, src))); }
+__device__ __forceinline__ sd shfl(sd a, int src) { return sd(shfl(a.v, src)); }
+
+// per-step constants derived from masses/radii (recomputed when the radius evolves)
+struct Consts {
+    double invI;
+    double As, Ap, Bk;   // tides: 4.5 m^2 R*^10 sigma*, 4.5 M^2 R^10 sigma, 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2)
+    double Ks, Kp;       // flattening: m k2f* R*^5, M k2f R^5
+    double M, Mg, Ih;    // host mass, mass_g, moment of inertia
+};
+
+__device__ __forceinline__ double pow5(double x) { double x2 = x * x; return x2 * x2 * x; }
+
+__device__ __forceinline__ void make_consts(const Lane& q, int hl, Consts& c) {
+    c.invI = 1. / q.I;
+    c.M = shfl(q.m, hl); c.Mg = shfl(q.mg, hl); c.Ih = shfl(q.I, hl);
+    double Rh5 = pow5(shfl(q.R, hl));
+    double R5 = pow5(q.R);
+    double sig_h = shfl(q.sigma, hl), k2t_h = shfl(q.k2t, hl), k2f_h = shfl(q.k2f, hl);
+    double m2 = q.m * q.m, M2 = c.M * c.M;
+    c.As = 4.5 * m2 * (Rh5 * Rh5) * sig_h;
+    c.Ap = 4.5 * M2 * (R5 * R5) * q.sigma;
+    c.Bk = 3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * q.k2t);
+    c.Ks = q.m * k2f_h * Rh5;
+    c.Kp = c.M * q.k2f * R5;
+}
+
+struct Roles {
+    bool valid;     // lane belongs to a live system slot and b < n_bodies
+    bool host;
+    bool planet;    // valid && !host
+    bool t_on, f_on, g_on;  // OrbitingBody for tides / flattening / GR
+};
+
+// ---------------------------------------------------------------------------------------------
+// Universe::calculate_additional_effects for the lane's body at (hr, hv) with the current L
+// (universe.rs:428-614). Returns the inertial additional acceleration and dL/dt of THIS body;
+// host-lane values are the group reductions.
+template <int GR>
+__device__ __forceinline__ void additional_effects(const KParams& P, const Roles& ro, int hl, Lane& q, const Consts& c, V3 hr,
+                                                   double inv_d, V3 hv, V3 r_host_inertial, V3 acc_newton, V3& a_out,
+                                                   V3& dl_out, double* tide_save) {
+    const int W = P.W;
+    // Q3: r.omega uses the spins of the previous evaluation (universe.rs:429-430)
+    V3 s_host_prev = shfl3(q.s, hl);
+    double rs_s = dot(hr, s_host_prev), rs_p = dot(hr, q.s);
+    // calculate_spin (particles/common.rs:3-15)
+    q.s = c.invI * q.L;
+    double w2 = dot(q.s, q.s);
+    V3 sh = shfl3(q.s, hl);
+    double wh2 = shfl(w2, hl);
+    double d = 1. / inv_d;  // only used multiplicatively below
+    double inv_d2 = inv_d * inv_d;
+    double radvel = dot(hr, hv) * inv_d;
+    V3 rxv = cross(hr, hv);
+    V3 a_p = v3(0., 0., 0.), dl_p = v3(0., 0., 0.);       // this body's own acceleration / torque
+    V3 a_h = v3(0., 0., 0.), dl_h = v3(0., 0., 0.);       // contribution to the host
+    const double inv_m = 1. / q.m, inv_M = 1. / c.M;
+    if (P.flags & FLAG_TIDES) {
+        // constant_time_lag.rs:206-332, tides/common.rs:223-345
+        double inv_d4 = inv_d2 * inv_d2;
+        double inv_d7 = inv_d4 * inv_d2 * inv_d;
+        double Fos = P.tides_host_central ? c.As * inv_d7 : 0.;
+        double Fop = c.Ap * inv_d7;
+        double Fsum = Fos + Fop;
+        // radial: conservative + dissipative (-13.5 vr/r^8 (...) = -3 vr/r (Fos + Fop))
+        double f3 = -c.Bk * inv_d7 - 2.0 * Fsum * radvel * inv_d;
+        V3 wxr_s = cross(sh, hr), wxr_p = cross(q.s, hr);
+        double k3 = f3 * inv_d, ks = Fos * inv_d, kp = Fop * inv_d;
+        V3 F = v3(k3 * hr.x + ks * (wxr_s.x - hv.x) + kp * (wxr_p.x - hv.x),
+                  k3 * hr.y + ks * (wxr_s.y - hv.y) + kp * (wxr_p.y - hv.y),
+                  k3 * hr.z + ks * (wxr_s.z - hv.z) + kp * (wxr_p.z - hv.z));
+        // torques (eqs 8-9 Bolmont+2015): N = Forth (d w - (r.w) r/d - (r x v)/d); dL/dt = -N
+        V3 Np = v3(Fop * (d * q.s.x - (rs_p * hr.x + rxv.x) * inv_d), Fop * (d * q.s.y - (rs_p * hr.y + rxv.y) * inv_d),
+                   Fop * (d * q.s.z - (rs_p * hr.z + rxv.z) * inv_d));
+        V3 Ns = v3(Fos * (d * sh.x - (rs_s * hr.x + rxv.x) * inv_d), Fos * (d * sh.y - (rs_s * hr.y + rxv.y) * inv_d),
+                   Fos * (d * sh.z - (rs_s * hr.z + rxv.z) * inv_d));
+        if (ro.t_on) {
+            a_p = a_p + inv_m * F;
+            a_h = a_h - inv_M * F;
+            dl_p = dl_p - Np;
+            dl_h = dl_h - Ns;
+        }
+        if (tide_save) {
+            // internals that calculate_denergy_dt (tides/common.rs:263-279) will read at the next snapshot
+            tide_save[0] = hr.x; tide_save[1] = hr.y; tide_save[2] = hr.z;
+            tide_save[3] = hv.x; tide_save[4] = hv.y; tide_save[5] = hv.z;
+            tide_save[6] = d; tide_save[7] = radvel; tide_save[8] = Fop;
+            tide_save[9] = -3.0 * Fop * radvel * inv_d;  // dissipative radial part with the star as a point mass
+            tide_save[10] = -Np.x; tide_save[11] = -Np.y; tide_save[12] = -Np.z;
+        }
+    }
+    if (P.flags & FLAG_FLAT) {
+        // oblate_spheroid.rs:12-97, rotational_flattening/common.rs:165-237
+        double inv_d5 = inv_d2 * inv_d2 * inv_d;
+        double inv_d7 = inv_d5 * inv_d2;
+        double Ks = P.flat_host_central ? c.Ks : 0.;
+        double Fos = -Ks * rs_s * inv_d5;
+        double Fop = -c.Kp * rs_p * inv_d5;
+        double Frad = -0.5 * inv_d5 * (Ks * wh2 + c.Kp * w2) + 2.5 * inv_d7 * (Ks * rs_s * rs_s + c.Kp * rs_p * rs_p);
+        V3 F = v3(Frad * hr.x + Fop * q.s.x + Fos * sh.x, Frad * hr.y + Fop * q.s.y + Fos * sh.y, Frad * hr.z + Fop * q.s.z + Fos * sh.z);
+        V3 Np = Fop * cross(hr, q.s);
+        V3 Ns = Fos * cross(hr, sh);
+        if (ro.f_on) {
+            a_p = a_p + inv_m * F;
+            a_h = a_h - inv_M * F;
+            dl_p = dl_p - Np;
+            dl_h = dl_h - Ns;
+        }
+    }
+    if (GR == PB200_GR_KIDDER1995) {
+        // general_relativity.rs:177-456
+        double v2 = dot(hv, hv);
+        double mgs = c.Mg + q.mg;
+        double f = c.Mg * q.mg / (mgs * mgs);
+        double A = mgs * inv_d2 * kInvC2;
+        double u = mgs * inv_d;
+        double rv2 = radvel * radvel;
+        // 1PN; the orthoradial term divides by |v| and multiplies by |v|: cancelled
+        double rad = -A * ((1.0 + 3.0 * f) * v2 - 2.0 * (2.0 + f) * u - 1.5 * f * rv2);
+        double orth = A * 2.0 * (2.0 - f) * radvel;
+        // 2PN (Kidder 1995 eq. 2.2d)
+        double f2 = f * f;
+        rad += -A * (0.75 * (12.0 + 29.0 * f) * (u * u) + f * (3.0 - 4.0 * f) * (v2 * v2) + 1.875 * f * (1.0 - 3.0 * f) * (rv2 * rv2)
+                     - 1.5 * f * (3.0 - 4.0 * f) * rv2 * v2 - 0.5 * f * (13.0 - 4.0 * f) * u * v2 - (2.0 + 25.0 * f + 2.0 * f2) * u * rv2);
+        orth += 0.5 * A * radvel * (f * (15.0 + 4.0 * f) * v2 - (4.0 + 41.0 * f + 8.0 * f2) * u - 3.0 * f * (3.0 + 2.0 * f) * rv2);
+        double kr = rad * inv_d;
+        V3 a = v3(kr * hr.x + orth * hv.x, kr * hr.y + orth * hv.y, kr * hr.z + orth * hv.z);
+        // 1.5PN spin-orbit (:300-456); component-wise products exactly as the reference writes them
+        V3 Ls = c.Ih * sh, Lp = q.I * q.s;
+        V3 nn = inv_d * hr;
+        double md = c.M - q.m;  // mass_factor * star_planet_mass
+        V3 msf = v3(md * (Lp.x * inv_m - Ls.x * inv_M), md * (Lp.y * inv_m - Ls.y * inv_M), md * (Lp.z * inv_m - Ls.z * inv_M));
+        V3 S = Ls + Lp;
+        V3 nxv = cross(nn, hv);
+        V3 e1 = v3(6. * nn.x * (nxv.x * (2. * S.x + msf.x)), 6. * nn.y * (nxv.y * (2. * S.y + msf.y)), 6. * nn.z * (nxv.z * (2. * S.z + msf.z)));
+        V3 e7 = v3(7. * S.x + 3. * msf.x, 7. * S.y + 3. * msf.y, 7. * S.z + 3. * msf.z);
+        V3 e2 = cross(hv, e7);
+        V3 e3s = v3(3. * S.x + msf.x, 3. * S.y + msf.y, 3. * S.z + msf.z);
+        V3 e3 = (3. * radvel) * cross(nn, e3s);
+        const double fa = kG * kInvC2;
+        a = a + fa * (e1 - e2 + e3);
+        // Kidder 1995 eqs 2.4a, 2.4b
+        double mu = (c.M * q.m) / (c.M + q.m);
+        V3 Lo = mu * rxv;
+        double fm_s = 2. + 1.5 * q.m * inv_M, fm_p = 2. + 1.5 * c.M * inv_m;
+        V3 LpxLs = cross(Lp, Ls);
+        V3 ds = fm_s * cross(Lo, Ls) - LpxLs + (3. * dot(nn, Lp)) * cross(nn, Ls);
+        V3 dp = fm_p * cross(Lo, Lp) + LpxLs + (3. * dot(nn, Ls)) * cross(nn, Lp);
+        if (ro.g_on) {
+            a_p = a_p + a;
+            a_h = a_h - (q.m * inv_M) * a;
+            dl_p = dl_p + fa * dp;
+            dl_h = dl_h + fa * ds;
+        }
+    }
+    // zero out lanes that are not orbiting bodies, then reduce onto the host
+    if (!ro.planet) { a_h = v3(0., 0., 0.); dl_h = v3(0., 0., 0.); a_p = v3(0., 0., 0.); dl_p = v3(0., 0., 0.); }
+    a_h = group_sum3(a_h, W);
+    dl_h = group_sum3(dl_h, W);
+    a_out = ro.host ? a_h : a_p;
+    dl_out = ro.host ? dl_h : dl_p;
+    (void)r_host_inertial; (void)acc_newton;
+}
+
+}  // namespace pb200

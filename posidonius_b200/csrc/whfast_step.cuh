@@ -1,0 +1,515 @@
+// whfast_step.cuh — the persistent-state step kernel: WHFast::iterate (integrator/whfast.rs:235-305) for
+// n_steps steps of every system of the ensemble, state in registers (see whfast_kernel.cuh for the mapping).
+//
+// The core below is a strict-arithmetic transcription (strict.cuh) of the reference's operation order; sums over
+// bodies that the reference accumulates serially are accumulated in the same order by walking the group with
+// shuffles (every lane carries the running sum, so all lanes hold bit-identical copies).
+#pragma once
+#include "gr_variants.cuh"
+
+namespace pb200 {
+
+#define PB_BLOCK 128
+#define PB_HIST_FIELDS 16  // time, pos3, spin3, vel3, mass, radius, rg2, love_number, sigma, denergy_dt
+#define PB_TIDE_SCRATCH 13
+
+struct SysState {
+    double t, last_hist;
+    unsigned int steps_done, n_hist_new;   // relative to the launch start
+    unsigned int event_step;               // steps_done when the status changed
+    int status;
+    unsigned int warnings;
+    int hist_count;
+    bool tswarn;
+};
+
+__device__ __forceinline__ void store_lane(const KParams& P, const Roles& ro, size_t sys, int b, const Lane& q, V3 acc,
+                                           const SysState& st) {
+    if (!ro.valid) return;
+    const size_t ns = (size_t)P.n_sys;
+    const size_t i = (size_t)b * ns + sys;
+    const size_t cs = (size_t)P.n_bodies * ns;
+    P.pos[i] = q.r.x.v; P.pos[i + cs] = q.r.y.v; P.pos[i + 2 * cs] = q.r.z.v;
+    P.vel[i] = q.v.x.v; P.vel[i + cs] = q.v.y.v; P.vel[i + 2 * cs] = q.v.z.v;
+    P.acc[i] = acc.x; P.acc[i + cs] = acc.y; P.acc[i + 2 * cs] = acc.z;
+    P.L[i] = q.L.x; P.L[i + cs] = q.L.y; P.L[i + 2 * cs] = q.L.z;
+    P.spin[i] = q.s.x; P.spin[i + cs] = q.s.y; P.spin[i + 2 * cs] = q.s.z;
+    P.verr[i] = q.ev.x; P.verr[i + cs] = q.ev.y; P.verr[i + 2 * cs] = q.ev.z;
+    P.lerr[i] = q.el.x; P.lerr[i + cs] = q.el.y; P.lerr[i + 2 * cs] = q.el.z;
+    P.radius[i] = q.R; P.rg2[i] = q.rg2; P.moi[i] = q.I;
+    if (b == 0) {
+        P.t[sys] = st.t; P.last_hist[sys] = st.last_hist;
+        unsigned long long it0 = P.iteration[sys];
+        P.iteration[sys] = it0 + st.steps_done;
+        P.n_hist[sys] += st.n_hist_new;
+        if (st.status != PB200_STATUS_OK) P.event_iteration[sys] = it0 + st.event_step;
+        P.tswarn[sys] = st.tswarn ? 1ull : 0ull;
+        P.status[sys] = st.status; P.warnings[sys] = st.warnings; P.hist_count[sys] = st.hist_count;
+    }
+}
+
+// effects/evolution.rs:516-546 for this lane's body (radius, radius of gyration -> moment of inertia)
+__device__ __forceinline__ void evolve_lane(const KParams& P, const Roles& ro, int b, double t, Lane& q) {
+    if (!ro.valid) return;
+    int ti = P.evo_table[b];
+    if (ti < 0) return;
+    const DevTable& T = P.tables[ti];
+    int i = table_upper(T.time, T.n_rows, t);
+    double nr = T.interp_radius ? table_interp(T.time, T.radius, T.n_rows, i, t) : q.R;
+    double ng = T.interp_rg2 ? table_interp(T.time, T.rg2, T.n_rows, i, t) : q.rg2;
+    if (nr != q.R || ng != q.rg2) {
+        q.R = nr; q.rg2 = ng;
+        q.I = (sd(q.m) * sd(q.rg2) * (sd(q.R) * sd(q.R))).v;
+    }
+}
+
+// Running sum over the NON-HOST bodies in index order, as the reference's serial loops accumulate
+// (`particles_left.chain(particles_right)`); `x` is the lane's own term. All lanes get the same bits.
+__device__ __forceinline__ S3 ordered_sum_others(S3 init, S3 x, int gb, int n, int host) {
+    S3 acc = init;
+    for (int k = 0; k < n; k++) {
+        if (k == host) continue;
+        acc = acc + shfl3(x, gb + k);
+    }
+    return acc;
+}
+__device__ __forceinline__ S3 ordered_diff_others(S3 init, S3 x, int gb, int n, int host) {
+    S3 acc = init;
+    for (int k = 0; k < n; k++) {
+        if (k == host) continue;
+        acc = acc - shfl3(x, gb + k);
+    }
+    return acc;
+}
+
+// Implicit midpoint on v and L (whfast.rs:322-466) around Universe::calculate_additional_effects.
+template <int COORD, int GR>
+__device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, int gb, int hl, int b, bool alive, Lane& q, Consts& c,
+                                         double t, bool evolution, V3 acc_newton, unsigned int& warnings, bool save_tides,
+                                         size_t sys) {
+    const int W = P.W;
+    const sd dt = sd(P.half_dt);
+    // positions do not change inside the midpoint: heliocentric position and 1/r once (universe.rs:318-351)
+    const S3 rh_s = shfl3(q.r, hl);
+    const V3 rh = plain(rh_s);
+    const V3 hr = plain(q.r - rh_s);
+    const double inv_d = rsqrt(dot(hr, hr));
+    const S3 vo = q.v;
+    const V3 Lo = q.L;
+    S3 dv = s3(sd(0.), sd(0.), sd(0.));
+    V3 dl = v3(0., 0., 0.);
+    bool done = !alive;  // group-uniform
+    bool converged = false;
+#pragma unroll 1
+    for (int it = 0; it < 10; it++) {
+        if (!__any_sync(FULL, !done)) break;
+        if (evolution && it == 0 && (P.flags & FLAG_EVO)) {
+            evolve_lane(P, ro, b, t, q);
+            make_consts(q, hl, c);
+        }
+        V3 hv = plain(q.v - shfl3(q.v, hl));
+        V3 a, dldt;
+        double scratch[PB_TIDE_SCRATCH];
+        additional_effects<GR>(P, ro, hl, q, c, hr, inv_d, hv, rh, acc_newton, a, dldt, save_tides ? scratch : nullptr);
+        if (save_tides && (P.flags & FLAG_TIDES) && ro.valid && !done) {
+            const size_t ns = (size_t)P.n_sys;
+            const size_t i = (size_t)b * ns + sys, cs = (size_t)P.n_bodies * ns;
+            for (int k = 0; k < PB_TIDE_SCRATCH; k++) P.tide_scratch[i + k * cs] = scratch[k];
+        }
+        if (GR == PB200_GR_ANDERSON1975 || GR == PB200_GR_NEWHALL1983) {
+            if (P.flags & FLAG_GR) {
+                V3 ag;
+                if (GR == PB200_GR_ANDERSON1975) gr_anderson1975(P, ro, gb, hl, b, q, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
+                else gr_newhall1983(P, ro, gb, hl, b, q, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
+                a = a + ag;
+            }
+        }
+        // final = orig + (dt * a - err)   (whfast.rs:353-378), with the previous final for the convergence test
+        S3 vf_old = vo + dv;
+        V3 Lf_old = v3(__dadd_rn(Lo.x, dl.x), __dadd_rn(Lo.y, dl.y), __dadd_rn(Lo.z, dl.z));
+        S3 ndv = s3(dt * sd(a.x) - sd(q.ev.x), dt * sd(a.y) - sd(q.ev.y), dt * sd(a.z) - sd(q.ev.z));
+        V3 ndl = v3((dt * sd(dldt.x) - sd(q.el.x)).v, (dt * sd(dldt.y) - sd(q.el.y)).v, (dt * sd(dldt.z) - sd(q.el.z)).v);
+        S3 vf = vo + ndv;
+        V3 Lf = P.spin_on ? v3(__dadd_rn(Lo.x, ndl.x), __dadd_rn(Lo.y, ndl.y), __dadd_rn(Lo.z, ndl.z)) : Lo;
+        bool conv_now = false;
+        if (it >= 2) {
+            // whfast.rs:424-451 (sums over bodies by butterfly: only the branch decision depends on them)
+            V3 ddv = plain(vf - vf_old), ddl = Lf - Lf_old, vfp = plain(vf);
+            double s_dv = ro.valid ? dot(ddv, ddv) : 0., s_fv = ro.valid ? dot(vfp, vfp) : 0.;
+            s_dv = group_sum(s_dv, W); s_fv = group_sum(s_fv, W);
+            bool okv = s_dv / s_fv < kEps2;
+            bool okl = true;
+            if (P.spin_on) {
+                double s_dl = ro.valid ? dot(ddl, ddl) : 0., s_fl = ro.valid ? dot(Lf, Lf) : 0.;
+                s_dl = group_sum(s_dl, W); s_fl = group_sum(s_fl, W);
+                okl = s_dl / s_fl < kEps2;
+            }
+            conv_now = okv && okl;
+        }
+        if (!done) {
+            dv = ndv; if (P.spin_on) dl = ndl;
+            if (conv_now) { done = true; converged = true; }
+            else {
+                // average (whfast.rs:453-466)
+                q.v = s3(sd(0.5) * (vo.x + vf.x), sd(0.5) * (vo.y + vf.y), sd(0.5) * (vo.z + vf.z));
+                if (P.spin_on) q.L = v3(__dmul_rn(0.5, __dadd_rn(Lo.x, Lf.x)), __dmul_rn(0.5, __dadd_rn(Lo.y, Lf.y)), __dmul_rn(0.5, __dadd_rn(Lo.z, Lf.z)));
+            }
+        }
+    }
+    if (alive) {
+        if (!converged) warnings |= PB200_WARN_MIDPOINT_NOT_CONVERGED;
+        q.v = vo + dv;
+        S3 e = (q.v - vo) - dv;
+        q.ev = plain(e);
+        if (P.spin_on) {
+            q.L = v3(__dadd_rn(Lo.x, dl.x), __dadd_rn(Lo.y, dl.y), __dadd_rn(Lo.z, dl.z));
+            q.el = v3(__dsub_rn(__dsub_rn(q.L.x, Lo.x), dl.x), __dsub_rn(__dsub_rn(q.L.y, Lo.y), dl.y), __dsub_rn(__dsub_rn(q.L.z, Lo.z), dl.z));
+        }
+    }
+}
+
+// particles/universe.rs:198-303 — Newtonian gravity with the WHFast ignore rules and the
+// Roche / collision / ejection checks (panic! in the reference, status word here). Strict arithmetic.
+template <int COORD>
+__device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, int gb, int b, size_t sys, const Lane& q, int& fail) {
+    S3 acc = s3(sd(0.), sd(0.), sd(0.));
+    const int n = P.n_bodies;
+    const int first_other = P.host == 0 ? 1 : 0;
+    fail = 0;
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+        S3 rj = shfl3(q.r, gb + j);
+        sd mj = sd(shfl(q.m, gb + j));
+        double Rj = shfl(q.R, gb + j);
+        if (j == b || !ro.valid) continue;
+        S3 d = q.r - rj;
+        sd d2 = d.x * d.x + d.y * d.y + d.z * d.z;
+        if (b < j) {
+            double rr = __ldg(P.roche + ((size_t)(b * n + j)) * (size_t)P.n_sys + sys);
+            double rs = __dadd_rn(q.R, Rj);
+            if (d2.v <= __dmul_rn(rr, rr)) { if (!fail) fail = PB200_STATUS_ROCHE_DESTROYED; }
+            if (d2.v <= __dmul_rn(rs, rs)) { if (!fail) fail = PB200_STATUS_COLLISION; }
+            if (b == P.host && d2.v > kMaxDistance2) { if (!fail) fail = PB200_STATUS_EJECTED; }
+        }
+        bool skip;
+        if (COORD == PB200_COORD_JACOBI) skip = (b == P.host && j == first_other) || (j == P.host && b == first_other);
+        else skip = (b == P.host || j == P.host);
+        if (skip) continue;
+        sd dist = ssqrt(d2);
+        sd pre = sd(-kG) / (dist * dist * dist) * mj;
+        acc.x = acc.x + pre * d.x; acc.y = acc.y + pre * d.y; acc.z = acc.z + pre * d.z;
+    }
+    return acc;
+}
+
+template <int COORD, int GR>
+__global__ void __launch_bounds__(PB_BLOCK) whfast_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
+    const int W = P.W;
+    const int n = P.n_bodies;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int b = (int)(gtid & (size_t)(W - 1));
+    const size_t sys = gtid >> P.shift;
+    const int gb = lane & ~(W - 1);
+    const int hl = gb + P.host;
+    const bool sys_ok = sys < (size_t)P.n_sys;
+    Roles ro;
+    ro.valid = sys_ok && b < n;
+    ro.host = ro.valid && b == P.host;
+    ro.planet = ro.valid && !ro.host;
+    ro.t_on = ro.planet && ((P.tides_orbiting >> b) & 1u);
+    ro.f_on = ro.planet && ((P.flat_orbiting >> b) & 1u);
+    ro.g_on = ro.planet && ((P.gr_orbiting >> b) & 1u);
+
+    Lane q;
+    SysState st;
+    V3 acc = v3(0., 0., 0.);
+    {
+        const size_t ns = (size_t)P.n_sys;
+        const size_t i = (size_t)b * ns + sys, cs = (size_t)n * ns;
+        if (ro.valid) {
+            q.r = s3(sd(P.pos[i]), sd(P.pos[i + cs]), sd(P.pos[i + 2 * cs]));
+            q.v = s3(sd(P.vel[i]), sd(P.vel[i + cs]), sd(P.vel[i + 2 * cs]));
+            q.L = v3(P.L[i], P.L[i + cs], P.L[i + 2 * cs]);
+            q.s = v3(P.spin[i], P.spin[i + cs], P.spin[i + 2 * cs]);
+            q.ev = v3(P.verr[i], P.verr[i + cs], P.verr[i + 2 * cs]);
+            q.el = v3(P.lerr[i], P.lerr[i + cs], P.lerr[i + 2 * cs]);
+            acc = v3(P.acc[i], P.acc[i + cs], P.acc[i + 2 * cs]);
+            q.m = P.mass[i]; q.mg = P.mass_g[i]; q.R = P.radius[i]; q.rg2 = P.rg2[i]; q.I = P.moi[i];
+            q.sigma = P.sigma[i]; q.k2t = P.k2t[i]; q.k2f = P.k2f[i];
+        } else {
+            q.r = s3(sd(1. + b), sd(0.), sd(0.)); q.v = s3(sd(0.), sd(0.), sd(0.));
+            q.L = v3(0., 0., 0.); q.s = v3(0., 0., 0.); q.ev = v3(0., 0., 0.); q.el = v3(0., 0., 0.);
+            q.m = 0.; q.mg = 0.; q.R = 0.; q.rg2 = 1.; q.I = 1.; q.sigma = 0.; q.k2t = 0.; q.k2f = 0.;
+        }
+        if (sys_ok) {
+            st.t = P.t[sys]; st.last_hist = P.last_hist[sys];
+            st.tswarn = P.tswarn[sys] != 0; st.status = P.status[sys]; st.warnings = P.warnings[sys]; st.hist_count = P.hist_count[sys];
+        } else {
+            st.t = 0.; st.last_hist = 0.; st.tswarn = true; st.status = PB200_STATUS_COMPLETED; st.warnings = 0; st.hist_count = 0;
+        }
+        st.steps_done = 0; st.n_hist_new = 0; st.event_step = 0;
+    }
+    bool alive = sys_ok && st.status == PB200_STATUS_OK;
+    Consts c;
+    make_consts(q, hl, c);
+
+    // constants of the transforms, all strict and in the reference's order
+    const sd m_s = sd(q.m);
+    const sd M_s = sd(shfl(q.m, hl));       // m0
+    const sd Mg_s = sd(shfl(q.mg, hl));
+    // total mass as inertial_to_*_posvel accumulate it: host first, then the others in index order
+    sd mtot = M_s;
+    sd eta_k = sd(0.), mu_k = sd(0.);        // Jacobi: cumulative mass / mass_g up to and including this body
+    {
+        sd mu = Mg_s;
+        if (COORD != PB200_COORD_JACOBI) mtot = sd(0.) + M_s;
+        for (int k = 0; k < n; k++) {
+            if (k == P.host) continue;
+            mtot = mtot + sd(shfl(q.m, gb + k));
+            mu = mu + sd(shfl(q.mg, gb + k));
+            if (k == b) { eta_k = mtot; mu_k = mu; }
+        }
+    }
+    const int first_other = P.host == 0 ? 1 : 0;
+    const sd dt_s = sd(P.dt), hdt_s = sd(P.half_dt);
+    const sd zero = sd(0.);
+    const S3 zero3 = s3(zero, zero, zero);
+
+#pragma unroll 1
+    for (unsigned long long step = 0; step < n_steps; step++) {
+        if (!__any_sync(FULL, alive)) break;
+        // ---- historic snapshot (whfast.rs:237-261, output.rs:119-163)
+        {
+            bool first = st.last_hist < 0.;
+            bool due = __dadd_rn(st.last_hist, P.hist_period) <= st.t;
+            bool snap = alive && (first || due);
+            if (__any_sync(FULL, snap)) {
+                Lane qs = q;
+                if (P.flags & FLAG_EVO) evolve_lane(P, ro, b, st.t, qs);
+                double invI = 1. / qs.I;
+                qs.s = invI * qs.L;
+                if (snap && ro.valid && st.hist_count < P.hist_capacity) {
+                    const size_t ns = (size_t)P.n_sys;
+                    const size_t i = (size_t)b * ns + sys, cs = (size_t)n * ns;
+                    double denergy = 0.;
+                    if ((P.flags & FLAG_TIDES) && ro.t_on) {
+                        // tides/common.rs:263-279 with the internals left by the last evaluation and the fresh spin
+                        double ts[PB_TIDE_SCRATCH];
+                        for (int k = 0; k < PB_TIDE_SCRATCH; k++) ts[k] = P.tide_scratch[i + k * cs];
+                        V3 tp = v3(ts[0], ts[1], ts[2]), tv = v3(ts[3], ts[4], ts[5]);
+                        double dist = ts[6], radvel = ts[7], orth_p = ts[8], diss_pm = ts[9];
+                        V3 tdl = v3(ts[10], ts[11], ts[12]);
+                        double factor2 = orth_p / dist;
+                        V3 wxr = cross(qs.s, tp);
+                        denergy = -((1.0 / dist * (diss_pm + factor2 * radvel)) * dot(tp, tv)
+                                    + factor2 * ((wxr.x - tv.x) * tv.x + (wxr.y - tv.y) * tv.y + (wxr.z - tv.z) * tv.z))
+                                  - dot(tdl, qs.s);
+                    }
+                    double* h = P.hist + (size_t)st.hist_count * PB_HIST_FIELDS * cs + i;
+                    h[0 * cs] = st.t;
+                    h[1 * cs] = qs.r.x.v; h[2 * cs] = qs.r.y.v; h[3 * cs] = qs.r.z.v;
+                    h[4 * cs] = qs.s.x; h[5 * cs] = qs.s.y; h[6 * cs] = qs.s.z;
+                    h[7 * cs] = qs.v.x.v; h[8 * cs] = qs.v.y.v; h[9 * cs] = qs.v.z.v;
+                    h[10 * cs] = qs.m; h[11 * cs] = qs.R; h[12 * cs] = qs.rg2;
+                    h[13 * cs] = qs.k2t; h[14 * cs] = qs.sigma; h[15 * cs] = denergy;
+                }
+                if (snap) {
+                    // the refresh changes the live state too (spin, evolving quantities)
+                    q.s = qs.s; q.R = qs.R; q.rg2 = qs.rg2; q.I = qs.I;
+                    if (!first) st.last_hist = __dadd_rn(st.last_hist, P.hist_period); else st.last_hist = 0.;
+                    st.n_hist_new += 1;
+                    if (st.hist_count < P.hist_capacity) st.hist_count += 1;
+                }
+                if (P.flags & FLAG_EVO) make_consts(q, hl, c);
+            }
+        }
+        // internals needed by the NEXT snapshot's denergy_dt are those of this step's last evaluation
+        const bool save_tides = (step + 1 == n_steps) || (__dadd_rn(st.last_hist, P.hist_period) <= __dadd_rn(st.t, P.dt));
+
+        // ---- first half of the velocity-dependent forces (whfast.rs:278)
+        midpoint<COORD, GR>(P, ro, gb, hl, b, alive, q, c, st.t, true, acc, st.warnings, false, sys);
+
+        // ---- first drift (whfast.rs:469-479)
+        S3 apos, avel;       // this body's alternative coordinates
+        S3 spos, svel;       // the host slot of the alternative coordinates (centre of mass), replicated in the group
+        const bool kwork = ro.planet && alive;
+        if (COORD == PB200_COORD_JACOBI) {
+            // inertial_to_jacobi_posvel (whfast.rs:889-933)
+            sd eta = M_s;
+            S3 s = eta * shfl3(q.r, hl), sv = eta * shfl3(q.v, hl);
+            apos = zero3; avel = zero3;
+            for (int k = 0; k < n; k++) {
+                if (k == P.host) continue;
+                sd mk = sd(shfl(q.m, gb + k));
+                S3 rk = shfl3(q.r, gb + k), vk = shfl3(q.v, gb + k);
+                sd ei = sd(1.) / eta;
+                eta = eta + mk;
+                sd pme = eta * ei;
+                S3 pk = rk - s * ei, wk = vk - sv * ei;
+                if (b == k) { apos = pk; avel = wk; }
+                s = s * pme + mk * pk; sv = sv * pme + mk * wk;
+            }
+            sd mi = sd(1.) / eta;
+            spos = s * mi; svel = sv * mi;
+            kepler_step(kwork, apos, avel, mu_k, hdt_s, st.tswarn, st.warnings);
+            spos = spos + hdt_s * svel;
+        } else {
+            // inertial_to_whds_and_democratic_heliocentric_posvel (whfast.rs:973-1023): host first, then the others
+            S3 mr = q.r * m_s, mv = q.v * m_s;
+            S3 sr = ordered_sum_others(zero3 + shfl3(mr, hl), mr, gb, n, P.host);
+            S3 sv = ordered_sum_others(zero3 + shfl3(mv, hl), mv, gb, n, P.host);
+            spos = sr / mtot; svel = sv / mtot;
+            apos = q.r - shfl3(q.r, hl);
+            avel = q.v - svel;
+            sd mu = Mg_s;
+            if (COORD == PB200_COORD_WHDS) {
+                sd f = (M_s + m_s) / M_s;
+                avel = avel * f;
+                mu = Mg_s + sd(q.mg);
+            }
+            kepler_step(kwork, apos, avel, mu, hdt_s, st.tswarn, st.warnings);
+            spos = spos + hdt_s * svel;
+            // jump_step (whfast.rs:507-556)
+            if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
+                S3 p = ordered_sum_others(zero3, m_s * avel, gb, n, P.host);
+                apos = s3(apos.x + hdt_s * p.x / M_s, apos.y + hdt_s * p.y / M_s, apos.z + hdt_s * p.z / M_s);
+            } else {
+                sd f = M_s + m_s;
+                S3 term = s3(m_s * avel.x / f, m_s * avel.y / f, m_s * avel.z / f);
+                S3 p = ordered_sum_others(zero3, term, gb, n, P.host);
+                apos = s3(apos.x + hdt_s * (p.x - term.x), apos.y + hdt_s * (p.y - term.y), apos.z + hdt_s * (p.z - term.z));
+            }
+        }
+        // alternative_to_inertial (positions; the velocities of this call are dead: the kick overwrites them)
+        if (COORD == PB200_COORD_JACOBI) {
+            sd eta = mtot;
+            S3 s = eta * spos;
+            for (int k = n - 1; k >= 0; k--) {
+                if (k == P.host) continue;
+                sd mk = sd(shfl(q.m, gb + k));
+                S3 pk = shfl3(apos, gb + k);
+                sd ei = sd(1.) / eta;
+                s = (s - mk * pk) * ei;
+                if (b == k) q.r = pk + s;
+                eta = eta - mk;
+                s = s * eta;
+            }
+            if (ro.host) q.r = s * (sd(1.) / eta);
+        } else {
+            // whds_and_democratic_heliocentric_to_inertial_pos (whfast.rs:1128-1155)
+            S3 term = s3(apos.x * m_s / mtot, apos.y * m_s / mtot, apos.z * m_s / mtot);
+            S3 star_r = ordered_diff_others(spos, term, gb, n, P.host);
+            q.r = ro.host ? star_r : apos + star_r;
+        }
+
+        // ---- gravity (whfast.rs:281)
+        int fail;
+        S3 anew_s = gravity<COORD>(P, ro, gb, b, sys, q, fail);
+        V3 anew = plain(anew_s);
+        // group-wide failure: lowest body index wins, like the reference's loop order
+        {
+            int code = (ro.valid && fail) ? ((b << 4) | fail) : 0x7fffffff;
+            for (int off = W >> 1; off > 0; off >>= 1) { int o = __shfl_xor_sync(FULL, code, off); code = o < code ? o : code; }
+            if (alive && code != 0x7fffffff) {
+                st.status = code & 15; st.event_step = st.steps_done; alive = false;
+                store_lane(P, ro, sys, b, q, anew, st);
+            }
+        }
+        if (alive) acc = anew;
+
+        // ---- kick + second drift (whfast.rs:482-491)
+        if (COORD == PB200_COORD_JACOBI) {
+            // inertial_to_jacobi_acc (whfast.rs:935-963) + jacobi_interaction_step (:566-592)
+            sd eta = M_s;
+            S3 sa = eta * shfl3(anew_s, hl);
+            S3 aacc = zero3;
+            for (int k = 0; k < n; k++) {
+                if (k == P.host) continue;
+                sd mk = sd(shfl(q.m, gb + k));
+                S3 ak = shfl3(anew_s, gb + k);
+                sd ei = sd(1.) / eta;
+                eta = eta + mk;
+                sd pme = eta * ei;
+                S3 ck = ak - sa * ei;
+                if (b == k) aacc = ck;
+                sa = sa * pme + mk * ck;
+            }
+            avel = avel + dt_s * aacc;
+            if (b != first_other) {
+                sd rj2i = sd(1.) / (apos.x * apos.x + apos.y * apos.y + apos.z * apos.z + sd(1e-12));
+                sd rji = ssqrt(rj2i);
+                sd rj3im = rji * rj2i * sd(kG) * eta_k;
+                sd prefac = dt_s * rj3im;
+                avel = avel + prefac * apos;
+            }
+            kepler_step(kwork, apos, avel, mu_k, hdt_s, st.tswarn, st.warnings);
+            spos = spos + hdt_s * svel;
+            // jacobi_to_inertial_posvel (whfast.rs:1034-1080)
+            sd et = mtot;
+            S3 s = et * spos, sv = et * svel;
+            S3 nr = q.r, nv = q.v;
+            for (int k = n - 1; k >= 0; k--) {
+                if (k == P.host) continue;
+                sd mk = sd(shfl(q.m, gb + k));
+                S3 pk = shfl3(apos, gb + k), wk = shfl3(avel, gb + k);
+                sd ei = sd(1.) / et;
+                s = (s - mk * pk) * ei; sv = (sv - mk * wk) * ei;
+                if (b == k) { nr = pk + s; nv = wk + sv; }
+                et = et - mk;
+                s = s * et; sv = sv * et;
+            }
+            if (ro.host) { sd mi = sd(1.) / et; nr = s * mi; nv = sv * mi; }
+            if (alive) { q.r = nr; q.v = nv; }
+        } else {
+            sd mu = Mg_s;
+            if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
+                // democratic_heliocentric_interaction_step (whfast.rs:594-608) + jump
+                avel = avel + dt_s * anew_s;
+                S3 p = ordered_sum_others(zero3, m_s * avel, gb, n, P.host);
+                apos = s3(apos.x + hdt_s * p.x / M_s, apos.y + hdt_s * p.y / M_s, apos.z + hdt_s * p.z / M_s);
+            } else {
+                // whds_interaction_step (whfast.rs:610-625) + jump
+                sd f = M_s + m_s;
+                avel = s3(avel.x + dt_s * f * anew_s.x / M_s, avel.y + dt_s * f * anew_s.y / M_s, avel.z + dt_s * f * anew_s.z / M_s);
+                S3 term = s3(m_s * avel.x / f, m_s * avel.y / f, m_s * avel.z / f);
+                S3 p = ordered_sum_others(zero3, term, gb, n, P.host);
+                apos = s3(apos.x + hdt_s * (p.x - term.x), apos.y + hdt_s * (p.y - term.y), apos.z + hdt_s * (p.z - term.z));
+                mu = Mg_s + sd(q.mg);
+            }
+            kepler_step(kwork, apos, avel, mu, hdt_s, st.tswarn, st.warnings);
+            spos = spos + hdt_s * svel;
+            // whds_and_democratic_heliocentric_to_inertial_posvel (whfast.rs:1090-1155)
+            S3 term = s3(apos.x * m_s / mtot, apos.y * m_s / mtot, apos.z * m_s / mtot);
+            S3 star_r = ordered_diff_others(spos, term, gb, n, P.host);
+            S3 nr = ro.host ? star_r : apos + star_r;
+            S3 nv, back;
+            if (COORD == PB200_COORD_WHDS) {
+                sd f = (M_s + m_s) / M_s;
+                nv = avel / f + svel;
+                back = avel * (m_s / (M_s + m_s));
+            } else {
+                nv = avel + svel;
+                back = avel * (m_s / M_s);
+            }
+            S3 star_v = ordered_diff_others(svel, back, gb, n, P.host);
+            if (ro.host) nv = star_v;
+            if (alive) { q.r = nr; q.v = nv; }
+        }
+
+        // ---- second half of the velocity-dependent forces (whfast.rs:293)
+        midpoint<COORD, GR>(P, ro, gb, hl, b, alive, q, c, st.t, false, acc, st.warnings, save_tides, sys);
+
+        if (alive) {
+            st.t = __dadd_rn(st.t, P.dt);
+            st.steps_done += 1;
+            if (__dadd_rn(st.t, P.dt) > P.time_limit) {
+                st.status = PB200_STATUS_COMPLETED; st.event_step = st.steps_done; alive = false;
+                store_lane(P, ro, sys, b, q, acc, st);
+            }
+        }
+    }
+    if (alive) store_lane(P, ro, sys, b, q, acc, st);
+}
+
+}  // namespace pb200

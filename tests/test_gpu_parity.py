@@ -1,0 +1,198 @@
+"""GPU parity: the CUDA ensemble (through the C ABI) against the reference's golden vectors and the CPU oracle.
+
+Tolerances (all written here, justified in DESIGN.md §Parity):
+  * golden fixtures (199 steps): the reference's own bar, |x - golden| < 1e-14 absolute on r, v, a.
+  * configuration ensembles vs the oracle on the same seeded inputs: 1e-10 relative (vector norm per body) on
+    r, v, spin after 10^3 steps, and FAST_TOL_1E4 after 10^4 steps. The WHFast core is bit-reproducing; the
+    perturbation forces use FMA/reciprocal arithmetic, so occasional last-bit differences seed the same
+    t^1.5 phase divergence that the CPU restatement shows against ITSELF when FMA contraction is enabled
+    (2.1e-10 on TRAPPIST-1 after 10^4 steps, measured).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, CONFIG_NAMES, config_case, load_json_gz
+from parity_util import gpu_state_of, oracle_state_of, rel_err
+
+pytestmark = pytest.mark.gpu
+
+with open(os.path.join(GOLDEN, "manifest.json")) as _f:
+    _MANIFEST = json.load(_f)
+
+TOL_1E3 = 1e-10
+FAST_TOL_1E4 = 1e-9
+
+
+@pytest.fixture(scope="module")
+def E():
+    from posidonius_b200 import ensemble
+    return ensemble
+
+
+@pytest.mark.parametrize("name", sorted(_MANIFEST["fixtures"]))
+def test_golden_fixture_on_gpu(E, name):
+    from posidonius_b200 import abi
+    from posidonius_b200.case import case_from_dict
+    fx = _MANIFEST["fixtures"][name]
+    case, tables = case_from_dict(load_json_gz(fx["case"]))
+    # several replicas so that groups share warps; every replica must land on the same golden vector
+    with E.Ensemble(case, tables, n_systems=5) as ens:
+        ens.initialize_physical_values()
+        ens.iterate(10 ** 6)
+        st, w, it = ens.status()
+        assert np.all(st == abi.STATUS_COMPLETED) and np.all(it == 199) and np.all(w == 0)
+        for s in (0, 4):
+            out = ens.get_case(s)
+            assert out.current_iteration == 199
+            for i, exp in enumerate(fx["particles"]):
+                for key in ("inertial_position", "inertial_velocity", "inertial_acceleration"):
+                    got = np.array(getattr(out.bodies[i], key)[:])
+                    want = np.array([exp[key]["x"], exp[key]["y"], exp[key]["z"]])
+                    assert np.all(np.abs(got - want) < fx["tolerance_abs"]), (name, s, i, key, got, want)
+
+
+def _run_config(E, idx, name, n_sys, steps):
+    from oracle.binding import run_ensemble
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import make_ensemble_cases
+    case, tables = case_from_dict(config_case(name))
+    cases = make_ensemble_cases(case, n_sys, 20261017 + idx)
+    with E.Ensemble(cases, tables) as ens:
+        ens.initialize_physical_values()
+        ens.iterate(steps)
+        g = gpu_state_of(ens)
+        st, w, it = ens.status()
+        e_gpu, l_gpu = ens.summary()
+    oc, ost, _ = run_ensemble(cases, n_sys, tables, steps, True, os.cpu_count() or 1)
+    o = oracle_state_of(oc)
+    return g, o, st, ost
+
+
+@pytest.mark.parametrize("idx,name", list(enumerate(CONFIG_NAMES)))
+def test_config_ensemble_vs_oracle_1e3_steps(E, idx, name):
+    g, o, st, ost = _run_config(E, idx, name, 32, 1000)
+    assert np.array_equal(st, ost)
+    for k in ("position", "velocity", "spin", "angular_momentum"):
+        assert rel_err(g[k], o[k]) < TOL_1E3, (name, k, rel_err(g[k], o[k]))
+    assert np.allclose(g["current_time"], o["current_time"], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("idx,name", list(enumerate(CONFIG_NAMES)))
+def test_config_ensemble_vs_oracle_1e4_steps(E, idx, name):
+    g, o, st, ost = _run_config(E, idx, name, 16, 10000)
+    assert np.array_equal(st, ost)
+    for k in ("position", "velocity", "spin"):
+        assert rel_err(g[k], o[k]) < FAST_TOL_1E4, (name, k, rel_err(g[k], o[k]))
+
+
+def test_energy_and_angular_momentum_drift_match_oracle(E):
+    """ΔE/E and ΔL/L over 10^4 steps of TRAPPIST-1 agree between the GPU and the oracle."""
+    from oracle.binding import OracleSystem
+    from posidonius_b200.case import case_from_dict
+    case, tables = case_from_dict(config_case("c4_trappist1"))
+    o = OracleSystem(case, tables)
+    o.initialize_physical_values()
+    e0, l0 = o.summary()
+    o.iterate(10000)
+    e1, l1 = o.summary()
+    with E.Ensemble(case, tables, n_systems=4) as ens:
+        ens.initialize_physical_values()
+        ge0, gl0 = ens.summary()
+        ens.iterate(10000)
+        ge1, gl1 = ens.summary()
+    assert abs(ge0[0] - e0) <= 1e-15 * abs(e0) and abs(gl0[0] - l0) <= 1e-15 * abs(l0)
+    d_oracle = (e1 - e0) / abs(e0)
+    d_gpu = (ge1[0] - ge0[0]) / abs(ge0[0])
+    assert abs(d_gpu - d_oracle) < 1e-12 + 1e-3 * abs(d_oracle), (d_gpu, d_oracle)
+    dl_oracle = (l1 - l0) / abs(l0)
+    dl_gpu = (gl1[0] - gl0[0]) / abs(gl0[0])
+    assert abs(dl_gpu - dl_oracle) < 1e-12 + 1e-3 * abs(dl_oracle), (dl_gpu, dl_oracle)
+
+
+def test_history_records_match_oracle(E):
+    """156-byte historic records (output.rs:119-163) produced on the device equal the oracle's, field by field."""
+    from oracle.binding import OracleSystem
+    from posidonius_b200 import abi
+    from posidonius_b200.case import case_from_dict
+    d = config_case("c3_case7_evolving")
+    d["historic_snapshot_period"] = 8.0  # every 100 steps
+    case, tables = case_from_dict(d)
+    o = OracleSystem(case, tables)
+    o.initialize_physical_values()
+    o.iterate(450)
+    raw = o.history()
+    with E.Ensemble(case, tables, n_systems=3) as ens:
+        ens.initialize_physical_values()
+        ens.iterate(450)
+        rec = ens.history_drain()
+    n = case.n_particles
+    assert rec.shape == (3, 5, n, abs(abi.HISTORIC_RECORD_BYTES))
+    assert len(raw) == 5 * n * abi.HISTORIC_RECORD_BYTES
+    dt = np.dtype([("current_time", "<f8"), ("time_step", "<f8"), ("particle", "<i4")] + [("f%d" % k, "<f8") for k in range(17)])
+    want = np.frombuffer(raw, dtype=dt).reshape(5, n)
+    got = np.frombuffer(rec[1].tobytes(), dtype=dt).reshape(5, n)
+    assert np.array_equal(got["particle"], want["particle"])
+    assert np.array_equal(got["current_time"], want["current_time"]) and np.array_equal(got["time_step"], want["time_step"])
+    for k in range(17):
+        a, b = got["f%d" % k], want["f%d" % k]
+        both_nan = np.isnan(a) & np.isnan(b)   # denergy_dt of the very first record is 0/0 in the reference too
+        scale = np.max(np.abs(b[~both_nan])) if np.any(~both_nan) else 1.0
+        assert np.all(both_nan | (np.abs(a - b) <= 1e-9 * max(scale, 1e-300))), (k, a, b)
+
+
+def test_status_completed_and_frozen(E):
+    from posidonius_b200 import abi
+    from posidonius_b200.case import case_from_dict
+    d = config_case("c2_case3")
+    d["universe"]["time_limit"] = 8.0
+    case, tables = case_from_dict(d)
+    with E.Ensemble(case, tables, n_systems=7) as ens:
+        ens.initialize_physical_values()
+        ens.iterate(50)
+        st, _, _ = ens.status()
+        assert np.all(st == abi.STATUS_OK)
+        ens.iterate(1000)
+        st, _, it = ens.status()
+        assert np.all(st == abi.STATUS_COMPLETED)
+        a = ens.download(("position", "current_time"))
+        ens.iterate(10)  # completed systems are frozen
+        b = ens.download(("position", "current_time"))
+        assert np.array_equal(a["position"], b["position"]) and np.array_equal(a["current_time"], b["current_time"])
+        # Q1: steps until t + dt > limit on the accumulated clock, exactly like the oracle
+        from oracle.binding import OracleSystem
+        o = OracleSystem(case, tables)
+        o.initialize_physical_values()
+        n = o.iterate(10 ** 6)
+        assert np.all(it == n)
+
+
+def test_collision_sets_status_instead_of_panicking(E):
+    from posidonius_b200 import abi
+    from posidonius_b200.case import case_from_dict
+    d = config_case("c2_case3")
+    case, tables = case_from_dict(d)
+    case.bodies[1].radius = 0.5  # planet radius larger than its orbital distance: overlap at the first gravity call
+    with E.Ensemble(case, tables, n_systems=4) as ens:
+        ens.initialize_physical_values()
+        ens.iterate(5)
+        st, _, it = ens.status()
+        assert np.all((st == abi.STATUS_COLLISION) | (st == abi.STATUS_ROCHE_DESTROYED)) and np.all(it == 0)
+
+
+def test_run_host_roundtrip_equals_device_resident_run(E):
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import make_ensemble_cases
+    case, tables = case_from_dict(config_case("c4_trappist1"))
+    cases = make_ensemble_cases(case, 64, 7)
+    with E.Ensemble(cases, tables) as a, E.Ensemble(cases, tables) as b:
+        a.initialize_physical_values()
+        b.initialize_physical_values()
+        a.iterate(100)
+        buf = b.download()
+        b.run_host(buf, 100)
+        ref = a.download()
+        for k in ref:
+            assert np.array_equal(ref[k], buf[k]), k

@@ -1,0 +1,101 @@
+"""CPU-side tests: the C ABI library loads and exports every declared symbol, the JSON reader rejects what the
+hot path does not cover (no fallback), ensemble packing, header/ctypes layout agreement."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import CONFIG_NAMES, ROOT, config_case, load_json_gz
+from posidonius_b200 import abi
+from posidonius_b200.case import InvalidCaseError, UnsupportedCaseError, case_from_dict
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    from posidonius_b200._lib import exported_symbols, lib
+    L = lib()
+    header = open(os.path.join(ROOT, "include", "posidonius_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)  # strip comments
+    declared = set(re.findall(r"^[a-z_0-9 \*]*\b(pb200_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(L, name), "libposidonius_b200.so does not export %s" % name
+    assert declared == set(exported_symbols())
+    assert b"sm_100a" in L.pb200_version()
+
+
+def test_ctypes_layout_matches_header_sizes():
+    # sizes implied by the header: doubles/ints only, natural alignment
+    assert C.sizeof(abi.Body) == 8 * (5 + 3 * 7 + 9) + 4 * 8
+    assert C.sizeof(abi.Case) == 8 * 9 + 8 * 3 + 4 * 14 + C.sizeof(abi.Body) * 10 + 8 * 30 * 2 + 8 * 100
+    assert C.sizeof(abi.StateView) == 8 * 11
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_config_cases_parse_and_validate_without_gpu(name):
+    from posidonius_b200.ensemble import validate_case
+    case, tables = case_from_dict(config_case(name))
+    validate_case(case, tables)  # host-only check, no device needed
+    assert case.n_particles >= 2 and case.coordinates_type in (0, 1, 2)
+
+
+def test_rejects_out_of_scope_cases(manifest):
+    for name, fx in manifest["reject"].items():
+        with pytest.raises(UnsupportedCaseError):
+            case_from_dict(load_json_gz(fx["case"]))
+
+
+def test_rejects_kaula_and_creep_models():
+    d = config_case("c4_trappist1")
+    model = d["universe"]["particles"][1]["tides"]["effect"]["OrbitingBody"]
+    d["universe"]["particles"][1]["tides"]["effect"]["OrbitingBody"] = {"Kaula": model["ConstantTimeLag"]}
+    with pytest.raises(UnsupportedCaseError):
+        case_from_dict(d)
+    d = config_case("c4_trappist1")
+    model = d["universe"]["particles"][1]["rotational_flattening"]["effect"]["OrbitingBody"]
+    d["universe"]["particles"][1]["rotational_flattening"]["effect"]["OrbitingBody"] = {"CreepCoplanar": model["OblateSpheroid"]}
+    with pytest.raises(UnsupportedCaseError):
+        case_from_dict(d)
+
+
+def test_validate_rejects_bad_structure():
+    from posidonius_b200.ensemble import validate_case
+    case, tables = case_from_dict(config_case("c1_example"))
+    case.consider_disk = 1
+    with pytest.raises(UnsupportedCaseError):
+        validate_case(case, tables)
+    case, tables = case_from_dict(config_case("c1_example"))
+    case.bodies[0].moment_of_inertia = 0.0
+    with pytest.raises(InvalidCaseError):
+        validate_case(case, tables)
+    case, tables = case_from_dict(config_case("c1_example"))
+    case.host_tides = 1
+    with pytest.raises(UnsupportedCaseError):
+        validate_case(case, tables)
+
+
+def test_perturbed_ensemble_member_zero_is_the_base_case():
+    from posidonius_b200.perturb import make_ensemble_cases
+    case, _ = case_from_dict(config_case("c4_trappist1"))
+    cases = make_ensemble_cases(case, 128, 20261017 + 4)
+    for b in range(case.n_particles):
+        assert cases[0].bodies[b].inertial_position[:] == case.bodies[b].inertial_position[:]
+        assert cases[0].bodies[b].inertial_velocity[:] == case.bodies[b].inertial_velocity[:]
+    p0 = np.array(case.bodies[3].heliocentric_position[:])
+    p9 = np.array(cases[9].bodies[3].heliocentric_position[:])
+    assert 0 < np.max(np.abs(p9 / p0 - 1.0)) <= 1e-3
+    # barycentric: total momentum vanishes
+    mom = sum(cases[9].bodies[b].mass * np.array(cases[9].bodies[b].inertial_velocity[:]) for b in range(case.n_particles))
+    assert np.max(np.abs(mom)) < 1e-18
+
+
+def test_no_device_reports_error_not_fallback():
+    """Without a GPU the ensemble constructor must fail loudly (PB200_E_CUDA), never integrate on the CPU."""
+    from posidonius_b200._lib import lib
+    if lib().pb200_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from posidonius_b200.ensemble import Ensemble, EnsembleError
+    case, tables = case_from_dict(config_case("c1_example"))
+    with pytest.raises(EnsembleError):
+        Ensemble(case, tables)
