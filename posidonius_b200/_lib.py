@@ -9,7 +9,8 @@ import os
 from . import abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libposidonius_b200.so")
+# PB200_LIB selects an experimental build variant of the same library (tuning runs only)
+LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(HERE, "libposidonius_b200.so")
 
 _SIGNATURES = {
     "pb200_version": (C.c_char_p, []),

@@ -22,20 +22,22 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, out=None, defines=()):
+    """out/defines: experimental variants (e.g. -DPB_MIN_BLOCKS=3) built next to the product library."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    target = out or LIB
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", target] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    log = os.path.join(HERE, "build.log")
+    log = os.path.join(HERE, "build.log" if out is None else os.path.basename(out) + ".log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + proc.stdout)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building %s (see %s)" % (LIB, log))
-    return LIB
+        raise RuntimeError("nvcc failed building %s (see %s)" % (target, log))
+    return target
 
 
 if __name__ == "__main__":

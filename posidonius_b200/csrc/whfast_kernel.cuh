@@ -142,8 +142,12 @@ __device__ __forceinline__ void stiefel_gs3(sd beta, sd x, sd& g0, sd& g1, sd& g
 // Universal-variable Kepler drift of one body (whfast.rs:676-833), strict arithmetic in the reference's
 // association order. `work` lanes only; the warp iterates until every working lane has met the reference's
 // exit test (exact repetition of x).
-__device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu, sd dt, bool& tswarn, unsigned int& warnings) {
-    const S3 p1 = pos, v1 = vel;
+__device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu_in, sd dt, bool& tswarn, unsigned int& warnings) {
+    // idle lanes (host slot, padding, stopped systems) get a benign state so that no lane drags the warp into the
+    // slow paths of the IEEE division / square root (zero or NaN operands)
+    const S3 p1 = work ? pos : s3(sd(1.), sd(0.), sd(0.));
+    const S3 v1 = work ? vel : s3(sd(0.), sd(0.), sd(0.));
+    const sd mu = work ? mu_in : sd(0.);
     const sd r0 = ssqrt(p1.x * p1.x + p1.y * p1.y + p1.z * p1.z);
     const sd r0i = sd(1.) / r0;
     const sd v2 = v1.x * v1.x + v1.y * v1.y + v1.z * v1.z;
@@ -151,14 +155,18 @@ __device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu, 
     const sd eta0 = p1.x * v1.x + p1.y * v1.y + p1.z * v1.z;
     const sd zeta0 = mu - beta * r0;
     sd x, g0, g1, g2, g3;
-    sd invperiod = sd(0.), x_per_period = sd(0.);
     const bool elliptic = beta.v > 0.;
     const sd two_pi = sd(2. * kPi);
+    // invperiod = sqrt(beta) beta / (2 pi mu) and x_per_period = 2 pi / sqrt(beta) only feed two threshold tests and the
+    // rare fallbacks. The tests are first decided on squared quantities with a factor-2 guard band (no sqrt/div);
+    // only a lane inside the band evaluates the reference's exact expression.
     if (elliptic) {
-        sd sqrt_beta = ssqrt(beta);
-        invperiod = sqrt_beta * beta / (two_pi * mu);
-        x_per_period = two_pi / sqrt_beta;
-        if (work && fabs(dt.v) * invperiod.v > 1. && !tswarn) { tswarn = true; warnings |= PB200_WARN_TIMESTEP_GT_PERIOD; }
+        if (work && !tswarn) {
+            double w = (dt.v * dt.v) * (beta.v * beta.v * beta.v), lim = (two_pi.v * mu.v) * (two_pi.v * mu.v);
+            bool warn = w > 2. * lim;
+            if (!warn && w > 0.5 * lim) { sd ip = ssqrt(beta) * beta / (two_pi * mu); warn = fabs(dt.v) * ip.v > 1.; }
+            if (warn) { tswarn = true; warnings |= PB200_WARN_TIMESTEP_GT_PERIOD; }
+        }
         sd dtr0i = dt * r0i;
         x = dtr0i * (sd(1.) - dtr0i * eta0 * sd(0.5) * r0i);
     } else {
@@ -170,7 +178,13 @@ __device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu, 
     sd e1 = eta0 * g1 + zeta0 * g2;
     sd ri = sd(1.) / (r0 + e1);
     x = ri * (x * e1 - eta0 * g2 - zeta0 * g3 + dt);
-    const bool quartic = work && elliptic && fabs((x - old_x).v) > (sd(0.01) * x_per_period).v;
+    bool quartic = false;
+    if (work && elliptic) {
+        double dx = (x - old_x).v;
+        double qv = dx * dx * beta.v, lim = (0.01 * two_pi.v) * (0.01 * two_pi.v);
+        quartic = qv > 2. * lim;
+        if (!quartic && qv > 0.5 * lim) { sd xpp = two_pi / ssqrt(beta); quartic = fabs(dx) > (sd(0.01) * xpp).v; }
+    }
     if (__any_sync(FULL, quartic)) {
         // Laguerre-like quartic solver (whfast.rs:732-755), rare: large steps only.
         if (quartic) {
@@ -215,6 +229,9 @@ __device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu, 
         if (bisect) {
             sd x_min, x_max;
             if (elliptic) {
+                sd sqrt_beta = ssqrt(beta);
+                sd invperiod = sqrt_beta * beta / (two_pi * mu);
+                sd x_per_period = two_pi / sqrt_beta;
                 x_min = x_per_period * sd(floor((dt * invperiod).v));
                 x_max = x_min + x_per_period;
             } else {
@@ -278,12 +295,16 @@ __device__ __forceinline__ S3 strict(V3 a) { return s3(sd(a.x), sd(a.y), sd(a.z)
 __device__ __forceinline__ S3 shfl3(S3 a, int src) { return s3(sd(shfl(a.x.v, src)), sd(shfl(a.y.v, src)), sd(shfl(a.z.v, src))); }
 __device__ __forceinline__ sd shfl(sd a, int src) { return sd(shfl(a.v, src)); }
 
-// per-step constants derived from masses/radii (recomputed when the radius evolves)
+// per-system constants derived from masses/radii (recomputed only when the radius evolves): every division whose
+// operands do not change between evaluations is done here once
 struct Consts {
     double invI;
     double As, Ap, Bk;   // tides: 4.5 m^2 R*^10 sigma*, 4.5 M^2 R^10 sigma, 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2)
     double Ks, Kp;       // flattening: m k2f* R*^5, M k2f R^5
     double M, Mg, Ih;    // host mass, mass_g, moment of inertia
+    double inv_m, inv_M; // 1/m, 1/M
+    double mgs, grf;     // GR: Mg + mg, factor = Mg mg / (Mg + mg)^2 (general_relativity.rs:98)
+    double mu_red;       // M m / (M + m)
 };
 
 __device__ __forceinline__ double pow5(double x) { double x2 = x * x; return x2 * x2 * x; }
@@ -300,6 +321,10 @@ __device__ __forceinline__ void make_consts(const Lane& q, int hl, Consts& c) {
     c.Bk = 3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * q.k2t);
     c.Ks = q.m * k2f_h * Rh5;
     c.Kp = c.M * q.k2f * R5;
+    c.inv_m = 1. / q.m; c.inv_M = 1. / c.M;
+    c.mgs = c.Mg + q.mg;
+    c.grf = c.Mg * q.mg / (c.mgs * c.mgs);
+    c.mu_red = (c.M * q.m) / (c.M + q.m);
 }
 
 struct Roles {
@@ -326,13 +351,13 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     double w2 = dot(q.s, q.s);
     V3 sh = shfl3(q.s, hl);
     double wh2 = shfl(w2, hl);
-    double d = 1. / inv_d;  // only used multiplicatively below
     double inv_d2 = inv_d * inv_d;
+    double d = dot(hr, hr) * inv_d;
     double radvel = dot(hr, hv) * inv_d;
     V3 rxv = cross(hr, hv);
     V3 a_p = v3(0., 0., 0.), dl_p = v3(0., 0., 0.);       // this body's own acceleration / torque
     V3 a_h = v3(0., 0., 0.), dl_h = v3(0., 0., 0.);       // contribution to the host
-    const double inv_m = 1. / q.m, inv_M = 1. / c.M;
+    const double inv_m = c.inv_m, inv_M = c.inv_M;
     if (P.flags & FLAG_TIDES) {
         // constant_time_lag.rs:206-332, tides/common.rs:223-345
         double inv_d4 = inv_d2 * inv_d2;
@@ -388,8 +413,8 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     if (GR == PB200_GR_KIDDER1995) {
         // general_relativity.rs:177-456
         double v2 = dot(hv, hv);
-        double mgs = c.Mg + q.mg;
-        double f = c.Mg * q.mg / (mgs * mgs);
+        double mgs = c.mgs;
+        double f = c.grf;
         double A = mgs * inv_d2 * kInvC2;
         double u = mgs * inv_d;
         double rv2 = radvel * radvel;
@@ -418,8 +443,7 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         const double fa = kG * kInvC2;
         a = a + fa * (e1 - e2 + e3);
         // Kidder 1995 eqs 2.4a, 2.4b
-        double mu = (c.M * q.m) / (c.M + q.m);
-        V3 Lo = mu * rxv;
+        V3 Lo = c.mu_red * rxv;
         double fm_s = 2. + 1.5 * q.m * inv_M, fm_p = 2. + 1.5 * c.M * inv_m;
         V3 LpxLs = cross(Lp, Ls);
         V3 ds = fm_s * cross(Lo, Ls) - LpxLs + (3. * dot(nn, Lp)) * cross(nn, Ls);

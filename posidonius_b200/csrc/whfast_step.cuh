@@ -92,7 +92,8 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, int 
     // positions do not change inside the midpoint: heliocentric position and 1/r once (universe.rs:318-351)
     const S3 rh_s = shfl3(q.r, hl);
     const V3 rh = plain(rh_s);
-    const V3 hr = plain(q.r - rh_s);
+    // idle lanes (host slot, padding) get a unit dummy so that rsqrt/div stay on their fast paths for the whole warp
+    const V3 hr = ro.planet ? plain(q.r - rh_s) : v3(1., 0., 0.);
     const double inv_d = rsqrt(dot(hr, hr));
     const S3 vo = q.v;
     const V3 Lo = q.L;
@@ -137,12 +138,13 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, int 
             V3 ddv = plain(vf - vf_old), ddl = Lf - Lf_old, vfp = plain(vf);
             double s_dv = ro.valid ? dot(ddv, ddv) : 0., s_fv = ro.valid ? dot(vfp, vfp) : 0.;
             s_dv = group_sum(s_dv, W); s_fv = group_sum(s_fv, W);
-            bool okv = s_dv / s_fv < kEps2;
+            // delta/total < eps^2 decided as delta < eps^2 * total (no division; NaN compares false either way)
+            bool okv = s_dv < kEps2 * s_fv;
             bool okl = true;
             if (P.spin_on) {
                 double s_dl = ro.valid ? dot(ddl, ddl) : 0., s_fl = ro.valid ? dot(Lf, Lf) : 0.;
                 s_dl = group_sum(s_dl, W); s_fl = group_sum(s_fl, W);
-                okl = s_dl / s_fl < kEps2;
+                okl = s_dl < kEps2 * s_fl;
             }
             conv_now = okv && okl;
         }
@@ -202,8 +204,12 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, int gb,
     return acc;
 }
 
+#ifndef PB_MIN_BLOCKS
+#define PB_MIN_BLOCKS 2
+#endif
+
 template <int COORD, int GR>
-__global__ void __launch_bounds__(PB_BLOCK) whfast_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
+__global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
     const int W = P.W;
     const int n = P.n_bodies;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,9 +244,10 @@ __global__ void __launch_bounds__(PB_BLOCK) whfast_steps_kernel(const __grid_con
             q.m = P.mass[i]; q.mg = P.mass_g[i]; q.R = P.radius[i]; q.rg2 = P.rg2[i]; q.I = P.moi[i];
             q.sigma = P.sigma[i]; q.k2t = P.k2t[i]; q.k2f = P.k2f[i];
         } else {
+            // padding lanes: finite, non-zero dummies (never read by live lanes, never stored)
             q.r = s3(sd(1. + b), sd(0.), sd(0.)); q.v = s3(sd(0.), sd(0.), sd(0.));
-            q.L = v3(0., 0., 0.); q.s = v3(0., 0., 0.); q.ev = v3(0., 0., 0.); q.el = v3(0., 0., 0.);
-            q.m = 0.; q.mg = 0.; q.R = 0.; q.rg2 = 1.; q.I = 1.; q.sigma = 0.; q.k2t = 0.; q.k2f = 0.;
+            q.L = v3(0., 0., 1.); q.s = v3(0., 0., 1.); q.ev = v3(0., 0., 0.); q.el = v3(0., 0., 0.);
+            q.m = 1.; q.mg = 1.; q.R = 1.; q.rg2 = 1.; q.I = 1.; q.sigma = 0.; q.k2t = 0.; q.k2f = 0.;
         }
         if (sys_ok) {
             st.t = P.t[sys]; st.last_hist = P.last_hist[sys];
@@ -271,10 +278,16 @@ __global__ void __launch_bounds__(PB_BLOCK) whfast_steps_kernel(const __grid_con
             if (k == b) { eta_k = mtot; mu_k = mu; }
         }
     }
+    // per-body constants of the heliocentric transforms (whfast.rs:1015, 1101, 1112-1114), divided once
+    sd back_w = sd(1.), whds_f = sd(1.);
+    if (COORD == PB200_COORD_WHDS) { whds_f = (M_s + m_s) / M_s; back_w = m_s / (M_s + m_s); }
+    if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) back_w = m_s / M_s;
+    const sd kepler_mu = COORD == PB200_COORD_JACOBI ? mu_k : (COORD == PB200_COORD_WHDS ? Mg_s + sd(q.mg) : Mg_s);
     const int first_other = P.host == 0 ? 1 : 0;
     const sd dt_s = sd(P.dt), hdt_s = sd(P.half_dt);
-    const sd zero = sd(0.);
+    const sd zero = sd(0.), one = sd(1.);
     const S3 zero3 = s3(zero, zero, zero);
+    const S3 one3 = s3(one, one, one);
 
 #pragma unroll 1
     for (unsigned long long step = 0; step < n_steps; step++) {
@@ -327,178 +340,146 @@ __global__ void __launch_bounds__(PB_BLOCK) whfast_steps_kernel(const __grid_con
         // internals needed by the NEXT snapshot's denergy_dt are those of this step's last evaluation
         const bool save_tides = (step + 1 == n_steps) || (__dadd_rn(st.last_hist, P.hist_period) <= __dadd_rn(st.t, P.dt));
 
-        // ---- first half of the velocity-dependent forces (whfast.rs:278)
-        midpoint<COORD, GR>(P, ro, gb, hl, b, alive, q, c, st.t, true, acc, st.warnings, false, sys);
-
-        // ---- first drift (whfast.rs:469-479)
-        S3 apos, avel;       // this body's alternative coordinates
-        S3 spos, svel;       // the host slot of the alternative coordinates (centre of mass), replicated in the group
-        const bool kwork = ro.planet && alive;
-        if (COORD == PB200_COORD_JACOBI) {
-            // inertial_to_jacobi_posvel (whfast.rs:889-933)
-            sd eta = M_s;
-            S3 s = eta * shfl3(q.r, hl), sv = eta * shfl3(q.v, hl);
-            apos = zero3; avel = zero3;
-            for (int k = 0; k < n; k++) {
-                if (k == P.host) continue;
-                sd mk = sd(shfl(q.m, gb + k));
-                S3 rk = shfl3(q.r, gb + k), vk = shfl3(q.v, gb + k);
-                sd ei = sd(1.) / eta;
-                eta = eta + mk;
-                sd pme = eta * ei;
-                S3 pk = rk - s * ei, wk = vk - sv * ei;
-                if (b == k) { apos = pk; avel = wk; }
-                s = s * pme + mk * pk; sv = sv * pme + mk * wk;
+        // One code instance of the midpoint serves both halves of the step (whfast.rs:278 and :293); the drift-kick-drift
+        // core runs between them. Likewise one instance of the Kepler solver serves both drifts.
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            if (half == 1) {
+                S3 apos, avel;       // this body's alternative coordinates
+                S3 spos, svel;       // the host slot of the alternative coordinates (centre of mass), replicated in the group
+                S3 anew_s = zero3;
+                const bool kwork = ro.planet && alive;
+                // ---- inertial -> alternative coordinates (whfast.rs:881-1023)
+                if (COORD == PB200_COORD_JACOBI) {
+                    sd eta = M_s;
+                    S3 s = eta * shfl3(q.r, hl), sv = eta * shfl3(q.v, hl);
+                    apos = one3; avel = zero3;
+                    for (int k = 0; k < n; k++) {
+                        if (k == P.host) continue;
+                        sd mk = sd(shfl(q.m, gb + k));
+                        S3 rk = shfl3(q.r, gb + k), vk = shfl3(q.v, gb + k);
+                        sd ei = one / eta;
+                        eta = eta + mk;
+                        sd pme = eta * ei;
+                        S3 pk = rk - s * ei, wk = vk - sv * ei;
+                        if (b == k) { apos = pk; avel = wk; }
+                        s = s * pme + mk * pk; sv = sv * pme + mk * wk;
+                    }
+                    sd mi = one / eta;
+                    spos = s * mi; svel = sv * mi;
+                } else {
+                    // host first, then the others (whfast.rs:986-995)
+                    S3 mr = q.r * m_s, mv = q.v * m_s;
+                    S3 sr = ordered_sum_others(zero3 + shfl3(mr, hl), mr, gb, n, P.host);
+                    S3 sv = ordered_sum_others(zero3 + shfl3(mv, hl), mv, gb, n, P.host);
+                    spos = sr / mtot; svel = sv / mtot;
+                    apos = q.r - shfl3(q.r, hl);
+                    avel = q.v - svel;
+                    if (COORD == PB200_COORD_WHDS) avel = avel * whds_f;
+                }
+#pragma unroll 1
+                for (int phase = 0; phase < 2; phase++) {
+                    if (phase == 1) {
+                        // ---- kick (whfast.rs:558-625)
+                        if (COORD == PB200_COORD_JACOBI) {
+                            // inertial_to_jacobi_acc (whfast.rs:935-963) + jacobi_interaction_step (:566-592)
+                            sd eta = M_s;
+                            S3 sa = eta * shfl3(anew_s, hl);
+                            S3 aacc = zero3;
+                            for (int k = 0; k < n; k++) {
+                                if (k == P.host) continue;
+                                sd mk = sd(shfl(q.m, gb + k));
+                                S3 ak = shfl3(anew_s, gb + k);
+                                sd ei = one / eta;
+                                eta = eta + mk;
+                                sd pme = eta * ei;
+                                S3 ck = ak - sa * ei;
+                                if (b == k) aacc = ck;
+                                sa = sa * pme + mk * ck;
+                            }
+                            avel = avel + dt_s * aacc;
+                            if (b != first_other) {
+                                sd rj2i = one / (apos.x * apos.x + apos.y * apos.y + apos.z * apos.z + sd(1e-12));
+                                sd rji = ssqrt(rj2i);
+                                sd rj3im = rji * rj2i * sd(kG) * eta_k;
+                                sd prefac = dt_s * rj3im;
+                                avel = avel + prefac * apos;
+                            }
+                        } else if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
+                            avel = avel + dt_s * anew_s;
+                        } else {
+                            sd f = M_s + m_s;
+                            avel = s3(avel.x + dt_s * f * anew_s.x / M_s, avel.y + dt_s * f * anew_s.y / M_s, avel.z + dt_s * f * anew_s.z / M_s);
+                        }
+                    }
+                    // ---- jump (whfast.rs:495-556): before the Kepler drift in the second half, after it in the first
+                    for (int jump_slot = 0; jump_slot < 2; jump_slot++) {
+                        if (jump_slot == 1) {
+                            kepler_step(kwork, apos, avel, kepler_mu, hdt_s, st.tswarn, st.warnings);
+                            spos = spos + hdt_s * svel;
+                        }
+                        if (COORD != PB200_COORD_JACOBI && jump_slot != phase) {
+                            if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
+                                S3 p = ordered_sum_others(zero3, m_s * avel, gb, n, P.host);
+                                apos = s3(apos.x + hdt_s * p.x / M_s, apos.y + hdt_s * p.y / M_s, apos.z + hdt_s * p.z / M_s);
+                            } else {
+                                sd f = M_s + m_s;
+                                S3 term = s3(m_s * avel.x / f, m_s * avel.y / f, m_s * avel.z / f);
+                                S3 p = ordered_sum_others(zero3, term, gb, n, P.host);
+                                apos = s3(apos.x + hdt_s * (p.x - term.x), apos.y + hdt_s * (p.y - term.y), apos.z + hdt_s * (p.z - term.z));
+                            }
+                        }
+                    }
+                    // ---- alternative -> inertial (whfast.rs:1026-1155)
+                    if (COORD == PB200_COORD_JACOBI) {
+                        sd et = mtot;
+                        S3 s = et * spos, sv = et * svel;
+                        S3 nr = q.r, nv = q.v;
+                        for (int k = n - 1; k >= 0; k--) {
+                            if (k == P.host) continue;
+                            sd mk = sd(shfl(q.m, gb + k));
+                            S3 pk = shfl3(apos, gb + k), wk = shfl3(avel, gb + k);
+                            sd ei = one / et;
+                            s = (s - mk * pk) * ei; sv = (sv - mk * wk) * ei;
+                            if (b == k) { nr = pk + s; nv = wk + sv; }
+                            et = et - mk;
+                            s = s * et; sv = sv * et;
+                        }
+                        if (ro.host) { sd mi = one / et; nr = s * mi; nv = sv * mi; }
+                        if (alive) { q.r = nr; q.v = nv; }
+                    } else {
+                        // positions (whfast.rs:1128-1155); the host lane divides a dummy instead of its zero vector
+                        S3 num = ro.planet ? apos * m_s : one3;
+                        S3 term = num / mtot;
+                        S3 star_r = ordered_diff_others(spos, term, gb, n, P.host);
+                        S3 nr = ro.host ? star_r : apos + star_r;
+                        if (alive) q.r = nr;
+                        if (phase == 1) {
+                            // velocities (whfast.rs:1090-1126); those of the first drift are dead (the kick overwrites them)
+                            S3 nv = (COORD == PB200_COORD_WHDS ? avel / whds_f : avel) + svel;
+                            S3 star_v = ordered_diff_others(svel, avel * back_w, gb, n, P.host);
+                            if (ro.host) nv = star_v;
+                            if (alive) q.v = nv;
+                        }
+                    }
+                    if (phase == 0) {
+                        // ---- gravity (whfast.rs:281)
+                        int fail;
+                        anew_s = gravity<COORD>(P, ro, gb, b, sys, q, fail);
+                        V3 anew = plain(anew_s);
+                        // group-wide failure: lowest body index wins, like the reference's loop order
+                        int code = (ro.valid && fail) ? ((b << 4) | fail) : 0x7fffffff;
+                        for (int off = W >> 1; off > 0; off >>= 1) { int o = __shfl_xor_sync(FULL, code, off); code = o < code ? o : code; }
+                        if (alive && code != 0x7fffffff) {
+                            st.status = code & 15; st.event_step = st.steps_done; alive = false;
+                            store_lane(P, ro, sys, b, q, anew, st);
+                        }
+                        if (alive) acc = anew;
+                    }
+                }
             }
-            sd mi = sd(1.) / eta;
-            spos = s * mi; svel = sv * mi;
-            kepler_step(kwork, apos, avel, mu_k, hdt_s, st.tswarn, st.warnings);
-            spos = spos + hdt_s * svel;
-        } else {
-            // inertial_to_whds_and_democratic_heliocentric_posvel (whfast.rs:973-1023): host first, then the others
-            S3 mr = q.r * m_s, mv = q.v * m_s;
-            S3 sr = ordered_sum_others(zero3 + shfl3(mr, hl), mr, gb, n, P.host);
-            S3 sv = ordered_sum_others(zero3 + shfl3(mv, hl), mv, gb, n, P.host);
-            spos = sr / mtot; svel = sv / mtot;
-            apos = q.r - shfl3(q.r, hl);
-            avel = q.v - svel;
-            sd mu = Mg_s;
-            if (COORD == PB200_COORD_WHDS) {
-                sd f = (M_s + m_s) / M_s;
-                avel = avel * f;
-                mu = Mg_s + sd(q.mg);
-            }
-            kepler_step(kwork, apos, avel, mu, hdt_s, st.tswarn, st.warnings);
-            spos = spos + hdt_s * svel;
-            // jump_step (whfast.rs:507-556)
-            if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
-                S3 p = ordered_sum_others(zero3, m_s * avel, gb, n, P.host);
-                apos = s3(apos.x + hdt_s * p.x / M_s, apos.y + hdt_s * p.y / M_s, apos.z + hdt_s * p.z / M_s);
-            } else {
-                sd f = M_s + m_s;
-                S3 term = s3(m_s * avel.x / f, m_s * avel.y / f, m_s * avel.z / f);
-                S3 p = ordered_sum_others(zero3, term, gb, n, P.host);
-                apos = s3(apos.x + hdt_s * (p.x - term.x), apos.y + hdt_s * (p.y - term.y), apos.z + hdt_s * (p.z - term.z));
-            }
+            midpoint<COORD, GR>(P, ro, gb, hl, b, alive, q, c, st.t, half == 0, acc, st.warnings, half == 1 && save_tides, sys);
         }
-        // alternative_to_inertial (positions; the velocities of this call are dead: the kick overwrites them)
-        if (COORD == PB200_COORD_JACOBI) {
-            sd eta = mtot;
-            S3 s = eta * spos;
-            for (int k = n - 1; k >= 0; k--) {
-                if (k == P.host) continue;
-                sd mk = sd(shfl(q.m, gb + k));
-                S3 pk = shfl3(apos, gb + k);
-                sd ei = sd(1.) / eta;
-                s = (s - mk * pk) * ei;
-                if (b == k) q.r = pk + s;
-                eta = eta - mk;
-                s = s * eta;
-            }
-            if (ro.host) q.r = s * (sd(1.) / eta);
-        } else {
-            // whds_and_democratic_heliocentric_to_inertial_pos (whfast.rs:1128-1155)
-            S3 term = s3(apos.x * m_s / mtot, apos.y * m_s / mtot, apos.z * m_s / mtot);
-            S3 star_r = ordered_diff_others(spos, term, gb, n, P.host);
-            q.r = ro.host ? star_r : apos + star_r;
-        }
-
-        // ---- gravity (whfast.rs:281)
-        int fail;
-        S3 anew_s = gravity<COORD>(P, ro, gb, b, sys, q, fail);
-        V3 anew = plain(anew_s);
-        // group-wide failure: lowest body index wins, like the reference's loop order
-        {
-            int code = (ro.valid && fail) ? ((b << 4) | fail) : 0x7fffffff;
-            for (int off = W >> 1; off > 0; off >>= 1) { int o = __shfl_xor_sync(FULL, code, off); code = o < code ? o : code; }
-            if (alive && code != 0x7fffffff) {
-                st.status = code & 15; st.event_step = st.steps_done; alive = false;
-                store_lane(P, ro, sys, b, q, anew, st);
-            }
-        }
-        if (alive) acc = anew;
-
-        // ---- kick + second drift (whfast.rs:482-491)
-        if (COORD == PB200_COORD_JACOBI) {
-            // inertial_to_jacobi_acc (whfast.rs:935-963) + jacobi_interaction_step (:566-592)
-            sd eta = M_s;
-            S3 sa = eta * shfl3(anew_s, hl);
-            S3 aacc = zero3;
-            for (int k = 0; k < n; k++) {
-                if (k == P.host) continue;
-                sd mk = sd(shfl(q.m, gb + k));
-                S3 ak = shfl3(anew_s, gb + k);
-                sd ei = sd(1.) / eta;
-                eta = eta + mk;
-                sd pme = eta * ei;
-                S3 ck = ak - sa * ei;
-                if (b == k) aacc = ck;
-                sa = sa * pme + mk * ck;
-            }
-            avel = avel + dt_s * aacc;
-            if (b != first_other) {
-                sd rj2i = sd(1.) / (apos.x * apos.x + apos.y * apos.y + apos.z * apos.z + sd(1e-12));
-                sd rji = ssqrt(rj2i);
-                sd rj3im = rji * rj2i * sd(kG) * eta_k;
-                sd prefac = dt_s * rj3im;
-                avel = avel + prefac * apos;
-            }
-            kepler_step(kwork, apos, avel, mu_k, hdt_s, st.tswarn, st.warnings);
-            spos = spos + hdt_s * svel;
-            // jacobi_to_inertial_posvel (whfast.rs:1034-1080)
-            sd et = mtot;
-            S3 s = et * spos, sv = et * svel;
-            S3 nr = q.r, nv = q.v;
-            for (int k = n - 1; k >= 0; k--) {
-                if (k == P.host) continue;
-                sd mk = sd(shfl(q.m, gb + k));
-                S3 pk = shfl3(apos, gb + k), wk = shfl3(avel, gb + k);
-                sd ei = sd(1.) / et;
-                s = (s - mk * pk) * ei; sv = (sv - mk * wk) * ei;
-                if (b == k) { nr = pk + s; nv = wk + sv; }
-                et = et - mk;
-                s = s * et; sv = sv * et;
-            }
-            if (ro.host) { sd mi = sd(1.) / et; nr = s * mi; nv = sv * mi; }
-            if (alive) { q.r = nr; q.v = nv; }
-        } else {
-            sd mu = Mg_s;
-            if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
-                // democratic_heliocentric_interaction_step (whfast.rs:594-608) + jump
-                avel = avel + dt_s * anew_s;
-                S3 p = ordered_sum_others(zero3, m_s * avel, gb, n, P.host);
-                apos = s3(apos.x + hdt_s * p.x / M_s, apos.y + hdt_s * p.y / M_s, apos.z + hdt_s * p.z / M_s);
-            } else {
-                // whds_interaction_step (whfast.rs:610-625) + jump
-                sd f = M_s + m_s;
-                avel = s3(avel.x + dt_s * f * anew_s.x / M_s, avel.y + dt_s * f * anew_s.y / M_s, avel.z + dt_s * f * anew_s.z / M_s);
-                S3 term = s3(m_s * avel.x / f, m_s * avel.y / f, m_s * avel.z / f);
-                S3 p = ordered_sum_others(zero3, term, gb, n, P.host);
-                apos = s3(apos.x + hdt_s * (p.x - term.x), apos.y + hdt_s * (p.y - term.y), apos.z + hdt_s * (p.z - term.z));
-                mu = Mg_s + sd(q.mg);
-            }
-            kepler_step(kwork, apos, avel, mu, hdt_s, st.tswarn, st.warnings);
-            spos = spos + hdt_s * svel;
-            // whds_and_democratic_heliocentric_to_inertial_posvel (whfast.rs:1090-1155)
-            S3 term = s3(apos.x * m_s / mtot, apos.y * m_s / mtot, apos.z * m_s / mtot);
-            S3 star_r = ordered_diff_others(spos, term, gb, n, P.host);
-            S3 nr = ro.host ? star_r : apos + star_r;
-            S3 nv, back;
-            if (COORD == PB200_COORD_WHDS) {
-                sd f = (M_s + m_s) / M_s;
-                nv = avel / f + svel;
-                back = avel * (m_s / (M_s + m_s));
-            } else {
-                nv = avel + svel;
-                back = avel * (m_s / M_s);
-            }
-            S3 star_v = ordered_diff_others(svel, back, gb, n, P.host);
-            if (ro.host) nv = star_v;
-            if (alive) { q.r = nr; q.v = nv; }
-        }
-
-        // ---- second half of the velocity-dependent forces (whfast.rs:293)
-        midpoint<COORD, GR>(P, ro, gb, hl, b, alive, q, c, st.t, false, acc, st.warnings, save_tides, sys);
 
         if (alive) {
             st.t = __dadd_rn(st.t, P.dt);

@@ -169,17 +169,34 @@ def test_status_completed_and_frozen(E):
         assert np.all(it == n)
 
 
-def test_collision_sets_status_instead_of_panicking(E):
-    from posidonius_b200 import abi
+def _displaced_case(name, factor):
+    """Config `name` with body 1 moved to `factor` x its heliocentric distance (same direction)."""
     from posidonius_b200.case import case_from_dict
-    d = config_case("c2_case3")
-    case, tables = case_from_dict(d)
-    case.bodies[1].radius = 0.5  # planet radius larger than its orbital distance: overlap at the first gravity call
+    case, tables = case_from_dict(config_case(name))
+    h = case.host_most_massive
+    for c in range(3):
+        rel = case.bodies[1].inertial_position[c] - case.bodies[h].inertial_position[c]
+        case.bodies[1].inertial_position[c] = case.bodies[h].inertial_position[c] + factor * rel
+    return case, tables
+
+
+@pytest.mark.parametrize("factor,expected", [(0.1, "ROCHE"), (1.0e4, "EJECTED")])
+def test_physical_failures_set_status_instead_of_panicking(E, factor, expected):
+    """universe.rs:224-238 panics; the ensemble records a status word and freezes the system. Same verdict as the oracle."""
+    from oracle.binding import OracleSystem
+    from posidonius_b200 import abi
+    case, tables = _displaced_case("c2_case3", factor)
+    o = OracleSystem(case, tables)
+    o.initialize_physical_values()
+    o.iterate(5)
+    ost, _, oit = o.status()
+    want = {"ROCHE": abi.STATUS_ROCHE_DESTROYED, "EJECTED": abi.STATUS_EJECTED}[expected]
+    assert ost == want and oit == 0
     with E.Ensemble(case, tables, n_systems=4) as ens:
         ens.initialize_physical_values()
         ens.iterate(5)
         st, _, it = ens.status()
-        assert np.all((st == abi.STATUS_COLLISION) | (st == abi.STATUS_ROCHE_DESTROYED)) and np.all(it == 0)
+        assert np.all(st == want) and np.all(it == 0)
 
 
 def test_run_host_roundtrip_equals_device_resident_run(E):
