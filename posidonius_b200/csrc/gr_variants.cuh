@@ -9,18 +9,19 @@ namespace pb200 {
 
 // Newtonian inertial accelerations with the terms WHFast ignored re-added (general_relativity.rs:641-678).
 // jacobi_coords: IgnoreGravityTerms::WHFastOne (only the first non-host particle is re-added), else WHFastTwo.
-__device__ __forceinline__ V3 gr_newtonian(const KParams& P, const Roles& ro, int gb, int hl, int b, const Lane& q, V3 hr,
+__device__ __forceinline__ V3 gr_newtonian(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, const Lane& q, V3 hr,
                                            V3 acc_newton, bool jacobi_coords) {
+    const double q_m = cold.get(K_M);
     const int first_other = P.host == 0 ? 1 : 0;
     bool included = ro.planet && (!jacobi_coords || b == first_other);
     V3 rh = shfl3(plain(q.r), hl);
-    double M = shfl(q.m, hl);
+    double M = shfl(q_m, hl);
     // Q9: host INERTIAL position minus the particle's HELIOCENTRIC position
     V3 dx = rh - hr;
     double r2 = dot(dx, dx);
     double r = sqrt(r2);
     double prefac = kG / (r2 * r);
-    V3 to_host = included ? (-(prefac * q.m)) * dx : v3(0., 0., 0.);
+    V3 to_host = included ? (-(prefac * q_m)) * dx : v3(0., 0., 0.);
     V3 own = included ? (prefac * M) * dx : v3(0., 0., 0.);
     // ordered sum over the non-host bodies, as the reference accumulates
     V3 hsum = v3(0., 0., 0.);
@@ -35,16 +36,17 @@ __device__ __forceinline__ V3 gr_newtonian(const KParams& P, const Roles& ro, in
 }
 
 // general_relativity.rs:461-636
-__device__ __forceinline__ void gr_anderson1975(const KParams& P, const Roles& ro, int gb, int hl, int b, const Lane& q, V3 hr,
+__device__ __forceinline__ void gr_anderson1975(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, const Lane& q, V3 hr,
                                                 V3 acc_newton, bool jacobi_coords, V3& a_out) {
-    V3 an = gr_newtonian(P, ro, gb, hl, b, q, hr, acc_newton, jacobi_coords);
+    const double q_m = cold.get(K_M), q_mg = cold.get(K_MG);
+    V3 an = gr_newtonian(P, ro, cold, gb, hl, b, q, hr, acc_newton, jacobi_coords);
     // inertial -> Jacobi over the OrbitingBody particles (:539-602); every lane carries the running sums
-    double eta = shfl(q.m, hl);
+    double eta = shfl(q_m, hl);
     V3 s = eta * shfl3(plain(q.r), hl), sv = eta * shfl3(plain(q.v), hl), sa = eta * shfl3(an, hl);
     V3 jp = v3(0., 0., 0.), jv = v3(0., 0., 0.), ja = v3(0., 0., 0.);
     for (int k = 0; k < P.n_bodies; k++) {
         if (k == P.host || !((P.gr_orbiting >> k) & 1u)) continue;
-        double mk = shfl(q.m, gb + k);
+        double mk = shfl(q_m, gb + k);
         V3 rk = shfl3(plain(q.r), gb + k), vk = shfl3(plain(q.v), gb + k), ak = shfl3(an, gb + k);
         double ei = 1. / eta;
         eta += mk;
@@ -54,7 +56,7 @@ __device__ __forceinline__ void gr_anderson1975(const KParams& P, const Roles& r
         s = pme * s + mk * pk; sv = pme * sv + mk * wk; sa = pme * sa + mk * ck;
     }
     const double jacobi_star_mass = eta;
-    const double mu = shfl(q.mg, hl);
+    const double mu = shfl(q_mg, hl);
     // fixed point on the velocity (:478-516)
     {
         V3 vi = jv;
@@ -88,7 +90,7 @@ __device__ __forceinline__ void gr_anderson1975(const KParams& P, const Roles& r
     V3 mine = v3(0., 0., 0.);
     for (int k = P.n_bodies - 1; k >= 0; k--) {
         if (k == P.host || !((P.gr_orbiting >> k) & 1u)) continue;
-        double mk = shfl(q.m, gb + k);
+        double mk = shfl(q_m, gb + k);
         V3 jk = shfl3(ja, gb + k);
         double ei = 1. / eta;
         sacc = ei * (sacc - mk * jk);
@@ -101,9 +103,10 @@ __device__ __forceinline__ void gr_anderson1975(const KParams& P, const Roles& r
 }
 
 // general_relativity.rs:683-895
-__device__ __forceinline__ void gr_newhall1983(const KParams& P, const Roles& ro, int gb, int hl, int b, const Lane& q, V3 hr,
+__device__ __forceinline__ void gr_newhall1983(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, const Lane& q, V3 hr,
                                                V3 acc_newton, bool jacobi_coords, V3& a_out) {
-    V3 an = gr_newtonian(P, ro, gb, hl, b, q, hr, acc_newton, jacobi_coords);
+    const double q_m = cold.get(K_M);
+    V3 an = gr_newtonian(P, ro, cold, gb, hl, b, q, hr, acc_newton, jacobi_coords);
     const int n = P.n_bodies;
     const bool en_i = (P.gr_enabled >> b) & 1u;
     const V3 qr = plain(q.r), qv = plain(q.v);
@@ -112,7 +115,7 @@ __device__ __forceinline__ void gr_newhall1983(const KParams& P, const Roles& ro
     for (int kk = -1; kk < n; kk++) {
         int k = kk < 0 ? P.host : kk;
         if (kk == P.host) continue;
-        double mk = shfl(q.m, gb + k);
+        double mk = shfl(q_m, gb + k);
         V3 rk = shfl3(qr, gb + k);
         if (k == b) continue;
         V3 dr = qr - rk;
@@ -123,7 +126,7 @@ __device__ __forceinline__ void gr_newhall1983(const KParams& P, const Roles& ro
     for (int kk = -1; kk < n; kk++) {
         int j = kk < 0 ? P.host : kk;
         if (kk == P.host) continue;
-        double mj = shfl(q.m, gb + j);
+        double mj = shfl(q_m, gb + j);
         V3 rj = shfl3(qr, gb + j), vj = shfl3(qv, gb + j);
         double potj = shfl(pot, gb + j);
         bool en_j = (P.gr_enabled >> j) & 1u;
@@ -157,7 +160,7 @@ __device__ __forceinline__ void gr_newhall1983(const KParams& P, const Roles& ro
         for (int kk = -1; kk < n; kk++) {
             int j = kk < 0 ? P.host : kk;
             if (kk == P.host) continue;
-            double mj = shfl(q.m, gb + j);
+            double mj = shfl(q_m, gb + j);
             V3 rj = shfl3(qr, gb + j);
             V3 tj = shfl3(tot, gb + j);
             bool en_j = (P.gr_enabled >> j) & 1u;

@@ -27,6 +27,16 @@ namespace pb200 {
 
 // Integrator::initialize_physical_values (whfast.rs:226-233): evolving quantities at t, spin = L/I
 // (universe.rs:305-316) and the Roche radii table (universe.rs:177-196).
+// evolved (radius, rg2) of body b at time t (effects/evolution.rs:458-476); inputs returned unchanged when NonEvolving
+__device__ __forceinline__ void evolved_values(const KParams& P, int b, double t, double& R, double& rg2) {
+    int ti = P.evo_table[b];
+    if (ti < 0) return;
+    const DevTable& T = P.tables[ti];
+    int i = table_upper(T.time, T.n_rows, t);
+    if (T.interp_radius) R = table_interp(T.time, T.radius, T.n_rows, i, t);
+    if (T.interp_rg2) rg2 = table_interp(T.time, T.rg2, T.n_rows, i, t);
+}
+
 __global__ void init_physical_kernel(const __grid_constant__ KParams P) {
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t ns = (size_t)P.n_sys;
@@ -34,26 +44,28 @@ __global__ void init_physical_kernel(const __grid_constant__ KParams P) {
     const size_t sys = gtid % ns;
     const int b = (int)(gtid / ns);
     const size_t i = (size_t)b * ns + sys, cs = (size_t)P.n_bodies * ns;
-    Roles ro; ro.valid = true; ro.host = b == P.host; ro.planet = !ro.host; ro.t_on = ro.f_on = ro.g_on = false;
-    Lane q;
-    q.m = P.mass[i]; q.R = P.radius[i]; q.rg2 = P.rg2[i]; q.I = P.moi[i];
-    if (P.flags & FLAG_EVO) evolve_lane(P, ro, b, P.t[sys], q);
-    P.radius[i] = q.R; P.rg2[i] = q.rg2; P.moi[i] = q.I;
-    double invI = 1. / q.I;
+    const double m = P.mass[i];
+    const double R0 = P.radius[i], g0 = P.rg2[i];
+    double R = R0, g = g0, I = P.moi[i];
+    if (P.flags & FLAG_EVO) evolved_values(P, b, P.t[sys], R, g);
+    if (R != R0 || g != g0) I = (sd(m) * sd(g) * (sd(R) * sd(R))).v;   // evolution.rs:527-531
+    double invI = 1. / I;
     P.spin[i] = P.L[i] * invI; P.spin[i + cs] = P.L[i + cs] * invI; P.spin[i + 2 * cs] = P.L[i + 2 * cs] * invI;
-    // Roche radii use the radii AFTER the evolution update (whfast.rs:231-232). Body j's evolved radius is recomputed
-    // here instead of read back, so no ordering between threads is needed (the update depends on t only).
+    // Roche radii use the radii AFTER the evolution update (whfast.rs:231-232). Body j's evolved radius is recomputed here:
+    // an evolving body's radius depends on t only and a non-evolving one is never rewritten, so it does not matter
+    // whether j's thread has already stored its value — no ordering between threads is needed.
     double* roche = const_cast<double*>(P.roche);
     for (int j = 0; j < P.n_bodies; j++) {
         if (j == b) continue;
         const size_t ij = (size_t)j * ns + sys;
-        Lane t; t.m = P.mass[ij]; t.R = P.radius[ij]; t.rg2 = 1.; t.I = 1.;
-        if (P.flags & FLAG_EVO) evolve_lane(P, ro, j, P.t[sys], t);
+        double mj = P.mass[ij], Rj = P.radius[ij], gj = 1.;
+        if (P.flags & FLAG_EVO) evolved_values(P, j, P.t[sys], Rj, gj);
         double rr;
-        if (q.m > t.m) rr = (t.R / 0.462) * cbrt(q.m / t.m);
-        else rr = (q.R / 0.462) * cbrt(t.m / q.m);
+        if (m > mj) rr = (Rj / 0.462) * cbrt(m / mj);
+        else rr = (R / 0.462) * cbrt(mj / m);
         roche[((size_t)(b * P.n_bodies + j)) * ns + sys] = rr;
     }
+    P.radius[i] = R; P.rg2[i] = g; P.moi[i] = I;
 }
 
 // Universe::compute_total_energy / compute_total_angular_momentum (universe.rs:625-658) after a heliocentric refresh.
@@ -179,15 +191,27 @@ static bool is_dynamical_tide_evolution(const pb200_body_t& b) {
            (b.evolution_type == PB200_EVO_LECONTECHABRIER2013 && b.evolution_parameter != 0.);
 }
 
+template <int COORD, int GR>
+static cudaError_t launch_one(pb200_ensemble* e, unsigned grid, unsigned long long n) {
+    // the cold slots need more than the default 48 KB of dynamic shared memory
+    static thread_local int configured_device = -1;
+    if (configured_device != e->device) {
+        cudaError_t err = cudaFuncSetAttribute(whfast_steps_kernel<COORD, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
+        if (err != cudaSuccess) return err;
+        configured_device = e->device;
+    }
+    whfast_steps_kernel<COORD, GR><<<grid, PB_BLOCK, PB_SMEM_BYTES, e->stream>>>(e->P, n);
+    return cudaGetLastError();
+}
+
 template <int COORD>
 static cudaError_t launch_gr(pb200_ensemble* e, unsigned grid, unsigned long long n) {
     switch (e->gr) {
-        case PB200_GR_KIDDER1995: whfast_steps_kernel<COORD, PB200_GR_KIDDER1995><<<grid, PB_BLOCK, 0, e->stream>>>(e->P, n); break;
-        case PB200_GR_ANDERSON1975: whfast_steps_kernel<COORD, PB200_GR_ANDERSON1975><<<grid, PB_BLOCK, 0, e->stream>>>(e->P, n); break;
-        case PB200_GR_NEWHALL1983: whfast_steps_kernel<COORD, PB200_GR_NEWHALL1983><<<grid, PB_BLOCK, 0, e->stream>>>(e->P, n); break;
-        default: whfast_steps_kernel<COORD, PB200_GR_DISABLED><<<grid, PB_BLOCK, 0, e->stream>>>(e->P, n); break;
+        case PB200_GR_KIDDER1995: return launch_one<COORD, PB200_GR_KIDDER1995>(e, grid, n);
+        case PB200_GR_ANDERSON1975: return launch_one<COORD, PB200_GR_ANDERSON1975>(e, grid, n);
+        case PB200_GR_NEWHALL1983: return launch_one<COORD, PB200_GR_NEWHALL1983>(e, grid, n);
+        default: return launch_one<COORD, PB200_GR_DISABLED>(e, grid, n);
     }
-    return cudaGetLastError();
 }
 
 extern "C" {

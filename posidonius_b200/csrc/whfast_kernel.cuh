@@ -282,50 +282,51 @@ __device__ __forceinline__ double table_interp(const double* __restrict__ time, 
     return (sd(__ldg(y + i - 1)) * (sd(1.) - pct) + sd(__ldg(y + i)) * pct).v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register / shared-memory split. Only what every phase touches lives in registers (Lane). Everything that is
+// read once per evaluation or once per step — per-system constants, the Kahan residuals, the midpoint's
+// originals, the position while the midpoint runs — lives in per-thread shared-memory slots (Cold), addressed
+// [slot][thread] so that a warp's access is one conflict-free 256-byte row. `volatile` keeps the compiler from
+// forwarding the stored values back into registers.
+#ifndef PB_BLOCK
+#define PB_BLOCK 128
+#endif
+
+enum ColdSlot : int {
+    // Kahan residuals (whfast.rs:117-119) and the midpoint's working set (whfast.rs:333-337)
+    S_EVX, S_EVY, S_EVZ, S_ELX, S_ELY, S_ELZ,
+    S_VOX, S_VOY, S_VOZ, S_LOX, S_LOY, S_LOZ,
+    S_DVX, S_DVY, S_DVZ, S_DLX, S_DLY, S_DLZ,
+    S_RX, S_RY, S_RZ,            // inertial position while the midpoint runs
+    S_AX, S_AY, S_AZ,            // Newtonian acceleration of the last gravity evaluation
+    // body parameters
+    K_M, K_MG, K_R, K_I,
+    // constants of the perturbation forces (every division with step-invariant operands is done once)
+    C_INVI, C_AS, C_AP, C_BK, C_KS, C_KP, C_IH, C_INVM, C_INVMH, C_MH, C_MGS, C_GRF, C_MURED, C_MD, C_MOM, C_FMS, C_FMP,
+    // constants of the coordinate transforms (strict)
+    K_MH, K_MGH, K_MTOT, K_KMU, K_BACKW, K_WHDSF, K_ETAK,
+    N_COLD_SLOTS
+};
+
+struct Cold {
+    volatile double* base;  // shared memory + threadIdx.x
+    __device__ __forceinline__ double get(int slot) const { return base[slot * PB_BLOCK]; }
+    __device__ __forceinline__ void set(int slot, double v) const { base[slot * PB_BLOCK] = v; }
+    __device__ __forceinline__ V3 get3(int slot) const { return v3(get(slot), get(slot + 1), get(slot + 2)); }
+    __device__ __forceinline__ void set3(int slot, V3 v) const { set(slot, v.x); set(slot + 1, v.y); set(slot + 2, v.z); }
+};
+
 // Per-lane register state.
 struct Lane {
     S3 r, v;            // inertial position / velocity (strict arithmetic only)
     V3 L, s;            // angular momentum, spin (of the previous evaluation)
-    V3 ev, el;          // Kahan residuals (whfast.rs:117-119)
-    double m, mg, R, rg2, I;
-    double sigma, k2t, k2f;
 };
 __device__ __forceinline__ V3 plain(S3 a) { return v3(a.x.v, a.y.v, a.z.v); }
 __device__ __forceinline__ S3 strict(V3 a) { return s3(sd(a.x), sd(a.y), sd(a.z)); }
 __device__ __forceinline__ S3 shfl3(S3 a, int src) { return s3(sd(shfl(a.x.v, src)), sd(shfl(a.y.v, src)), sd(shfl(a.z.v, src))); }
 __device__ __forceinline__ sd shfl(sd a, int src) { return sd(shfl(a.v, src)); }
 
-// per-system constants derived from masses/radii (recomputed only when the radius evolves): every division whose
-// operands do not change between evaluations is done here once
-struct Consts {
-    double invI;
-    double As, Ap, Bk;   // tides: 4.5 m^2 R*^10 sigma*, 4.5 M^2 R^10 sigma, 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2)
-    double Ks, Kp;       // flattening: m k2f* R*^5, M k2f R^5
-    double M, Mg, Ih;    // host mass, mass_g, moment of inertia
-    double inv_m, inv_M; // 1/m, 1/M
-    double mgs, grf;     // GR: Mg + mg, factor = Mg mg / (Mg + mg)^2 (general_relativity.rs:98)
-    double mu_red;       // M m / (M + m)
-};
-
 __device__ __forceinline__ double pow5(double x) { double x2 = x * x; return x2 * x2 * x; }
-
-__device__ __forceinline__ void make_consts(const Lane& q, int hl, Consts& c) {
-    c.invI = 1. / q.I;
-    c.M = shfl(q.m, hl); c.Mg = shfl(q.mg, hl); c.Ih = shfl(q.I, hl);
-    double Rh5 = pow5(shfl(q.R, hl));
-    double R5 = pow5(q.R);
-    double sig_h = shfl(q.sigma, hl), k2t_h = shfl(q.k2t, hl), k2f_h = shfl(q.k2f, hl);
-    double m2 = q.m * q.m, M2 = c.M * c.M;
-    c.As = 4.5 * m2 * (Rh5 * Rh5) * sig_h;
-    c.Ap = 4.5 * M2 * (R5 * R5) * q.sigma;
-    c.Bk = 3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * q.k2t);
-    c.Ks = q.m * k2f_h * Rh5;
-    c.Kp = c.M * q.k2f * R5;
-    c.inv_m = 1. / q.m; c.inv_M = 1. / c.M;
-    c.mgs = c.Mg + q.mg;
-    c.grf = c.Mg * q.mg / (c.mgs * c.mgs);
-    c.mu_red = (c.M * q.m) / (c.M + q.m);
-}
 
 struct Roles {
     bool valid;     // lane belongs to a live system slot and b < n_bodies
@@ -334,20 +335,51 @@ struct Roles {
     bool t_on, f_on, g_on;  // OrbitingBody for tides / flattening / GR
 };
 
+// Derives the force constants from masses, radii and dissipation parameters (cold path: launch start and whenever a
+// radius evolves). sigma / k2 are fetched from global memory here, they are not kept on chip.
+__device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys) {
+    double sigma = 0., k2t = 0., k2f = 0.;
+    if (ro.valid) {
+        const size_t i = (size_t)b * (size_t)P.n_sys + sys;
+        sigma = P.sigma[i]; k2t = P.k2t[i]; k2f = P.k2f[i];
+    }
+    const double m = cold.get(K_M), mg = cold.get(K_MG), R = cold.get(K_R), I = cold.get(K_I);
+    const double M = shfl(m, hl), Mg = shfl(mg, hl), Ih = shfl(I, hl);
+    const double Rh5 = pow5(shfl(R, hl));
+    const double R5 = pow5(R);
+    const double sig_h = shfl(sigma, hl), k2t_h = shfl(k2t, hl), k2f_h = shfl(k2f, hl);
+    const double m2 = m * m, M2 = M * M;
+    cold.set(C_INVI, 1. / I);
+    cold.set(C_AS, 4.5 * m2 * (Rh5 * Rh5) * sig_h);               // 4.5 m^2 R*^10 sigma*   (constant_time_lag.rs:232-234)
+    cold.set(C_AP, 4.5 * M2 * (R5 * R5) * sigma);                 // 4.5 M^2 R^10 sigma     (constant_time_lag.rs:243-245)
+    cold.set(C_BK, 3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * k2t)); // 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2) (:283-285)
+    cold.set(C_KS, m * k2f_h * Rh5);                              // flattening: m k2f* R*^5 (oblate_spheroid.rs:37)
+    cold.set(C_KP, M * k2f * R5);                                 //             M k2f R^5   (oblate_spheroid.rs:42)
+    cold.set(C_IH, Ih);
+    cold.set(C_INVM, 1. / m); cold.set(C_INVMH, 1. / M); cold.set(C_MH, M);
+    const double mgs = Mg + mg;
+    cold.set(C_MGS, mgs);
+    cold.set(C_GRF, Mg * mg / (mgs * mgs));                       // general_relativity.rs:98
+    cold.set(C_MURED, (M * m) / (M + m));                         // general_relativity.rs:383
+    cold.set(C_MD, M - m);                                        // mass_factor * star_planet_mass (:319-321, 336)
+    cold.set(C_MOM, m / M);
+    cold.set(C_FMS, 2. + 1.5 * m / M);                            // :390
+    cold.set(C_FMP, 2. + 1.5 * M / m);                            // :419
+}
+
 // ---------------------------------------------------------------------------------------------
 // Universe::calculate_additional_effects for the lane's body at (hr, hv) with the current L
 // (universe.rs:428-614). Returns the inertial additional acceleration and dL/dt of THIS body;
 // host-lane values are the group reductions.
 template <int GR>
-__device__ __forceinline__ void additional_effects(const KParams& P, const Roles& ro, int hl, Lane& q, const Consts& c, V3 hr,
-                                                   double inv_d, V3 hv, V3 r_host_inertial, V3 acc_newton, V3& a_out,
-                                                   V3& dl_out, double* tide_save) {
+__device__ __forceinline__ void additional_effects(const KParams& P, const Roles& ro, const Cold& cold, int hl, Lane& q, V3 hr,
+                                                   double inv_d, V3 hv, V3& a_out, V3& dl_out, double* tide_save) {
     const int W = P.W;
     // Q3: r.omega uses the spins of the previous evaluation (universe.rs:429-430)
     V3 s_host_prev = shfl3(q.s, hl);
     double rs_s = dot(hr, s_host_prev), rs_p = dot(hr, q.s);
     // calculate_spin (particles/common.rs:3-15)
-    q.s = c.invI * q.L;
+    q.s = cold.get(C_INVI) * q.L;
     double w2 = dot(q.s, q.s);
     V3 sh = shfl3(q.s, hl);
     double wh2 = shfl(w2, hl);
@@ -357,16 +389,16 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     V3 rxv = cross(hr, hv);
     V3 a_p = v3(0., 0., 0.), dl_p = v3(0., 0., 0.);       // this body's own acceleration / torque
     V3 a_h = v3(0., 0., 0.), dl_h = v3(0., 0., 0.);       // contribution to the host
-    const double inv_m = c.inv_m, inv_M = c.inv_M;
+    const double inv_m = cold.get(C_INVM), inv_M = cold.get(C_INVMH);
     if (P.flags & FLAG_TIDES) {
         // constant_time_lag.rs:206-332, tides/common.rs:223-345
         double inv_d4 = inv_d2 * inv_d2;
         double inv_d7 = inv_d4 * inv_d2 * inv_d;
-        double Fos = P.tides_host_central ? c.As * inv_d7 : 0.;
-        double Fop = c.Ap * inv_d7;
+        double Fos = P.tides_host_central ? cold.get(C_AS) * inv_d7 : 0.;
+        double Fop = cold.get(C_AP) * inv_d7;
         double Fsum = Fos + Fop;
         // radial: conservative + dissipative (-13.5 vr/r^8 (...) = -3 vr/r (Fos + Fop))
-        double f3 = -c.Bk * inv_d7 - 2.0 * Fsum * radvel * inv_d;
+        double f3 = -cold.get(C_BK) * inv_d7 - 2.0 * Fsum * radvel * inv_d;
         V3 wxr_s = cross(sh, hr), wxr_p = cross(q.s, hr);
         double k3 = f3 * inv_d, ks = Fos * inv_d, kp = Fop * inv_d;
         V3 F = v3(k3 * hr.x + ks * (wxr_s.x - hv.x) + kp * (wxr_p.x - hv.x),
@@ -396,10 +428,11 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         // oblate_spheroid.rs:12-97, rotational_flattening/common.rs:165-237
         double inv_d5 = inv_d2 * inv_d2 * inv_d;
         double inv_d7 = inv_d5 * inv_d2;
-        double Ks = P.flat_host_central ? c.Ks : 0.;
+        double Ks = P.flat_host_central ? cold.get(C_KS) : 0.;
+        double Kp = cold.get(C_KP);
         double Fos = -Ks * rs_s * inv_d5;
-        double Fop = -c.Kp * rs_p * inv_d5;
-        double Frad = -0.5 * inv_d5 * (Ks * wh2 + c.Kp * w2) + 2.5 * inv_d7 * (Ks * rs_s * rs_s + c.Kp * rs_p * rs_p);
+        double Fop = -Kp * rs_p * inv_d5;
+        double Frad = -0.5 * inv_d5 * (Ks * wh2 + Kp * w2) + 2.5 * inv_d7 * (Ks * rs_s * rs_s + Kp * rs_p * rs_p);
         V3 F = v3(Frad * hr.x + Fop * q.s.x + Fos * sh.x, Frad * hr.y + Fop * q.s.y + Fos * sh.y, Frad * hr.z + Fop * q.s.z + Fos * sh.z);
         V3 Np = Fop * cross(hr, q.s);
         V3 Ns = Fos * cross(hr, sh);
@@ -413,8 +446,8 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     if (GR == PB200_GR_KIDDER1995) {
         // general_relativity.rs:177-456
         double v2 = dot(hv, hv);
-        double mgs = c.mgs;
-        double f = c.grf;
+        double mgs = cold.get(C_MGS);
+        double f = cold.get(C_GRF);
         double A = mgs * inv_d2 * kInvC2;
         double u = mgs * inv_d;
         double rv2 = radvel * radvel;
@@ -429,9 +462,9 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         double kr = rad * inv_d;
         V3 a = v3(kr * hr.x + orth * hv.x, kr * hr.y + orth * hv.y, kr * hr.z + orth * hv.z);
         // 1.5PN spin-orbit (:300-456); component-wise products exactly as the reference writes them
-        V3 Ls = c.Ih * sh, Lp = q.I * q.s;
+        V3 Ls = cold.get(C_IH) * sh, Lp = cold.get(K_I) * q.s;
         V3 nn = inv_d * hr;
-        double md = c.M - q.m;  // mass_factor * star_planet_mass
+        double md = cold.get(C_MD);
         V3 msf = v3(md * (Lp.x * inv_m - Ls.x * inv_M), md * (Lp.y * inv_m - Ls.y * inv_M), md * (Lp.z * inv_m - Ls.z * inv_M));
         V3 S = Ls + Lp;
         V3 nxv = cross(nn, hv);
@@ -443,14 +476,13 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         const double fa = kG * kInvC2;
         a = a + fa * (e1 - e2 + e3);
         // Kidder 1995 eqs 2.4a, 2.4b
-        V3 Lo = c.mu_red * rxv;
-        double fm_s = 2. + 1.5 * q.m * inv_M, fm_p = 2. + 1.5 * c.M * inv_m;
+        V3 Lo = cold.get(C_MURED) * rxv;
         V3 LpxLs = cross(Lp, Ls);
-        V3 ds = fm_s * cross(Lo, Ls) - LpxLs + (3. * dot(nn, Lp)) * cross(nn, Ls);
-        V3 dp = fm_p * cross(Lo, Lp) + LpxLs + (3. * dot(nn, Ls)) * cross(nn, Lp);
+        V3 ds = cold.get(C_FMS) * cross(Lo, Ls) - LpxLs + (3. * dot(nn, Lp)) * cross(nn, Ls);
+        V3 dp = cold.get(C_FMP) * cross(Lo, Lp) + LpxLs + (3. * dot(nn, Ls)) * cross(nn, Lp);
         if (ro.g_on) {
             a_p = a_p + a;
-            a_h = a_h - (q.m * inv_M) * a;
+            a_h = a_h - cold.get(C_MOM) * a;
             dl_p = dl_p + fa * dp;
             dl_h = dl_h + fa * ds;
         }
@@ -461,7 +493,6 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     dl_h = group_sum3(dl_h, W);
     a_out = ro.host ? a_h : a_p;
     dl_out = ro.host ? dl_h : dl_p;
-    (void)r_host_inertial; (void)acc_newton;
 }
 
 }  // namespace pb200

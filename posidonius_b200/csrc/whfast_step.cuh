@@ -9,7 +9,9 @@
 
 namespace pb200 {
 
+#ifndef PB_BLOCK
 #define PB_BLOCK 128
+#endif
 #define PB_HIST_FIELDS 16  // time, pos3, spin3, vel3, mass, radius, rg2, love_number, sigma, denergy_dt
 #define PB_TIDE_SCRATCH 13
 
@@ -23,7 +25,7 @@ struct SysState {
     bool tswarn;
 };
 
-__device__ __forceinline__ void store_lane(const KParams& P, const Roles& ro, size_t sys, int b, const Lane& q, V3 acc,
+__device__ __forceinline__ void store_lane(const KParams& P, const Roles& ro, const Cold& cold, size_t sys, int b, const Lane& q,
                                            const SysState& st) {
     if (!ro.valid) return;
     const size_t ns = (size_t)P.n_sys;
@@ -31,12 +33,12 @@ __device__ __forceinline__ void store_lane(const KParams& P, const Roles& ro, si
     const size_t cs = (size_t)P.n_bodies * ns;
     P.pos[i] = q.r.x.v; P.pos[i + cs] = q.r.y.v; P.pos[i + 2 * cs] = q.r.z.v;
     P.vel[i] = q.v.x.v; P.vel[i + cs] = q.v.y.v; P.vel[i + 2 * cs] = q.v.z.v;
-    P.acc[i] = acc.x; P.acc[i + cs] = acc.y; P.acc[i + 2 * cs] = acc.z;
+    P.acc[i] = cold.get(S_AX); P.acc[i + cs] = cold.get(S_AY); P.acc[i + 2 * cs] = cold.get(S_AZ);
     P.L[i] = q.L.x; P.L[i + cs] = q.L.y; P.L[i + 2 * cs] = q.L.z;
     P.spin[i] = q.s.x; P.spin[i + cs] = q.s.y; P.spin[i + 2 * cs] = q.s.z;
-    P.verr[i] = q.ev.x; P.verr[i + cs] = q.ev.y; P.verr[i + 2 * cs] = q.ev.z;
-    P.lerr[i] = q.el.x; P.lerr[i + cs] = q.el.y; P.lerr[i + 2 * cs] = q.el.z;
-    P.radius[i] = q.R; P.rg2[i] = q.rg2; P.moi[i] = q.I;
+    P.verr[i] = cold.get(S_EVX); P.verr[i + cs] = cold.get(S_EVY); P.verr[i + 2 * cs] = cold.get(S_EVZ);
+    P.lerr[i] = cold.get(S_ELX); P.lerr[i + cs] = cold.get(S_ELY); P.lerr[i + 2 * cs] = cold.get(S_ELZ);
+    // radius / radius of gyration / moment of inertia are written when they evolve (evolve_lane)
     if (b == 0) {
         P.t[sys] = st.t; P.last_hist[sys] = st.last_hist;
         unsigned long long it0 = P.iteration[sys];
@@ -48,19 +50,25 @@ __device__ __forceinline__ void store_lane(const KParams& P, const Roles& ro, si
     }
 }
 
-// effects/evolution.rs:516-546 for this lane's body (radius, radius of gyration -> moment of inertia)
-__device__ __forceinline__ void evolve_lane(const KParams& P, const Roles& ro, int b, double t, Lane& q) {
-    if (!ro.valid) return;
+// effects/evolution.rs:516-546 for this lane's body (radius, radius of gyration -> moment of inertia). Cold path:
+// the evolving quantities live in global memory (rg2) and in the cold slots (R, I). Returns true when something changed.
+__device__ __forceinline__ bool evolve_lane(const KParams& P, const Roles& ro, const Cold& cold, int b, size_t sys, double t, bool commit) {
+    if (!ro.valid || !commit) return false;
     int ti = P.evo_table[b];
-    if (ti < 0) return;
+    if (ti < 0) return false;
     const DevTable& T = P.tables[ti];
+    const size_t idx = (size_t)b * (size_t)P.n_sys + sys;
+    const double R = cold.get(K_R), rg2 = P.rg2[idx];
     int i = table_upper(T.time, T.n_rows, t);
-    double nr = T.interp_radius ? table_interp(T.time, T.radius, T.n_rows, i, t) : q.R;
-    double ng = T.interp_rg2 ? table_interp(T.time, T.rg2, T.n_rows, i, t) : q.rg2;
-    if (nr != q.R || ng != q.rg2) {
-        q.R = nr; q.rg2 = ng;
-        q.I = (sd(q.m) * sd(q.rg2) * (sd(q.R) * sd(q.R))).v;
+    double nr = T.interp_radius ? table_interp(T.time, T.radius, T.n_rows, i, t) : R;
+    double ng = T.interp_rg2 ? table_interp(T.time, T.rg2, T.n_rows, i, t) : rg2;
+    if (nr != R || ng != rg2) {
+        double I = (sd(cold.get(K_M)) * sd(ng) * (sd(nr) * sd(nr))).v;
+        cold.set(K_R, nr); cold.set(K_I, I);
+        P.radius[idx] = nr; P.rg2[idx] = ng; P.moi[idx] = I;
+        return true;
     }
+    return false;
 }
 
 // Running sum over the NON-HOST bodies in index order, as the reference's serial loops accumulate
@@ -83,35 +91,34 @@ __device__ __forceinline__ S3 ordered_diff_others(S3 init, S3 x, int gb, int n, 
 }
 
 // Implicit midpoint on v and L (whfast.rs:322-466) around Universe::calculate_additional_effects.
+// Registers across the evaluation: v, L, spin, heliocentric position and 1/r. Originals, increments and Kahan
+// residuals sit in the cold slots and are touched once per iteration.
 template <int COORD, int GR>
-__device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, int gb, int hl, int b, bool alive, Lane& q, Consts& c,
-                                         double t, bool evolution, V3 acc_newton, unsigned int& warnings, bool save_tides,
-                                         size_t sys) {
+__device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, bool alive, Lane& q,
+                                         double t, bool evolution, unsigned int& warnings, bool save_tides, size_t sys) {
     const int W = P.W;
     const sd dt = sd(P.half_dt);
     // positions do not change inside the midpoint: heliocentric position and 1/r once (universe.rs:318-351)
     const S3 rh_s = shfl3(q.r, hl);
-    const V3 rh = plain(rh_s);
     // idle lanes (host slot, padding) get a unit dummy so that rsqrt/div stay on their fast paths for the whole warp
     const V3 hr = ro.planet ? plain(q.r - rh_s) : v3(1., 0., 0.);
     const double inv_d = rsqrt(dot(hr, hr));
-    const S3 vo = q.v;
-    const V3 Lo = q.L;
-    S3 dv = s3(sd(0.), sd(0.), sd(0.));
-    V3 dl = v3(0., 0., 0.);
+    cold.set3(S_RX, plain(q.r));
+    cold.set3(S_VOX, plain(q.v)); cold.set3(S_LOX, q.L);
+    cold.set3(S_DVX, v3(0., 0., 0.)); cold.set3(S_DLX, v3(0., 0., 0.));
     bool done = !alive;  // group-uniform
     bool converged = false;
 #pragma unroll 1
     for (int it = 0; it < 10; it++) {
         if (!__any_sync(FULL, !done)) break;
         if (evolution && it == 0 && (P.flags & FLAG_EVO)) {
-            evolve_lane(P, ro, b, t, q);
-            make_consts(q, hl, c);
+            bool changed = evolve_lane(P, ro, cold, b, sys, t, alive);
+            if (__any_sync(FULL, changed)) make_consts(P, ro, cold, hl, b, sys);
         }
         V3 hv = plain(q.v - shfl3(q.v, hl));
         V3 a, dldt;
         double scratch[PB_TIDE_SCRATCH];
-        additional_effects<GR>(P, ro, hl, q, c, hr, inv_d, hv, rh, acc_newton, a, dldt, save_tides ? scratch : nullptr);
+        additional_effects<GR>(P, ro, cold, hl, q, hr, inv_d, hv, a, dldt, save_tides ? scratch : nullptr);
         if (save_tides && (P.flags & FLAG_TIDES) && ro.valid && !done) {
             const size_t ns = (size_t)P.n_sys;
             const size_t i = (size_t)b * ns + sys, cs = (size_t)P.n_bodies * ns;
@@ -120,16 +127,23 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, int 
         if (GR == PB200_GR_ANDERSON1975 || GR == PB200_GR_NEWHALL1983) {
             if (P.flags & FLAG_GR) {
                 V3 ag;
-                if (GR == PB200_GR_ANDERSON1975) gr_anderson1975(P, ro, gb, hl, b, q, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
-                else gr_newhall1983(P, ro, gb, hl, b, q, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
+                Lane qq = q;
+                qq.r = strict(cold.get3(S_RX));
+                V3 acc_newton = cold.get3(S_AX);
+                if (GR == PB200_GR_ANDERSON1975) gr_anderson1975(P, ro, cold, gb, hl, b, qq, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
+                else gr_newhall1983(P, ro, cold, gb, hl, b, qq, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
                 a = a + ag;
             }
         }
         // final = orig + (dt * a - err)   (whfast.rs:353-378), with the previous final for the convergence test
-        S3 vf_old = vo + dv;
-        V3 Lf_old = v3(__dadd_rn(Lo.x, dl.x), __dadd_rn(Lo.y, dl.y), __dadd_rn(Lo.z, dl.z));
-        S3 ndv = s3(dt * sd(a.x) - sd(q.ev.x), dt * sd(a.y) - sd(q.ev.y), dt * sd(a.z) - sd(q.ev.z));
-        V3 ndl = v3((dt * sd(dldt.x) - sd(q.el.x)).v, (dt * sd(dldt.y) - sd(q.el.y)).v, (dt * sd(dldt.z) - sd(q.el.z)).v);
+        const S3 vo = strict(cold.get3(S_VOX));
+        const V3 Lo = cold.get3(S_LOX);
+        const V3 ev = cold.get3(S_EVX), el = cold.get3(S_ELX);
+        S3 vf_old = vo + strict(cold.get3(S_DVX));
+        V3 dl_old = cold.get3(S_DLX);
+        V3 Lf_old = v3(__dadd_rn(Lo.x, dl_old.x), __dadd_rn(Lo.y, dl_old.y), __dadd_rn(Lo.z, dl_old.z));
+        S3 ndv = s3(dt * sd(a.x) - sd(ev.x), dt * sd(a.y) - sd(ev.y), dt * sd(a.z) - sd(ev.z));
+        V3 ndl = v3((dt * sd(dldt.x) - sd(el.x)).v, (dt * sd(dldt.y) - sd(el.y)).v, (dt * sd(dldt.z) - sd(el.z)).v);
         S3 vf = vo + ndv;
         V3 Lf = P.spin_on ? v3(__dadd_rn(Lo.x, ndl.x), __dadd_rn(Lo.y, ndl.y), __dadd_rn(Lo.z, ndl.z)) : Lo;
         bool conv_now = false;
@@ -149,7 +163,7 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, int 
             conv_now = okv && okl;
         }
         if (!done) {
-            dv = ndv; if (P.spin_on) dl = ndl;
+            cold.set3(S_DVX, plain(ndv)); if (P.spin_on) cold.set3(S_DLX, ndl);
             if (conv_now) { done = true; converged = true; }
             else {
                 // average (whfast.rs:453-466)
@@ -158,14 +172,16 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, int 
             }
         }
     }
+    q.r = strict(cold.get3(S_RX));
     if (alive) {
         if (!converged) warnings |= PB200_WARN_MIDPOINT_NOT_CONVERGED;
+        const S3 vo = strict(cold.get3(S_VOX)), dv = strict(cold.get3(S_DVX));
         q.v = vo + dv;
-        S3 e = (q.v - vo) - dv;
-        q.ev = plain(e);
+        cold.set3(S_EVX, plain((q.v - vo) - dv));
         if (P.spin_on) {
+            const V3 Lo = cold.get3(S_LOX), dl = cold.get3(S_DLX);
             q.L = v3(__dadd_rn(Lo.x, dl.x), __dadd_rn(Lo.y, dl.y), __dadd_rn(Lo.z, dl.z));
-            q.el = v3(__dsub_rn(__dsub_rn(q.L.x, Lo.x), dl.x), __dsub_rn(__dsub_rn(q.L.y, Lo.y), dl.y), __dsub_rn(__dsub_rn(q.L.z, Lo.z), dl.z));
+            cold.set3(S_ELX, v3(__dsub_rn(__dsub_rn(q.L.x, Lo.x), dl.x), __dsub_rn(__dsub_rn(q.L.y, Lo.y), dl.y), __dsub_rn(__dsub_rn(q.L.z, Lo.z), dl.z)));
         }
     }
 }
@@ -173,22 +189,23 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, int 
 // particles/universe.rs:198-303 — Newtonian gravity with the WHFast ignore rules and the
 // Roche / collision / ejection checks (panic! in the reference, status word here). Strict arithmetic.
 template <int COORD>
-__device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, int gb, int b, size_t sys, const Lane& q, int& fail) {
+__device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const Cold& cold, int gb, int b, size_t sys, const Lane& q, int& fail) {
     S3 acc = s3(sd(0.), sd(0.), sd(0.));
+    const double q_m = cold.get(K_M), q_R = cold.get(K_R);
     const int n = P.n_bodies;
     const int first_other = P.host == 0 ? 1 : 0;
     fail = 0;
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
         S3 rj = shfl3(q.r, gb + j);
-        sd mj = sd(shfl(q.m, gb + j));
-        double Rj = shfl(q.R, gb + j);
+        sd mj = sd(shfl(q_m, gb + j));
+        double Rj = shfl(q_R, gb + j);
         if (j == b || !ro.valid) continue;
         S3 d = q.r - rj;
         sd d2 = d.x * d.x + d.y * d.y + d.z * d.z;
         if (b < j) {
             double rr = __ldg(P.roche + ((size_t)(b * n + j)) * (size_t)P.n_sys + sys);
-            double rs = __dadd_rn(q.R, Rj);
+            double rs = __dadd_rn(q_R, Rj);
             if (d2.v <= __dmul_rn(rr, rr)) { if (!fail) fail = PB200_STATUS_ROCHE_DESTROYED; }
             if (d2.v <= __dmul_rn(rs, rs)) { if (!fail) fail = PB200_STATUS_COLLISION; }
             if (b == P.host && d2.v > kMaxDistance2) { if (!fail) fail = PB200_STATUS_EJECTED; }
@@ -205,11 +222,19 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, int gb,
 }
 
 #ifndef PB_MIN_BLOCKS
-#define PB_MIN_BLOCKS 2
+#define PB_MIN_BLOCKS 3   // 168 registers/thread, 12 warps/SM, no spills (measured best: profiles/r1_variants.md)
 #endif
+#ifdef PB_MAXNREG
+#define PB_KERNEL_ATTR __launch_bounds__(PB_BLOCK) __maxnreg__(PB_MAXNREG)
+#else
+#define PB_KERNEL_ATTR __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS)
+#endif
+#define PB_SMEM_BYTES (N_COLD_SLOTS * PB_BLOCK * sizeof(double))
+
+extern __shared__ double pb_smem[];
 
 template <int COORD, int GR>
-__global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
+__global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
     const int W = P.W;
     const int n = P.n_bodies;
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,10 +251,11 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
     ro.t_on = ro.planet && ((P.tides_orbiting >> b) & 1u);
     ro.f_on = ro.planet && ((P.flat_orbiting >> b) & 1u);
     ro.g_on = ro.planet && ((P.gr_orbiting >> b) & 1u);
+    Cold cold;
+    cold.base = pb_smem + threadIdx.x;
 
     Lane q;
     SysState st;
-    V3 acc = v3(0., 0., 0.);
     {
         const size_t ns = (size_t)P.n_sys;
         const size_t i = (size_t)b * ns + sys, cs = (size_t)n * ns;
@@ -238,16 +264,16 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
             q.v = s3(sd(P.vel[i]), sd(P.vel[i + cs]), sd(P.vel[i + 2 * cs]));
             q.L = v3(P.L[i], P.L[i + cs], P.L[i + 2 * cs]);
             q.s = v3(P.spin[i], P.spin[i + cs], P.spin[i + 2 * cs]);
-            q.ev = v3(P.verr[i], P.verr[i + cs], P.verr[i + 2 * cs]);
-            q.el = v3(P.lerr[i], P.lerr[i + cs], P.lerr[i + 2 * cs]);
-            acc = v3(P.acc[i], P.acc[i + cs], P.acc[i + 2 * cs]);
-            q.m = P.mass[i]; q.mg = P.mass_g[i]; q.R = P.radius[i]; q.rg2 = P.rg2[i]; q.I = P.moi[i];
-            q.sigma = P.sigma[i]; q.k2t = P.k2t[i]; q.k2f = P.k2f[i];
+            cold.set3(S_EVX, v3(P.verr[i], P.verr[i + cs], P.verr[i + 2 * cs]));
+            cold.set3(S_ELX, v3(P.lerr[i], P.lerr[i + cs], P.lerr[i + 2 * cs]));
+            cold.set3(S_AX, v3(P.acc[i], P.acc[i + cs], P.acc[i + 2 * cs]));
+            cold.set(K_M, P.mass[i]); cold.set(K_MG, P.mass_g[i]); cold.set(K_R, P.radius[i]); cold.set(K_I, P.moi[i]);
         } else {
             // padding lanes: finite, non-zero dummies (never read by live lanes, never stored)
             q.r = s3(sd(1. + b), sd(0.), sd(0.)); q.v = s3(sd(0.), sd(0.), sd(0.));
-            q.L = v3(0., 0., 1.); q.s = v3(0., 0., 1.); q.ev = v3(0., 0., 0.); q.el = v3(0., 0., 0.);
-            q.m = 1.; q.mg = 1.; q.R = 1.; q.rg2 = 1.; q.I = 1.; q.sigma = 0.; q.k2t = 0.; q.k2f = 0.;
+            q.L = v3(0., 0., 1.); q.s = v3(0., 0., 1.);
+            cold.set3(S_EVX, v3(0., 0., 0.)); cold.set3(S_ELX, v3(0., 0., 0.)); cold.set3(S_AX, v3(0., 0., 0.));
+            cold.set(K_M, 1.); cold.set(K_MG, 1.); cold.set(K_R, 1.); cold.set(K_I, 1.);
         }
         if (sys_ok) {
             st.t = P.t[sys]; st.last_hist = P.last_hist[sys];
@@ -258,33 +284,33 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
         st.steps_done = 0; st.n_hist_new = 0; st.event_step = 0;
     }
     bool alive = sys_ok && st.status == PB200_STATUS_OK;
-    Consts c;
-    make_consts(q, hl, c);
+    make_consts(P, ro, cold, hl, b, sys);
 
-    // constants of the transforms, all strict and in the reference's order
-    const sd m_s = sd(q.m);
-    const sd M_s = sd(shfl(q.m, hl));       // m0
-    const sd Mg_s = sd(shfl(q.mg, hl));
-    // total mass as inertial_to_*_posvel accumulate it: host first, then the others in index order
-    sd mtot = M_s;
-    sd eta_k = sd(0.), mu_k = sd(0.);        // Jacobi: cumulative mass / mass_g up to and including this body
+    // constants of the transforms, all strict and in the reference's order; parked in the cold slots
     {
+        const sd m_s = sd(cold.get(K_M)), mg_s = sd(cold.get(K_MG));
+        const sd M_s = sd(shfl(m_s.v, hl));       // m0
+        const sd Mg_s = sd(shfl(mg_s.v, hl));
+        // total mass as inertial_to_*_posvel accumulate it: host first, then the others in index order
+        sd mtot = M_s;
+        sd eta_k = sd(0.), mu_k = sd(0.);        // Jacobi: cumulative mass / mass_g up to and including this body
         sd mu = Mg_s;
         if (COORD != PB200_COORD_JACOBI) mtot = sd(0.) + M_s;
         for (int k = 0; k < n; k++) {
             if (k == P.host) continue;
-            mtot = mtot + sd(shfl(q.m, gb + k));
-            mu = mu + sd(shfl(q.mg, gb + k));
+            mtot = mtot + sd(shfl(m_s.v, gb + k));
+            mu = mu + sd(shfl(mg_s.v, gb + k));
             if (k == b) { eta_k = mtot; mu_k = mu; }
         }
+        // per-body constants of the heliocentric transforms (whfast.rs:1015, 1101, 1112-1114), divided once
+        sd back_w = sd(1.), whds_f = sd(1.);
+        if (COORD == PB200_COORD_WHDS) { whds_f = (M_s + m_s) / M_s; back_w = m_s / (M_s + m_s); }
+        if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) back_w = m_s / M_s;
+        const sd kepler_mu = COORD == PB200_COORD_JACOBI ? mu_k : (COORD == PB200_COORD_WHDS ? Mg_s + mg_s : Mg_s);
+        cold.set(K_MH, M_s.v); cold.set(K_MGH, Mg_s.v); cold.set(K_MTOT, mtot.v); cold.set(K_KMU, kepler_mu.v);
+        cold.set(K_BACKW, back_w.v); cold.set(K_WHDSF, whds_f.v); cold.set(K_ETAK, eta_k.v);
     }
-    // per-body constants of the heliocentric transforms (whfast.rs:1015, 1101, 1112-1114), divided once
-    sd back_w = sd(1.), whds_f = sd(1.);
-    if (COORD == PB200_COORD_WHDS) { whds_f = (M_s + m_s) / M_s; back_w = m_s / (M_s + m_s); }
-    if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) back_w = m_s / M_s;
-    const sd kepler_mu = COORD == PB200_COORD_JACOBI ? mu_k : (COORD == PB200_COORD_WHDS ? Mg_s + sd(q.mg) : Mg_s);
     const int first_other = P.host == 0 ? 1 : 0;
-    const sd dt_s = sd(P.dt), hdt_s = sd(P.half_dt);
     const sd zero = sd(0.), one = sd(1.);
     const S3 zero3 = s3(zero, zero, zero);
     const S3 one3 = s3(one, one, one);
@@ -298,10 +324,11 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
             bool due = __dadd_rn(st.last_hist, P.hist_period) <= st.t;
             bool snap = alive && (first || due);
             if (__any_sync(FULL, snap)) {
-                Lane qs = q;
-                if (P.flags & FLAG_EVO) evolve_lane(P, ro, b, st.t, qs);
-                double invI = 1. / qs.I;
-                qs.s = invI * qs.L;
+                // refresh: evolving quantities and spin = L / I (universe.rs:305-316); it changes the live state too
+                bool changed = false;
+                if (P.flags & FLAG_EVO) changed = evolve_lane(P, ro, cold, b, sys, st.t, snap);
+                if (__any_sync(FULL, changed)) make_consts(P, ro, cold, hl, b, sys);
+                if (snap) q.s = cold.get(C_INVI) * q.L;
                 if (snap && ro.valid && st.hist_count < P.hist_capacity) {
                     const size_t ns = (size_t)P.n_sys;
                     const size_t i = (size_t)b * ns + sys, cs = (size_t)n * ns;
@@ -314,27 +341,24 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
                         double dist = ts[6], radvel = ts[7], orth_p = ts[8], diss_pm = ts[9];
                         V3 tdl = v3(ts[10], ts[11], ts[12]);
                         double factor2 = orth_p / dist;
-                        V3 wxr = cross(qs.s, tp);
+                        V3 wxr = cross(q.s, tp);
                         denergy = -((1.0 / dist * (diss_pm + factor2 * radvel)) * dot(tp, tv)
                                     + factor2 * ((wxr.x - tv.x) * tv.x + (wxr.y - tv.y) * tv.y + (wxr.z - tv.z) * tv.z))
-                                  - dot(tdl, qs.s);
+                                  - dot(tdl, q.s);
                     }
                     double* h = P.hist + (size_t)st.hist_count * PB_HIST_FIELDS * cs + i;
                     h[0 * cs] = st.t;
-                    h[1 * cs] = qs.r.x.v; h[2 * cs] = qs.r.y.v; h[3 * cs] = qs.r.z.v;
-                    h[4 * cs] = qs.s.x; h[5 * cs] = qs.s.y; h[6 * cs] = qs.s.z;
-                    h[7 * cs] = qs.v.x.v; h[8 * cs] = qs.v.y.v; h[9 * cs] = qs.v.z.v;
-                    h[10 * cs] = qs.m; h[11 * cs] = qs.R; h[12 * cs] = qs.rg2;
-                    h[13 * cs] = qs.k2t; h[14 * cs] = qs.sigma; h[15 * cs] = denergy;
+                    h[1 * cs] = q.r.x.v; h[2 * cs] = q.r.y.v; h[3 * cs] = q.r.z.v;
+                    h[4 * cs] = q.s.x; h[5 * cs] = q.s.y; h[6 * cs] = q.s.z;
+                    h[7 * cs] = q.v.x.v; h[8 * cs] = q.v.y.v; h[9 * cs] = q.v.z.v;
+                    h[10 * cs] = cold.get(K_M); h[11 * cs] = cold.get(K_R); h[12 * cs] = P.rg2[i];
+                    h[13 * cs] = P.k2t[i]; h[14 * cs] = P.sigma[i]; h[15 * cs] = denergy;
                 }
                 if (snap) {
-                    // the refresh changes the live state too (spin, evolving quantities)
-                    q.s = qs.s; q.R = qs.R; q.rg2 = qs.rg2; q.I = qs.I;
                     if (!first) st.last_hist = __dadd_rn(st.last_hist, P.hist_period); else st.last_hist = 0.;
                     st.n_hist_new += 1;
                     if (st.hist_count < P.hist_capacity) st.hist_count += 1;
                 }
-                if (P.flags & FLAG_EVO) make_consts(q, hl, c);
             }
         }
         // internals needed by the NEXT snapshot's denergy_dt are those of this step's last evaluation
@@ -345,6 +369,8 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             if (half == 1) {
+                const sd m_s = sd(cold.get(K_M)), M_s = sd(cold.get(K_MH)), mtot = sd(cold.get(K_MTOT));
+                const sd dt_s = sd(P.dt), hdt_s = sd(P.half_dt);
                 S3 apos, avel;       // this body's alternative coordinates
                 S3 spos, svel;       // the host slot of the alternative coordinates (centre of mass), replicated in the group
                 S3 anew_s = zero3;
@@ -356,7 +382,7 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
                     apos = one3; avel = zero3;
                     for (int k = 0; k < n; k++) {
                         if (k == P.host) continue;
-                        sd mk = sd(shfl(q.m, gb + k));
+                        sd mk = sd(shfl(m_s.v, gb + k));
                         S3 rk = shfl3(q.r, gb + k), vk = shfl3(q.v, gb + k);
                         sd ei = one / eta;
                         eta = eta + mk;
@@ -375,7 +401,7 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
                     spos = sr / mtot; svel = sv / mtot;
                     apos = q.r - shfl3(q.r, hl);
                     avel = q.v - svel;
-                    if (COORD == PB200_COORD_WHDS) avel = avel * whds_f;
+                    if (COORD == PB200_COORD_WHDS) avel = avel * sd(cold.get(K_WHDSF));
                 }
 #pragma unroll 1
                 for (int phase = 0; phase < 2; phase++) {
@@ -388,7 +414,7 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
                             S3 aacc = zero3;
                             for (int k = 0; k < n; k++) {
                                 if (k == P.host) continue;
-                                sd mk = sd(shfl(q.m, gb + k));
+                                sd mk = sd(shfl(m_s.v, gb + k));
                                 S3 ak = shfl3(anew_s, gb + k);
                                 sd ei = one / eta;
                                 eta = eta + mk;
@@ -401,7 +427,7 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
                             if (b != first_other) {
                                 sd rj2i = one / (apos.x * apos.x + apos.y * apos.y + apos.z * apos.z + sd(1e-12));
                                 sd rji = ssqrt(rj2i);
-                                sd rj3im = rji * rj2i * sd(kG) * eta_k;
+                                sd rj3im = rji * rj2i * sd(kG) * sd(cold.get(K_ETAK));
                                 sd prefac = dt_s * rj3im;
                                 avel = avel + prefac * apos;
                             }
@@ -415,7 +441,7 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
                     // ---- jump (whfast.rs:495-556): before the Kepler drift in the second half, after it in the first
                     for (int jump_slot = 0; jump_slot < 2; jump_slot++) {
                         if (jump_slot == 1) {
-                            kepler_step(kwork, apos, avel, kepler_mu, hdt_s, st.tswarn, st.warnings);
+                            kepler_step(kwork, apos, avel, sd(cold.get(K_KMU)), hdt_s, st.tswarn, st.warnings);
                             spos = spos + hdt_s * svel;
                         }
                         if (COORD != PB200_COORD_JACOBI && jump_slot != phase) {
@@ -437,7 +463,7 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
                         S3 nr = q.r, nv = q.v;
                         for (int k = n - 1; k >= 0; k--) {
                             if (k == P.host) continue;
-                            sd mk = sd(shfl(q.m, gb + k));
+                            sd mk = sd(shfl(m_s.v, gb + k));
                             S3 pk = shfl3(apos, gb + k), wk = shfl3(avel, gb + k);
                             sd ei = one / et;
                             s = (s - mk * pk) * ei; sv = (sv - mk * wk) * ei;
@@ -456,8 +482,8 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
                         if (alive) q.r = nr;
                         if (phase == 1) {
                             // velocities (whfast.rs:1090-1126); those of the first drift are dead (the kick overwrites them)
-                            S3 nv = (COORD == PB200_COORD_WHDS ? avel / whds_f : avel) + svel;
-                            S3 star_v = ordered_diff_others(svel, avel * back_w, gb, n, P.host);
+                            S3 nv = (COORD == PB200_COORD_WHDS ? avel / sd(cold.get(K_WHDSF)) : avel) + svel;
+                            S3 star_v = ordered_diff_others(svel, avel * sd(cold.get(K_BACKW)), gb, n, P.host);
                             if (ro.host) nv = star_v;
                             if (alive) q.v = nv;
                         }
@@ -465,20 +491,20 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
                     if (phase == 0) {
                         // ---- gravity (whfast.rs:281)
                         int fail;
-                        anew_s = gravity<COORD>(P, ro, gb, b, sys, q, fail);
-                        V3 anew = plain(anew_s);
+                        anew_s = gravity<COORD>(P, ro, cold, gb, b, sys, q, fail);
                         // group-wide failure: lowest body index wins, like the reference's loop order
                         int code = (ro.valid && fail) ? ((b << 4) | fail) : 0x7fffffff;
                         for (int off = W >> 1; off > 0; off >>= 1) { int o = __shfl_xor_sync(FULL, code, off); code = o < code ? o : code; }
-                        if (alive && code != 0x7fffffff) {
+                        const bool died = alive && code != 0x7fffffff;
+                        if (alive) cold.set3(S_AX, plain(anew_s));
+                        if (died) {
                             st.status = code & 15; st.event_step = st.steps_done; alive = false;
-                            store_lane(P, ro, sys, b, q, anew, st);
+                            store_lane(P, ro, cold, sys, b, q, st);
                         }
-                        if (alive) acc = anew;
                     }
                 }
             }
-            midpoint<COORD, GR>(P, ro, gb, hl, b, alive, q, c, st.t, half == 0, acc, st.warnings, half == 1 && save_tides, sys);
+            midpoint<COORD, GR>(P, ro, cold, gb, hl, b, alive, q, st.t, half == 0, st.warnings, half == 1 && save_tides, sys);
         }
 
         if (alive) {
@@ -486,11 +512,11 @@ __global__ void __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS) whfast_steps_kernel(c
             st.steps_done += 1;
             if (__dadd_rn(st.t, P.dt) > P.time_limit) {
                 st.status = PB200_STATUS_COMPLETED; st.event_step = st.steps_done; alive = false;
-                store_lane(P, ro, sys, b, q, acc, st);
+                store_lane(P, ro, cold, sys, b, q, st);
             }
         }
     }
-    if (alive) store_lane(P, ro, sys, b, q, acc, st);
+    if (alive) store_lane(P, ro, cold, sys, b, q, st);
 }
 
 }  // namespace pb200
