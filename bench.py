@@ -212,11 +212,11 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - t1
 
+    from posidonius_b200.shard import reduce_timing
     elapsed = torch.tensor([kernel_ms * 1e-3, wall, e2e_wall], dtype=torch.float64, device="cuda")
     counts = torch.tensor([alive, n_sys], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)   # the only collective: per-rank summaries after the timed region
+    # the only collective: max of the timed regions, per-rank summaries — after the timed region
+    elapsed, counts = reduce_timing(elapsed, counts, dist if world > 1 else None)
     kern_s, wall_s, e2e_s = [float(x) for x in elapsed.tolist()]
     total_sys = world * n_sys
     units = total_sys * spc * args.steps
@@ -237,7 +237,10 @@ def main():
             "e2e": {"value": units / e2e_s, "unit": "system-steps/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-                         "frac": achieved / (fp64_peak / 1e12) if fp64_peak else None, "traffic": None,
+                         "frac": achieved / (fp64_peak / 1e12) if fp64_peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 65536 systems, ncu --set full
+                         # (profiles/r1_ncu_step_kernel_summary.txt); independent of the steps per launch
+                         "traffic": 350.9e6 * n_sys / 65536.0,
                          "peak_source": "measured here: DFMA-chain microbenchmark (pb200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                          "frac_of_theoretical_37.2": achieved / FP64_THEORETICAL_TFLOPS,
                          "flops_per_system_step": FLOPS_PER_SYSTEM_STEP},
