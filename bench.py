@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--systems", type=int, default=65536, help="systems per GPU")
     ap.add_argument("--steps-per-call", type=int, default=1000, help="WHFast steps per launch (one bench step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--arithmetic", default="fast", choices=["fast", "strict"],
+                    help="fast (default): FMA/reciprocal forces; strict: forces bit-reproducible against the reference arithmetic")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -167,7 +169,7 @@ def main():
     n_sys, spc = args.systems, args.steps_per_call
     # keep the whole run inside the case's time limit
     cases = make_ensemble_cases(case, n_sys, 20261017 + CONFIG_INDEX + 1000 * rank)
-    ens = Ensemble(cases, tables, device=local)
+    ens = Ensemble(cases, tables, device=local, arithmetic=1 if args.arithmetic == "strict" else 0)
     ens.initialize_physical_values()
     ens.synchronize()
     # pinned host buffers of the boundary call
@@ -230,7 +232,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "systems_per_gpu": n_sys, "bodies": case.n_particles, "whfast_steps_per_step": spc,
                        "effects": "tides(CTL)+rotational_flattening(oblate)+GR(Kidder1995)", "coordinates": "DemocraticHeliocentric",
-                       "time_step_days": case.time_step, "parallelism": "ensemble-sharded x%d, no collective" % world,
+                       "time_step_days": case.time_step, "arithmetic": args.arithmetic, "parallelism": "ensemble-sharded x%d, no collective" % world,
                        "l2": "state (%.0f MB/GPU) larger than L2; registers hold it between launch start and end" % (io_bytes / 1e6),
                        "wall_clock_value": units / wall_s, "systems_alive": int(counts[0]), "systems_total": int(counts[1])},
             "clocks": clocks,

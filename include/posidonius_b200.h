@@ -197,6 +197,15 @@ int pb200_ensemble_set_time_limit(pb200_ensemble_t* e, double time_limit);
 int pb200_ensemble_set_snapshot_periods(pb200_ensemble_t* e, double historic_snapshot_period,
                                         double recovery_snapshot_period);
 
+/* Arithmetic of the perturbation forces (tides, flattening, GR). The WHFast core is always strict IEEE in the
+ * reference's operation order. PB200_ARITH_FAST (default): FMA contraction, reciprocal reuse, hoisted constants —
+ * results agree with the reference to roundoff-growth level. PB200_ARITH_STRICT: the forces too are
+ * evaluated operation by operation as the reference writes them; the whole step is then bit-reproducible against the
+ * CPU restatement of the reference, at about half the throughput. */
+#define PB200_ARITH_FAST 0
+#define PB200_ARITH_STRICT 1
+int pb200_ensemble_set_arithmetic(pb200_ensemble_t* e, int mode);
+
 /* Integrator::initialize_physical_values (whfast.rs:226-233): spin = L/I, evolving
  * quantities at t = 0, Roche radii. Fails with PB200_E_INVALID on a resumed ensemble
  * (current_time != 0), like the reference's panic. */

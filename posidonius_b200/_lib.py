@@ -24,6 +24,7 @@ _SIGNATURES = {
     "pb200_ensemble_n_systems": (C.c_size_t, [C.c_void_p]),
     "pb200_ensemble_set_time_limit": (C.c_int, [C.c_void_p, C.c_double]),
     "pb200_ensemble_set_snapshot_periods": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
+    "pb200_ensemble_set_arithmetic": (C.c_int, [C.c_void_p, C.c_int]),
     "pb200_ensemble_initialize_physical_values": (C.c_int, [C.c_void_p]),
     "pb200_ensemble_step": (C.c_int, [C.c_void_p, C.c_uint64]),
     "pb200_ensemble_synchronize": (C.c_int, [C.c_void_p]),

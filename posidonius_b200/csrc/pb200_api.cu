@@ -168,6 +168,7 @@ struct pb200_ensemble {
     unsigned int* d_records = nullptr;
     size_t records_capacity = 0;
     double recovery_snapshot_period = 0.;
+    int arithmetic = PB200_ARITH_FAST;
     // host mirror of the ensemble clock (exact snapshot counting without a device round trip)
     bool uniform_clock = true;
     double clock_t = 0., clock_last_hist = -1.;
@@ -191,26 +192,31 @@ static bool is_dynamical_tide_evolution(const pb200_body_t& b) {
            (b.evolution_type == PB200_EVO_LECONTECHABRIER2013 && b.evolution_parameter != 0.);
 }
 
-template <int COORD, int GR>
+template <int COORD, int GR, int ARITH>
 static cudaError_t launch_one(pb200_ensemble* e, unsigned grid, unsigned long long n) {
     // the cold slots need more than the default 48 KB of dynamic shared memory
     static thread_local int configured_device = -1;
     if (configured_device != e->device) {
-        cudaError_t err = cudaFuncSetAttribute(whfast_steps_kernel<COORD, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
+        cudaError_t err = cudaFuncSetAttribute(whfast_steps_kernel<COORD, GR, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
         if (err != cudaSuccess) return err;
         configured_device = e->device;
     }
-    whfast_steps_kernel<COORD, GR><<<grid, PB_BLOCK, PB_SMEM_BYTES, e->stream>>>(e->P, n);
+    whfast_steps_kernel<COORD, GR, ARITH><<<grid, PB_BLOCK, PB_SMEM_BYTES, e->stream>>>(e->P, n);
     return cudaGetLastError();
 }
 
 template <int COORD>
 static cudaError_t launch_gr(pb200_ensemble* e, unsigned grid, unsigned long long n) {
+    if (e->arithmetic == PB200_ARITH_STRICT) {
+        // the strict forces exist for Kidder1995 / no GR (pb200_ensemble_set_arithmetic rejects the other variants)
+        if (e->gr == PB200_GR_KIDDER1995) return launch_one<COORD, PB200_GR_KIDDER1995, 1>(e, grid, n);
+        return launch_one<COORD, PB200_GR_DISABLED, 1>(e, grid, n);
+    }
     switch (e->gr) {
-        case PB200_GR_KIDDER1995: return launch_one<COORD, PB200_GR_KIDDER1995>(e, grid, n);
-        case PB200_GR_ANDERSON1975: return launch_one<COORD, PB200_GR_ANDERSON1975>(e, grid, n);
-        case PB200_GR_NEWHALL1983: return launch_one<COORD, PB200_GR_NEWHALL1983>(e, grid, n);
-        default: return launch_one<COORD, PB200_GR_DISABLED>(e, grid, n);
+        case PB200_GR_KIDDER1995: return launch_one<COORD, PB200_GR_KIDDER1995, 0>(e, grid, n);
+        case PB200_GR_ANDERSON1975: return launch_one<COORD, PB200_GR_ANDERSON1975, 0>(e, grid, n);
+        case PB200_GR_NEWHALL1983: return launch_one<COORD, PB200_GR_NEWHALL1983, 0>(e, grid, n);
+        default: return launch_one<COORD, PB200_GR_DISABLED, 0>(e, grid, n);
     }
 }
 
@@ -489,6 +495,15 @@ int pb200_ensemble_set_snapshot_periods(pb200_ensemble_t* e, double historic, do
     if (!e) return set_error(PB200_E_INVALID, "null ensemble");
     if (historic > 0. && e->P.hist_period != historic) { e->P.hist_period = historic; e->tmpl.historic_snapshot_period = historic; }
     if (recovery > 0. && e->recovery_snapshot_period != recovery) { e->recovery_snapshot_period = recovery; e->tmpl.recovery_snapshot_period = recovery; }
+    return PB200_OK;
+}
+
+int pb200_ensemble_set_arithmetic(pb200_ensemble_t* e, int mode) {
+    if (!e) return set_error(PB200_E_INVALID, "null ensemble");
+    if (mode != PB200_ARITH_FAST && mode != PB200_ARITH_STRICT) return set_error(PB200_E_INVALID, "unknown arithmetic mode");
+    if (mode == PB200_ARITH_STRICT && (e->gr == PB200_GR_ANDERSON1975 || e->gr == PB200_GR_NEWHALL1983))
+        return set_error(PB200_E_UNSUPPORTED, "PB200_ARITH_STRICT covers GR Kidder1995 (or no GR); Anderson1975 / Newhall1983 run in PB200_ARITH_FAST");
+    e->arithmetic = mode;
     return PB200_OK;
 }
 

@@ -305,6 +305,8 @@ enum ColdSlot : int {
     C_INVI, C_AS, C_AP, C_BK, C_KS, C_KP, C_IH, C_INVM, C_INVMH, C_MH, C_MGS, C_GRF, C_MURED, C_MD, C_MOM, C_FMS, C_FMP,
     // constants of the coordinate transforms (strict)
     K_MH, K_MGH, K_MTOT, K_KMU, K_BACKW, K_WHDSF, K_ETAK,
+    // strict arithmetic mode (strict_effects.cuh): two more constants and the 4-vector exchange buffer for the host sums
+    Z_0, Z_1, X_0, X_1, X_2, X_3, X_4, X_5, X_6, X_7, X_8, X_9, X_10, X_11,
     N_COLD_SLOTS
 };
 

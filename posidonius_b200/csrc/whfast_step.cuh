@@ -6,6 +6,7 @@
 // shuffles (every lane carries the running sum, so all lanes hold bit-identical copies).
 #pragma once
 #include "gr_variants.cuh"
+#include "strict_effects.cuh"
 
 namespace pb200 {
 
@@ -93,7 +94,7 @@ __device__ __forceinline__ S3 ordered_diff_others(S3 init, S3 x, int gb, int n, 
 // Implicit midpoint on v and L (whfast.rs:322-466) around Universe::calculate_additional_effects.
 // Registers across the evaluation: v, L, spin, heliocentric position and 1/r. Originals, increments and Kahan
 // residuals sit in the cold slots and are touched once per iteration.
-template <int COORD, int GR>
+template <int COORD, int GR, int ARITH>
 __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, bool alive, Lane& q,
                                          double t, bool evolution, unsigned int& warnings, bool save_tides, size_t sys) {
     const int W = P.W;
@@ -101,8 +102,10 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
     // positions do not change inside the midpoint: heliocentric position and 1/r once (universe.rs:318-351)
     const S3 rh_s = shfl3(q.r, hl);
     // idle lanes (host slot, padding) get a unit dummy so that rsqrt/div stay on their fast paths for the whole warp
-    const V3 hr = ro.planet ? plain(q.r - rh_s) : v3(1., 0., 0.);
-    const double inv_d = rsqrt(dot(hr, hr));
+    const S3 hr_s = ro.planet ? q.r - rh_s : s3(sd(1.), sd(0.), sd(0.));
+    const V3 hr = plain(hr_s);
+    const double inv_d = ARITH ? 0. : rsqrt(dot(hr, hr));
+    const sd dist_s = ARITH ? ssqrt(hr_s.x * hr_s.x + hr_s.y * hr_s.y + hr_s.z * hr_s.z) : sd(1.);   // universe.rs:328-330
     cold.set3(S_RX, plain(q.r));
     cold.set3(S_VOX, plain(q.v)); cold.set3(S_LOX, q.L);
     cold.set3(S_DVX, v3(0., 0., 0.)); cold.set3(S_DLX, v3(0., 0., 0.));
@@ -112,13 +115,19 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
     for (int it = 0; it < 10; it++) {
         if (!__any_sync(FULL, !done)) break;
         if (evolution && it == 0 && (P.flags & FLAG_EVO)) {
-            bool changed = evolve_lane(P, ro, cold, b, sys, t, alive);
-            if (__any_sync(FULL, changed)) make_consts(P, ro, cold, hl, b, sys);
+            // once per step in evolving configurations: re-derive the constants unconditionally (warp-uniform control flow
+            // around the shuffles inside make_consts*)
+            (void)evolve_lane(P, ro, cold, b, sys, t, alive);
+            __syncwarp();
+            if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
         }
-        V3 hv = plain(q.v - shfl3(q.v, hl));
+        const S3 vh_s = shfl3(q.v, hl);   // every lane takes part in the shuffle; the select comes after
+        const S3 hv_s = ro.planet ? q.v - vh_s : s3(sd(0.), sd(1.), sd(0.));
+        V3 hv = plain(hv_s);
         V3 a, dldt;
         double scratch[PB_TIDE_SCRATCH];
-        additional_effects<GR>(P, ro, cold, hl, q, hr, inv_d, hv, a, dldt, save_tides ? scratch : nullptr);
+        if (ARITH) additional_effects_strict<GR>(P, ro, cold, hl, b, q, hr_s, dist_s, hv_s, a, dldt, save_tides ? scratch : nullptr);
+        else additional_effects<GR>(P, ro, cold, hl, q, hr, inv_d, hv, a, dldt, save_tides ? scratch : nullptr);
         if (save_tides && (P.flags & FLAG_TIDES) && ro.valid && !done) {
             const size_t ns = (size_t)P.n_sys;
             const size_t i = (size_t)b * ns + sys, cs = (size_t)P.n_bodies * ns;
@@ -233,7 +242,7 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const C
 
 extern __shared__ double pb_smem[];
 
-template <int COORD, int GR>
+template <int COORD, int GR, int ARITH>
 __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
     const int W = P.W;
     const int n = P.n_bodies;
@@ -284,7 +293,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
         st.steps_done = 0; st.n_hist_new = 0; st.event_step = 0;
     }
     bool alive = sys_ok && st.status == PB200_STATUS_OK;
-    make_consts(P, ro, cold, hl, b, sys);
+    if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
 
     // constants of the transforms, all strict and in the reference's order; parked in the cold slots
     {
@@ -325,10 +334,12 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
             bool snap = alive && (first || due);
             if (__any_sync(FULL, snap)) {
                 // refresh: evolving quantities and spin = L / I (universe.rs:305-316); it changes the live state too
-                bool changed = false;
-                if (P.flags & FLAG_EVO) changed = evolve_lane(P, ro, cold, b, sys, st.t, snap);
-                if (__any_sync(FULL, changed)) make_consts(P, ro, cold, hl, b, sys);
-                if (snap) q.s = cold.get(C_INVI) * q.L;
+                if (P.flags & FLAG_EVO) {
+                    (void)evolve_lane(P, ro, cold, b, sys, st.t, snap);
+                    __syncwarp();
+                    if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
+                }
+                if (snap) { sd I = sd(cold.get(K_I)); q.s = v3((sd(q.L.x) / I).v, (sd(q.L.y) / I).v, (sd(q.L.z) / I).v); }   // spin = L / I (common.rs:9-11)
                 if (snap && ro.valid && st.hist_count < P.hist_capacity) {
                     const size_t ns = (size_t)P.n_sys;
                     const size_t i = (size_t)b * ns + sys, cs = (size_t)n * ns;
@@ -504,7 +515,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     }
                 }
             }
-            midpoint<COORD, GR>(P, ro, cold, gb, hl, b, alive, q, st.t, half == 0, st.warnings, half == 1 && save_tides, sys);
+            midpoint<COORD, GR, ARITH>(P, ro, cold, gb, hl, b, alive, q, st.t, half == 0, st.warnings, half == 1 && save_tides, sys);
         }
 
         if (alive) {

@@ -34,8 +34,9 @@ def validate_case(case, tables):
 
 
 class Ensemble:
-    def __init__(self, cases, tables, n_systems=None, device=0):
-        """cases: one abi.Case (replicated n_systems times) or a ctypes array / list of n_systems cases."""
+    def __init__(self, cases, tables, n_systems=None, device=0, arithmetic=abi.ARITH_FAST):
+        """cases: one abi.Case (replicated n_systems times) or a ctypes array / list of n_systems cases.
+        arithmetic: abi.ARITH_FAST (default) or abi.ARITH_STRICT (bit-reproducible forces, see the header)."""
         if isinstance(cases, abi.Case):
             arr = (abi.Case * 1)(cases)
             n_cases = 1
@@ -52,6 +53,11 @@ class Ensemble:
         self.n_systems = n_systems
         self.n_particles = lib().pb200_ensemble_n_particles(self._h)
         self.device = device
+        if arithmetic != abi.ARITH_FAST:
+            self.set_arithmetic(arithmetic)
+
+    def set_arithmetic(self, mode):
+        _check(lib().pb200_ensemble_set_arithmetic(self._h, mode))
 
     # -- lifetime
     def close(self):

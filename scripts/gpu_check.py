@@ -28,6 +28,8 @@ def load(rel):
 
 def main():
     steps_cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+    arith = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    n_members = int(sys.argv[3]) if len(sys.argv) > 3 else 64
     man = json.load(open(os.path.join(G, "manifest.json")))
     print("fp64 peak (DFMA chain): %.2f TFLOP/s" % (measure_fp64_peak() / 1e12))
     for name, fx in sorted(man["fixtures"].items()):
@@ -47,9 +49,9 @@ def main():
         ens.close()
     for idx, name in enumerate(["c1_example", "c2_case3", "c3_case7", "c3_case7_evolving", "c4_trappist1", "c5_circumbinary"]):
         case, tables = case_from_dict(load("configs/%s.json.gz" % name))
-        n_sys = 64
+        n_sys = n_members
         cases = make_ensemble_cases(case, n_sys, 20261017 + idx)
-        ens = Ensemble(cases, tables)
+        ens = Ensemble(cases, tables, arithmetic=arith)
         ens.initialize_physical_values()
         t0 = time.time()
         ens.iterate(steps_cfg)

@@ -54,13 +54,13 @@ def test_golden_fixture_on_gpu(E, name):
                     assert np.all(np.abs(got - want) < fx["tolerance_abs"]), (name, s, i, key, got, want)
 
 
-def _run_config(E, idx, name, n_sys, steps):
+def _run_config(E, idx, name, n_sys, steps, arithmetic=0):
     from oracle.binding import run_ensemble
     from posidonius_b200.case import case_from_dict
     from posidonius_b200.perturb import make_ensemble_cases
     case, tables = case_from_dict(config_case(name))
     cases = make_ensemble_cases(case, n_sys, 20261017 + idx)
-    with E.Ensemble(cases, tables) as ens:
+    with E.Ensemble(cases, tables, arithmetic=arithmetic) as ens:
         ens.initialize_physical_values()
         ens.iterate(steps)
         g = gpu_state_of(ens)
@@ -86,6 +86,44 @@ def test_config_ensemble_vs_oracle_1e4_steps(E, idx, name):
     assert np.array_equal(st, ost)
     for k in ("position", "velocity", "spin"):
         assert rel_err(g[k], o[k]) < FAST_TOL_1E4, (name, k, rel_err(g[k], o[k]))
+
+
+@pytest.mark.parametrize("idx,name", list(enumerate(CONFIG_NAMES)))
+def test_strict_mode_is_bit_identical_to_oracle_1e4_steps(E, idx, name):
+    """PB200_ARITH_STRICT: every member of every configuration ensemble equals the CPU oracle BIT FOR BIT in r, v, L,
+    spin and the Kahan residuals after 10^4 steps (the oracle itself is bit-exact against the reference goldens)."""
+    from posidonius_b200 import abi
+    g, o, st, ost = _run_config(E, idx, name, 16, 10000, arithmetic=abi.ARITH_STRICT)
+    assert np.array_equal(st, ost)
+    for k in ("position", "velocity", "angular_momentum", "spin", "velocity_errors", "angular_momentum_errors", "current_time"):
+        assert np.array_equal(g[k], o[k]), (name, k, rel_err(g[k], o[k]) if g[k].ndim == 3 else None)
+
+
+def test_strict_mode_golden_fixtures_bit_exact(E):
+    from posidonius_b200 import abi
+    from posidonius_b200.case import case_from_dict
+    for name in ("test_integrator-whfast_jacobi", "test_integrator-whfast_democraticheliocentric", "test_integrator-whfast_whds",
+                 "test_evolution-m_dwarf_baraffe2015", "test_general_relativity-none"):
+        fx = _MANIFEST["fixtures"][name]
+        case, tables = case_from_dict(load_json_gz(fx["case"]))
+        with E.Ensemble(case, tables, n_systems=3, arithmetic=abi.ARITH_STRICT) as ens:
+            ens.initialize_physical_values()
+            ens.iterate(10 ** 6)
+            out = ens.get_case(2)
+            for i, exp in enumerate(fx["particles"]):
+                for key in ("inertial_position", "inertial_velocity", "inertial_acceleration"):
+                    got = list(getattr(out.bodies[i], key)[:])
+                    want = [exp[key]["x"], exp[key]["y"], exp[key]["z"]]
+                    assert got == want, (name, i, key, got, want)
+
+
+def test_strict_mode_rejects_unported_gr_variants(E):
+    from posidonius_b200 import abi
+    from posidonius_b200.case import UnsupportedCaseError, case_from_dict
+    fx = _MANIFEST["fixtures"]["test_general_relativity-newhall1983"]
+    case, tables = case_from_dict(load_json_gz(fx["case"]))
+    with pytest.raises(UnsupportedCaseError):
+        E.Ensemble(case, tables, arithmetic=abi.ARITH_STRICT)
 
 
 def test_energy_and_angular_momentum_drift_match_oracle(E):
