@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libposidonius_b200.so")
 SOURCES = ["pb200_api.cu"]
-HEADERS = ["whfast_kernel.cuh", "gr_variants.cuh", "whfast_step.cuh"]
+HEADERS = ["strict.cuh", "whfast_kernel.cuh", "forces_fast.cuh", "gr_variants.cuh", "strict_effects.cuh", "whfast_step.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--fmad=true", "-Xptxas", "-v",

@@ -1,0 +1,182 @@
+// forces_fast.cuh — PB200_ARITH_FAST perturbation forces (tides, flattening, GR Kidder1995) and their per-system constants.
+// Included once per geometry specialisation (see pb200_api.cu), inside namespace PB_NS; no include guard on purpose.
+#include "whfast_kernel.cuh"
+
+namespace PB_NS {
+using namespace pb200;
+
+// Derives the force constants from masses, radii and dissipation parameters (cold path: launch start and whenever a
+// radius evolves). sigma / k2 are fetched from global memory here, they are not kept on chip.
+__device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys) {
+    double sigma = 0., k2t = 0., k2f = 0.;
+    if (ro.valid) {
+        const size_t i = (size_t)b * (size_t)P.n_sys + sys;
+        sigma = P.sigma[i]; k2t = P.k2t[i]; k2f = P.k2f[i];
+    }
+    const double m = cold.get(K_M), mg = cold.get(K_MG), R = cold.get(K_R), I = cold.get(K_I);
+    const double M = shfl(m, hl), Mg = shfl(mg, hl), Ih = shfl(I, hl);
+    const double Rh5 = pow5(shfl(R, hl));
+    const double R5 = pow5(R);
+    const double sig_h = shfl(sigma, hl), k2t_h = shfl(k2t, hl), k2f_h = shfl(k2f, hl);
+    const double m2 = m * m, M2 = M * M;
+    cold.set(C_INVI, 1. / I);
+    cold.set(C_AS, 4.5 * m2 * (Rh5 * Rh5) * sig_h);               // 4.5 m^2 R*^10 sigma*   (constant_time_lag.rs:232-234)
+    cold.set(C_AP, 4.5 * M2 * (R5 * R5) * sigma);                 // 4.5 M^2 R^10 sigma     (constant_time_lag.rs:243-245)
+    cold.set(C_BK, 3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * k2t)); // 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2) (:283-285)
+    cold.set(C_KS, m * k2f_h * Rh5);                              // flattening: m k2f* R*^5 (oblate_spheroid.rs:37)
+    cold.set(C_KP, M * k2f * R5);                                 //             M k2f R^5   (oblate_spheroid.rs:42)
+    cold.set(C_IH, Ih);
+    cold.set(C_INVM, 1. / m); cold.set(C_INVMH, 1. / M); cold.set(C_MH, M);
+    const double mgs = Mg + mg;
+    cold.set(C_MGS, mgs);
+    cold.set(C_GRF, Mg * mg / (mgs * mgs));                       // general_relativity.rs:98
+    cold.set(C_MURED, (M * m) / (M + m));                         // general_relativity.rs:383
+    cold.set(C_MD, M - m);                                        // mass_factor * star_planet_mass (:319-321, 336)
+    cold.set(C_MOM, m / M);
+    cold.set(C_FMS, 2. + 1.5 * m / M);                            // :390
+    cold.set(C_FMP, 2. + 1.5 * M / m);                            // :419
+    // polynomials in the GR factor f of the 1PN / 2PN terms (general_relativity.rs:197-205, 256-268): per-system constants
+    const double f = Mg * mg / (mgs * mgs), f2 = f * f;
+    cold.set(G_0, 1.0 + 3.0 * f);
+    cold.set(G_0 + 1, 2.0 * (2.0 + f));
+    cold.set(G_0 + 2, 1.5 * f);
+    cold.set(G_0 + 3, 2.0 * (2.0 - f));
+    cold.set(G_0 + 4, 0.75 * (12.0 + 29.0 * f));
+    cold.set(G_0 + 5, f * (3.0 - 4.0 * f));
+    cold.set(G_0 + 6, 1.875 * f * (1.0 - 3.0 * f));
+    cold.set(G_0 + 7, 1.5 * f * (3.0 - 4.0 * f));
+    cold.set(G_0 + 8, 0.5 * f * (13.0 - 4.0 * f));
+    cold.set(G_0 + 9, 2.0 + 25.0 * f + 2.0 * f2);
+    cold.set(G_0 + 10, f * (15.0 + 4.0 * f));
+    cold.set(G_0 + 11, 4.0 + 41.0 * f + 8.0 * f2);
+    cold.set(G_0 + 12, 3.0 * f * (3.0 + 2.0 * f));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Universe::calculate_additional_effects for the lane's body at (hr, hv) with the current L
+// (universe.rs:428-614). Returns the inertial additional acceleration and dL/dt of THIS body;
+// host-lane values are the group reductions.
+template <int GR>
+__device__ __forceinline__ void additional_effects(const KParams& P, const Roles& ro, const Cold& cold, int hl, Lane& q, V3 hr,
+                                                   double inv_d, V3 hv, V3& a_out, V3& dl_out, double* tide_save) {
+    const int W = PB_W(P);
+    // Q3: r.omega uses the spins of the previous evaluation (universe.rs:429-430)
+    V3 s_host_prev = shfl3(q.s, hl);
+    double rs_s = dot(hr, s_host_prev), rs_p = dot(hr, q.s);
+    // calculate_spin (particles/common.rs:3-15)
+    q.s = cold.get(C_INVI) * q.L;
+    double w2 = dot(q.s, q.s);
+    V3 sh = shfl3(q.s, hl);
+    double wh2 = shfl(w2, hl);
+    double inv_d2 = inv_d * inv_d;
+    double d = dot(hr, hr) * inv_d;
+    double radvel = dot(hr, hv) * inv_d;
+    V3 rxv = cross(hr, hv);
+    V3 a_p = v3(0., 0., 0.), dl_p = v3(0., 0., 0.);       // this body's own acceleration / torque
+    V3 a_h = v3(0., 0., 0.), dl_h = v3(0., 0., 0.);       // contribution to the host
+    const double inv_m = cold.get(C_INVM), inv_M = cold.get(C_INVMH);
+    if (P.flags & FLAG_TIDES) {
+        // constant_time_lag.rs:206-332, tides/common.rs:223-345
+        double inv_d4 = inv_d2 * inv_d2;
+        double inv_d7 = inv_d4 * inv_d2 * inv_d;
+        double Fos = P.tides_host_central ? cold.get(C_AS) * inv_d7 : 0.;
+        double Fop = cold.get(C_AP) * inv_d7;
+        double Fsum = Fos + Fop;
+        // radial: conservative + dissipative (-13.5 vr/r^8 (...) = -3 vr/r (Fos + Fop))
+        double f3 = -cold.get(C_BK) * inv_d7 - 2.0 * Fsum * radvel * inv_d;
+        V3 wxr_s = cross(sh, hr), wxr_p = cross(q.s, hr);
+        double k3 = f3 * inv_d, ks = Fos * inv_d, kp = Fop * inv_d;
+        V3 F = v3(k3 * hr.x + ks * (wxr_s.x - hv.x) + kp * (wxr_p.x - hv.x),
+                  k3 * hr.y + ks * (wxr_s.y - hv.y) + kp * (wxr_p.y - hv.y),
+                  k3 * hr.z + ks * (wxr_s.z - hv.z) + kp * (wxr_p.z - hv.z));
+        // torques (eqs 8-9 Bolmont+2015): N = Forth (d w - (r.w) r/d - (r x v)/d); dL/dt = -N
+        V3 Np = v3(Fop * (d * q.s.x - (rs_p * hr.x + rxv.x) * inv_d), Fop * (d * q.s.y - (rs_p * hr.y + rxv.y) * inv_d),
+                   Fop * (d * q.s.z - (rs_p * hr.z + rxv.z) * inv_d));
+        V3 Ns = v3(Fos * (d * sh.x - (rs_s * hr.x + rxv.x) * inv_d), Fos * (d * sh.y - (rs_s * hr.y + rxv.y) * inv_d),
+                   Fos * (d * sh.z - (rs_s * hr.z + rxv.z) * inv_d));
+        if (ro.t_on) {
+            a_p = a_p + inv_m * F;
+            a_h = a_h - inv_M * F;
+            dl_p = dl_p - Np;
+            dl_h = dl_h - Ns;
+        }
+        if (tide_save) {
+            // internals that calculate_denergy_dt (tides/common.rs:263-279) will read at the next snapshot
+            tide_save[0] = hr.x; tide_save[1] = hr.y; tide_save[2] = hr.z;
+            tide_save[3] = hv.x; tide_save[4] = hv.y; tide_save[5] = hv.z;
+            tide_save[6] = d; tide_save[7] = radvel; tide_save[8] = Fop;
+            tide_save[9] = -3.0 * Fop * radvel * inv_d;  // dissipative radial part with the star as a point mass
+            tide_save[10] = -Np.x; tide_save[11] = -Np.y; tide_save[12] = -Np.z;
+        }
+    }
+    if (P.flags & FLAG_FLAT) {
+        // oblate_spheroid.rs:12-97, rotational_flattening/common.rs:165-237
+        double inv_d5 = inv_d2 * inv_d2 * inv_d;
+        double inv_d7 = inv_d5 * inv_d2;
+        double Ks = P.flat_host_central ? cold.get(C_KS) : 0.;
+        double Kp = cold.get(C_KP);
+        double Fos = -Ks * rs_s * inv_d5;
+        double Fop = -Kp * rs_p * inv_d5;
+        double Frad = -0.5 * inv_d5 * (Ks * wh2 + Kp * w2) + 2.5 * inv_d7 * (Ks * rs_s * rs_s + Kp * rs_p * rs_p);
+        V3 F = v3(Frad * hr.x + Fop * q.s.x + Fos * sh.x, Frad * hr.y + Fop * q.s.y + Fos * sh.y, Frad * hr.z + Fop * q.s.z + Fos * sh.z);
+        V3 Np = Fop * cross(hr, q.s);
+        V3 Ns = Fos * cross(hr, sh);
+        if (ro.f_on) {
+            a_p = a_p + inv_m * F;
+            a_h = a_h - inv_M * F;
+            dl_p = dl_p - Np;
+            dl_h = dl_h - Ns;
+        }
+    }
+    if (GR == PB200_GR_KIDDER1995) {
+        // general_relativity.rs:177-456
+        double v2 = dot(hv, hv);
+        double mgs = cold.get(C_MGS);
+        double A = mgs * inv_d2 * kInvC2;
+        double u = mgs * inv_d;
+        double rv2 = radvel * radvel;
+        // 1PN; the orthoradial term divides by |v| and multiplies by |v|: cancelled. Coefficients G_k: make_consts.
+        double rad = -A * (cold.get(G_0) * v2 - cold.get(G_0 + 1) * u - cold.get(G_0 + 2) * rv2);
+        double orth = A * cold.get(G_0 + 3) * radvel;
+        // 2PN (Kidder 1995 eq. 2.2d)
+        rad += -A * (cold.get(G_0 + 4) * (u * u) + cold.get(G_0 + 5) * (v2 * v2) + cold.get(G_0 + 6) * (rv2 * rv2)
+                     - cold.get(G_0 + 7) * rv2 * v2 - cold.get(G_0 + 8) * u * v2 - cold.get(G_0 + 9) * u * rv2);
+        orth += 0.5 * A * radvel * (cold.get(G_0 + 10) * v2 - cold.get(G_0 + 11) * u - cold.get(G_0 + 12) * rv2);
+        double kr = rad * inv_d;
+        V3 a = v3(kr * hr.x + orth * hv.x, kr * hr.y + orth * hv.y, kr * hr.z + orth * hv.z);
+        // 1.5PN spin-orbit (:300-456); component-wise products exactly as the reference writes them
+        V3 Ls = cold.get(C_IH) * sh, Lp = cold.get(K_I) * q.s;
+        V3 nn = inv_d * hr;
+        double md = cold.get(C_MD);
+        V3 msf = v3(md * (Lp.x * inv_m - Ls.x * inv_M), md * (Lp.y * inv_m - Ls.y * inv_M), md * (Lp.z * inv_m - Ls.z * inv_M));
+        V3 S = Ls + Lp;
+        V3 nxv = cross(nn, hv);
+        V3 e1 = v3(6. * nn.x * (nxv.x * (2. * S.x + msf.x)), 6. * nn.y * (nxv.y * (2. * S.y + msf.y)), 6. * nn.z * (nxv.z * (2. * S.z + msf.z)));
+        V3 e7 = v3(7. * S.x + 3. * msf.x, 7. * S.y + 3. * msf.y, 7. * S.z + 3. * msf.z);
+        V3 e2 = cross(hv, e7);
+        V3 e3s = v3(3. * S.x + msf.x, 3. * S.y + msf.y, 3. * S.z + msf.z);
+        V3 e3 = (3. * radvel) * cross(nn, e3s);
+        const double fa = kG * kInvC2;
+        a = a + fa * (e1 - e2 + e3);
+        // Kidder 1995 eqs 2.4a, 2.4b
+        V3 Lo = cold.get(C_MURED) * rxv;
+        V3 LpxLs = cross(Lp, Ls);
+        V3 ds = cold.get(C_FMS) * cross(Lo, Ls) - LpxLs + (3. * dot(nn, Lp)) * cross(nn, Ls);
+        V3 dp = cold.get(C_FMP) * cross(Lo, Lp) + LpxLs + (3. * dot(nn, Ls)) * cross(nn, Lp);
+        if (ro.g_on) {
+            a_p = a_p + a;
+            a_h = a_h - cold.get(C_MOM) * a;
+            dl_p = dl_p + fa * dp;
+            dl_h = dl_h + fa * ds;
+        }
+    }
+    // zero out lanes that are not orbiting bodies, then reduce onto the host
+    if (!ro.planet) { a_h = v3(0., 0., 0.); dl_h = v3(0., 0., 0.); a_p = v3(0., 0., 0.); dl_p = v3(0., 0., 0.); }
+    a_h = group_sum3(a_h, W);
+    dl_h = group_sum3(dl_h, W);
+    a_out = ro.host ? a_h : a_p;
+    dl_out = ro.host ? dl_h : dl_p;
+}
+
+
+}  // namespace PB_NS

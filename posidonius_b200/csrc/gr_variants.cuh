@@ -2,17 +2,17 @@
 // reference, effects/general_relativity.rs:461-895). Lane = body; the serial Jacobi recurrences are
 // carried redundantly by every lane of the group, the all-pairs sums of Newhall walk the group with
 // shuffles. These variants are selected by one fixture each upstream; they are correct, not tuned.
-#pragma once
-#include "whfast_kernel.cuh"
+#include "forces_fast.cuh"
 
-namespace pb200 {
+namespace PB_NS {
+using namespace pb200;
 
 // Newtonian inertial accelerations with the terms WHFast ignored re-added (general_relativity.rs:641-678).
 // jacobi_coords: IgnoreGravityTerms::WHFastOne (only the first non-host particle is re-added), else WHFastTwo.
 __device__ __forceinline__ V3 gr_newtonian(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, const Lane& q, V3 hr,
                                            V3 acc_newton, bool jacobi_coords) {
     const double q_m = cold.get(K_M);
-    const int first_other = P.host == 0 ? 1 : 0;
+    const int first_other = PB_HOST(P) == 0 ? 1 : 0;
     bool included = ro.planet && (!jacobi_coords || b == first_other);
     V3 rh = shfl3(plain(q.r), hl);
     double M = shfl(q_m, hl);
@@ -25,8 +25,8 @@ __device__ __forceinline__ V3 gr_newtonian(const KParams& P, const Roles& ro, co
     V3 own = included ? (prefac * M) * dx : v3(0., 0., 0.);
     // ordered sum over the non-host bodies, as the reference accumulates
     V3 hsum = v3(0., 0., 0.);
-    for (int k = 0; k < P.n_bodies; k++) {
-        if (k == P.host) continue;
+    for (int k = 0; k < PB_N(P); k++) {
+        if (k == PB_HOST(P)) continue;
         V3 t = shfl3(to_host, gb + k);
         hsum = hsum + t;
     }
@@ -44,8 +44,8 @@ __device__ __forceinline__ void gr_anderson1975(const KParams& P, const Roles& r
     double eta = shfl(q_m, hl);
     V3 s = eta * shfl3(plain(q.r), hl), sv = eta * shfl3(plain(q.v), hl), sa = eta * shfl3(an, hl);
     V3 jp = v3(0., 0., 0.), jv = v3(0., 0., 0.), ja = v3(0., 0., 0.);
-    for (int k = 0; k < P.n_bodies; k++) {
-        if (k == P.host || !((P.gr_orbiting >> k) & 1u)) continue;
+    for (int k = 0; k < PB_N(P); k++) {
+        if (k == PB_HOST(P) || !((P.gr_orbiting >> k) & 1u)) continue;
         double mk = shfl(q_m, gb + k);
         V3 rk = shfl3(plain(q.r), gb + k), vk = shfl3(plain(q.v), gb + k), ak = shfl3(an, gb + k);
         double ei = 1. / eta;
@@ -88,8 +88,8 @@ __device__ __forceinline__ void gr_anderson1975(const KParams& P, const Roles& r
     eta = jacobi_star_mass;
     V3 sacc = v3(0., 0., 0.);
     V3 mine = v3(0., 0., 0.);
-    for (int k = P.n_bodies - 1; k >= 0; k--) {
-        if (k == P.host || !((P.gr_orbiting >> k) & 1u)) continue;
+    for (int k = PB_N(P) - 1; k >= 0; k--) {
+        if (k == PB_HOST(P) || !((P.gr_orbiting >> k) & 1u)) continue;
         double mk = shfl(q_m, gb + k);
         V3 jk = shfl3(ja, gb + k);
         double ei = 1. / eta;
@@ -107,14 +107,14 @@ __device__ __forceinline__ void gr_newhall1983(const KParams& P, const Roles& ro
                                                V3 acc_newton, bool jacobi_coords, V3& a_out) {
     const double q_m = cold.get(K_M);
     V3 an = gr_newtonian(P, ro, cold, gb, hl, b, q, hr, acc_newton, jacobi_coords);
-    const int n = P.n_bodies;
+    const int n = PB_N(P);
     const bool en_i = (P.gr_enabled >> b) & 1u;
     const V3 qr = plain(q.r), qv = plain(q.v);
     // potential-like sums: pot_i = sum_{k != i} G m_k / r_ik
     double pot = 0.;
     for (int kk = -1; kk < n; kk++) {
-        int k = kk < 0 ? P.host : kk;
-        if (kk == P.host) continue;
+        int k = kk < 0 ? PB_HOST(P) : kk;
+        if (kk == PB_HOST(P)) continue;
         double mk = shfl(q_m, gb + k);
         V3 rk = shfl3(qr, gb + k);
         if (k == b) continue;
@@ -124,8 +124,8 @@ __device__ __forceinline__ void gr_newhall1983(const KParams& P, const Roles& ro
     double vi2 = dot(qv, qv);
     V3 ac = v3(0., 0., 0.);
     for (int kk = -1; kk < n; kk++) {
-        int j = kk < 0 ? P.host : kk;
-        if (kk == P.host) continue;
+        int j = kk < 0 ? PB_HOST(P) : kk;
+        if (kk == PB_HOST(P)) continue;
         double mj = shfl(q_m, gb + j);
         V3 rj = shfl3(qr, gb + j), vj = shfl3(qv, gb + j);
         double potj = shfl(pot, gb + j);
@@ -158,8 +158,8 @@ __device__ __forceinline__ void gr_newhall1983(const KParams& P, const Roles& ro
         V3 nc = v3(0., 0., 0.);
         V3 tot = an + a_old;
         for (int kk = -1; kk < n; kk++) {
-            int j = kk < 0 ? P.host : kk;
-            if (kk == P.host) continue;
+            int j = kk < 0 ? PB_HOST(P) : kk;
+            if (kk == PB_HOST(P)) continue;
             double mj = shfl(q_m, gb + j);
             V3 rj = shfl3(qr, gb + j);
             V3 tj = shfl3(tot, gb + j);
@@ -183,7 +183,7 @@ __device__ __forceinline__ void gr_newhall1983(const KParams& P, const Roles& ro
         }
         // group max (NaN compares false, as in the reference)
         double mx = dev;
-        for (int off = P.W >> 1; off > 0; off >>= 1) { double o = shfl_xor(mx, off); mx = o > mx ? o : mx; }
+        for (int off = PB_W(P) >> 1; off > 0; off >>= 1) { double o = shfl_xor(mx, off); mx = o > mx ? o : mx; }
         if (!group_done) {
             a_new = cand;
             if (mx < dev_limit) group_done = true;
@@ -192,4 +192,4 @@ __device__ __forceinline__ void gr_newhall1983(const KParams& P, const Roles& ro
     a_out = (ro.host || ro.g_on) ? a_new : v3(0., 0., 0.);
 }
 
-}  // namespace pb200
+}  // namespace PB_NS

@@ -8,7 +8,31 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include "whfast_kernel.cuh"
+
+// The device code of the step is compiled twice: for any geometry at run time (pbgen) and for exactly 8 bodies with the
+// host at index 0 (pbn8: the TRAPPIST-1 layout — body loops unroll, shuffle lanes are immediates).
+#define PB_NS pbgen
+#define PB_FIXED_N 0
+#define PB_FIXED_W 0
+#define PB_FIXED_SHIFT 0
 #include "whfast_step.cuh"
+#undef PB_NS
+#undef PB_FIXED_N
+#undef PB_FIXED_W
+#undef PB_FIXED_SHIFT
+#define PB_NS pbn8
+#define PB_FIXED_N 8
+#define PB_FIXED_W 8
+#define PB_FIXED_SHIFT 3
+#include "whfast_step.cuh"
+#undef PB_NS
+#undef PB_FIXED_N
+#undef PB_FIXED_W
+#undef PB_FIXED_SHIFT
+#define PB_FIXED_N 0
+#define PB_FIXED_W 0
+#define PB_FIXED_SHIFT 0
 
 using namespace pb200;
 
@@ -169,6 +193,7 @@ struct pb200_ensemble {
     size_t records_capacity = 0;
     double recovery_snapshot_period = 0.;
     int arithmetic = PB200_ARITH_FAST;
+    bool force_generic = false;   // PB200_FORCE_GENERIC=1 in the environment: bypass the 8-body specialisation (A/B tests)
     // host mirror of the ensemble clock (exact snapshot counting without a device round trip)
     bool uniform_clock = true;
     double clock_t = 0., clock_last_hist = -1.;
@@ -197,11 +222,24 @@ static cudaError_t launch_one(pb200_ensemble* e, unsigned grid, unsigned long lo
     // the cold slots need more than the default 48 KB of dynamic shared memory
     static thread_local int configured_device = -1;
     if (configured_device != e->device) {
-        cudaError_t err = cudaFuncSetAttribute(whfast_steps_kernel<COORD, GR, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
+        cudaError_t err = cudaFuncSetAttribute(pbgen::whfast_steps_kernel<COORD, GR, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
         if (err != cudaSuccess) return err;
         configured_device = e->device;
     }
-    whfast_steps_kernel<COORD, GR, ARITH><<<grid, PB_BLOCK, PB_SMEM_BYTES, e->stream>>>(e->P, n);
+    pbgen::whfast_steps_kernel<COORD, GR, ARITH><<<grid, PB_BLOCK, PB_SMEM_BYTES, e->stream>>>(e->P, n);
+    return cudaGetLastError();
+}
+
+// 8 bodies, host at index 0, democratic heliocentric, Kidder1995, fast arithmetic: the specialised instance
+static cudaError_t launch_n8(pb200_ensemble* e, unsigned grid, unsigned long long n) {
+    static thread_local int configured_device = -1;
+    auto kernel = pbn8::whfast_steps_kernel<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995, 0>;
+    if (configured_device != e->device) {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
+        if (err != cudaSuccess) return err;
+        configured_device = e->device;
+    }
+    kernel<<<grid, PB_BLOCK, PB_SMEM_BYTES, e->stream>>>(e->P, n);
     return cudaGetLastError();
 }
 
@@ -344,6 +382,7 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     e->gr = c0.consider_general_relativity ? c0.general_relativity_implementation : PB200_GR_DISABLED;
     e->recovery_snapshot_period = c0.recovery_snapshot_period;
     e->clock_t = c0.current_time; e->clock_last_hist = c0.last_historic_snapshot_time;
+    { const char* fg = getenv("PB200_FORCE_GENERIC"); e->force_generic = fg && fg[0] == '1'; }
     for (size_t s = 1; s < n_cases; s++)
         if (cases[s].current_time != c0.current_time || cases[s].last_historic_snapshot_time != c0.last_historic_snapshot_time) e->uniform_clock = false;
     KParams& P = e->P;
@@ -559,7 +598,10 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
     {
         cudaError_t err;
-        switch (e->coord) {
+        const bool n8 = e->n_bodies == 8 && e->P.host == 0 && e->coord == PB200_COORD_DEMOCRATIC_HELIOCENTRIC &&
+                        e->gr == PB200_GR_KIDDER1995 && e->arithmetic == PB200_ARITH_FAST && !e->force_generic;
+        if (n8) err = launch_n8(e, grid, n_steps);
+        else switch (e->coord) {
             case PB200_COORD_JACOBI: err = launch_gr<PB200_COORD_JACOBI>(e, grid, n_steps); break;
             case PB200_COORD_DEMOCRATIC_HELIOCENTRIC: err = launch_gr<PB200_COORD_DEMOCRATIC_HELIOCENTRIC>(e, grid, n_steps); break;
             default: err = launch_gr<PB200_COORD_WHDS>(e, grid, n_steps); break;

@@ -6,10 +6,9 @@
 // `powi` follows LLVM's square-and-multiply expansion. Together with the strict core this makes the whole step
 // bit-reproducible against the oracle (tests/test_gpu_parity.py::test_strict_mode_is_bit_identical...).
 // Cost: ~50 true divisions per planet per evaluation instead of 1 rsqrt — about half the throughput of the fast mode.
-#pragma once
-#include "whfast_kernel.cuh"
 
-namespace pb200 {
+namespace PB_NS {
+using namespace pb200;
 
 // strict-mode constants overlay the fast-mode constant slots (C_INVI..C_FMP, 17 slots) plus Z_0, Z_1
 enum StrictSlot : int {
@@ -68,7 +67,7 @@ __device__ __forceinline__ void put3(const Cold& cold, int slot, S3 v) { cold.se
 template <int GR>
 __device__ __forceinline__ void additional_effects_strict(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, Lane& q,
                                                           S3 hr, sd dist, S3 hv, V3& a_out, V3& dl_out, double* tide_save) {
-    const int n = P.n_bodies;
+    const int n = PB_N(P);
     const sd zero = sd(0.);
     // Q3: r.omega with the spins of the previous evaluation (tides/common.rs:155-160 = rotational_flattening/common.rs:105-110)
     const S3 sp_prev = strict(q.s), sh_prev = shfl3(sp_prev, hl);
@@ -156,12 +155,12 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
         __syncwarp();
         if (ro.host) {
             const sd neg_inv_M = sd(-1.0) * inv_M;   // -1.0 * factor2
-            S3 sF = host_ordered_sum(cold, X_0, b, n, P.host);
+            S3 sF = host_ordered_sum(cold, X_0, b, n, PB_HOST(P));
             h_t_acc = s3(neg_inv_M * sF.x, neg_inv_M * sF.y, neg_inv_M * sF.z);
-            h_t_dl = host_ordered_sum(cold, X_0 + 3, b, n, P.host);
-            S3 sG = host_ordered_sum(cold, X_0 + 6, b, n, P.host);
+            h_t_dl = host_ordered_sum(cold, X_0 + 3, b, n, PB_HOST(P));
+            S3 sG = host_ordered_sum(cold, X_0 + 6, b, n, PB_HOST(P));
             h_f_acc = s3(neg_inv_M * sG.x, neg_inv_M * sG.y, neg_inv_M * sG.z);
-            h_f_dl = host_ordered_sum(cold, X_0 + 9, b, n, P.host);
+            h_f_dl = host_ordered_sum(cold, X_0 + 9, b, n, PB_HOST(P));
         }
         __syncwarp();
     }
@@ -240,11 +239,11 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
         put3(cold, X_0, x1); put3(cold, X_0 + 3, x2); put3(cold, X_0 + 6, x3); put3(cold, X_0 + 9, x4);
         __syncwarp();
         if (ro.host) {
-            S3 s1 = host_ordered_sum(cold, X_0, b, n, P.host), s2 = host_ordered_sum(cold, X_0 + 3, b, n, P.host);
-            S3 s3_ = host_ordered_sum(cold, X_0 + 6, b, n, P.host);
+            S3 s1 = host_ordered_sum(cold, X_0, b, n, PB_HOST(P)), s2 = host_ordered_sum(cold, X_0 + 3, b, n, PB_HOST(P));
+            S3 s3_ = host_ordered_sum(cold, X_0 + 6, b, n, PB_HOST(P));
             const sd m1 = sd(-1.0);
             h_g_acc = s3(m1 * s1.x + m1 * s2.x + m1 * s3_.x, m1 * s1.y + m1 * s2.y + m1 * s3_.y, m1 * s1.z + m1 * s2.z + m1 * s3_.z);
-            h_g_dl = host_ordered_sum(cold, X_0 + 9, b, n, P.host);
+            h_g_dl = host_ordered_sum(cold, X_0 + 9, b, n, PB_HOST(P));
         }
         __syncwarp();
     }
@@ -261,4 +260,4 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
     dl_out = plain(dl);
 }
 
-}  // namespace pb200
+}  // namespace PB_NS

@@ -4,11 +4,11 @@
 // The core below is a strict-arithmetic transcription (strict.cuh) of the reference's operation order; sums over
 // bodies that the reference accumulates serially are accumulated in the same order by walking the group with
 // shuffles (every lane carries the running sum, so all lanes hold bit-identical copies).
-#pragma once
 #include "gr_variants.cuh"
 #include "strict_effects.cuh"
 
-namespace pb200 {
+namespace PB_NS {
+using namespace pb200;
 
 #ifndef PB_BLOCK
 #define PB_BLOCK 128
@@ -31,7 +31,7 @@ __device__ __forceinline__ void store_lane(const KParams& P, const Roles& ro, co
     if (!ro.valid) return;
     const size_t ns = (size_t)P.n_sys;
     const size_t i = (size_t)b * ns + sys;
-    const size_t cs = (size_t)P.n_bodies * ns;
+    const size_t cs = (size_t)PB_N(P) * ns;
     P.pos[i] = q.r.x.v; P.pos[i + cs] = q.r.y.v; P.pos[i + 2 * cs] = q.r.z.v;
     P.vel[i] = q.v.x.v; P.vel[i + cs] = q.v.y.v; P.vel[i + 2 * cs] = q.v.z.v;
     P.acc[i] = cold.get(S_AX); P.acc[i + cs] = cold.get(S_AY); P.acc[i + 2 * cs] = cold.get(S_AZ);
@@ -97,7 +97,7 @@ __device__ __forceinline__ S3 ordered_diff_others(S3 init, S3 x, int gb, int n, 
 template <int COORD, int GR, int ARITH>
 __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, bool alive, Lane& q,
                                          double t, bool evolution, unsigned int& warnings, bool save_tides, size_t sys) {
-    const int W = P.W;
+    const int W = PB_W(P);
     const sd dt = sd(P.half_dt);
     // positions do not change inside the midpoint: heliocentric position and 1/r once (universe.rs:318-351)
     const S3 rh_s = shfl3(q.r, hl);
@@ -130,7 +130,7 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
         else additional_effects<GR>(P, ro, cold, hl, q, hr, inv_d, hv, a, dldt, save_tides ? scratch : nullptr);
         if (save_tides && (P.flags & FLAG_TIDES) && ro.valid && !done) {
             const size_t ns = (size_t)P.n_sys;
-            const size_t i = (size_t)b * ns + sys, cs = (size_t)P.n_bodies * ns;
+            const size_t i = (size_t)b * ns + sys, cs = (size_t)PB_N(P) * ns;
             for (int k = 0; k < PB_TIDE_SCRATCH; k++) P.tide_scratch[i + k * cs] = scratch[k];
         }
         if (GR == PB200_GR_ANDERSON1975 || GR == PB200_GR_NEWHALL1983) {
@@ -201,8 +201,8 @@ template <int COORD>
 __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const Cold& cold, int gb, int b, size_t sys, const Lane& q, int& fail) {
     S3 acc = s3(sd(0.), sd(0.), sd(0.));
     const double q_m = cold.get(K_M), q_R = cold.get(K_R);
-    const int n = P.n_bodies;
-    const int first_other = P.host == 0 ? 1 : 0;
+    const int n = PB_N(P);
+    const int first_other = PB_HOST(P) == 0 ? 1 : 0;
     fail = 0;
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
@@ -217,11 +217,11 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const C
             double rs = __dadd_rn(q_R, Rj);
             if (d2.v <= __dmul_rn(rr, rr)) { if (!fail) fail = PB200_STATUS_ROCHE_DESTROYED; }
             if (d2.v <= __dmul_rn(rs, rs)) { if (!fail) fail = PB200_STATUS_COLLISION; }
-            if (b == P.host && d2.v > kMaxDistance2) { if (!fail) fail = PB200_STATUS_EJECTED; }
+            if (b == PB_HOST(P) && d2.v > kMaxDistance2) { if (!fail) fail = PB200_STATUS_EJECTED; }
         }
         bool skip;
-        if (COORD == PB200_COORD_JACOBI) skip = (b == P.host && j == first_other) || (j == P.host && b == first_other);
-        else skip = (b == P.host || j == P.host);
+        if (COORD == PB200_COORD_JACOBI) skip = (b == PB_HOST(P) && j == first_other) || (j == PB_HOST(P) && b == first_other);
+        else skip = (b == PB_HOST(P) || j == PB_HOST(P));
         if (skip) continue;
         sd dist = ssqrt(d2);
         sd pre = sd(-kG) / (dist * dist * dist) * mj;
@@ -244,18 +244,18 @@ extern __shared__ double pb_smem[];
 
 template <int COORD, int GR, int ARITH>
 __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
-    const int W = P.W;
-    const int n = P.n_bodies;
+    const int W = PB_W(P);
+    const int n = PB_N(P);
     const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int b = (int)(gtid & (size_t)(W - 1));
-    const size_t sys = gtid >> P.shift;
+    const size_t sys = gtid >> PB_SHIFT(P);
     const int gb = lane & ~(W - 1);
-    const int hl = gb + P.host;
+    const int hl = gb + PB_HOST(P);
     const bool sys_ok = sys < (size_t)P.n_sys;
     Roles ro;
     ro.valid = sys_ok && b < n;
-    ro.host = ro.valid && b == P.host;
+    ro.host = ro.valid && b == PB_HOST(P);
     ro.planet = ro.valid && !ro.host;
     ro.t_on = ro.planet && ((P.tides_orbiting >> b) & 1u);
     ro.f_on = ro.planet && ((P.flat_orbiting >> b) & 1u);
@@ -306,7 +306,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
         sd mu = Mg_s;
         if (COORD != PB200_COORD_JACOBI) mtot = sd(0.) + M_s;
         for (int k = 0; k < n; k++) {
-            if (k == P.host) continue;
+            if (k == PB_HOST(P)) continue;
             mtot = mtot + sd(shfl(m_s.v, gb + k));
             mu = mu + sd(shfl(mg_s.v, gb + k));
             if (k == b) { eta_k = mtot; mu_k = mu; }
@@ -319,7 +319,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
         cold.set(K_MH, M_s.v); cold.set(K_MGH, Mg_s.v); cold.set(K_MTOT, mtot.v); cold.set(K_KMU, kepler_mu.v);
         cold.set(K_BACKW, back_w.v); cold.set(K_WHDSF, whds_f.v); cold.set(K_ETAK, eta_k.v);
     }
-    const int first_other = P.host == 0 ? 1 : 0;
+    const int first_other = PB_HOST(P) == 0 ? 1 : 0;
     const sd zero = sd(0.), one = sd(1.);
     const S3 zero3 = s3(zero, zero, zero);
     const S3 one3 = s3(one, one, one);
@@ -392,7 +392,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     S3 s = eta * shfl3(q.r, hl), sv = eta * shfl3(q.v, hl);
                     apos = one3; avel = zero3;
                     for (int k = 0; k < n; k++) {
-                        if (k == P.host) continue;
+                        if (k == PB_HOST(P)) continue;
                         sd mk = sd(shfl(m_s.v, gb + k));
                         S3 rk = shfl3(q.r, gb + k), vk = shfl3(q.v, gb + k);
                         sd ei = one / eta;
@@ -407,8 +407,8 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                 } else {
                     // host first, then the others (whfast.rs:986-995)
                     S3 mr = q.r * m_s, mv = q.v * m_s;
-                    S3 sr = ordered_sum_others(zero3 + shfl3(mr, hl), mr, gb, n, P.host);
-                    S3 sv = ordered_sum_others(zero3 + shfl3(mv, hl), mv, gb, n, P.host);
+                    S3 sr = ordered_sum_others(zero3 + shfl3(mr, hl), mr, gb, n, PB_HOST(P));
+                    S3 sv = ordered_sum_others(zero3 + shfl3(mv, hl), mv, gb, n, PB_HOST(P));
                     spos = sr / mtot; svel = sv / mtot;
                     apos = q.r - shfl3(q.r, hl);
                     avel = q.v - svel;
@@ -424,7 +424,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                             S3 sa = eta * shfl3(anew_s, hl);
                             S3 aacc = zero3;
                             for (int k = 0; k < n; k++) {
-                                if (k == P.host) continue;
+                                if (k == PB_HOST(P)) continue;
                                 sd mk = sd(shfl(m_s.v, gb + k));
                                 S3 ak = shfl3(anew_s, gb + k);
                                 sd ei = one / eta;
@@ -457,12 +457,12 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         }
                         if (COORD != PB200_COORD_JACOBI && jump_slot != phase) {
                             if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
-                                S3 p = ordered_sum_others(zero3, m_s * avel, gb, n, P.host);
+                                S3 p = ordered_sum_others(zero3, m_s * avel, gb, n, PB_HOST(P));
                                 apos = s3(apos.x + hdt_s * p.x / M_s, apos.y + hdt_s * p.y / M_s, apos.z + hdt_s * p.z / M_s);
                             } else {
                                 sd f = M_s + m_s;
                                 S3 term = s3(m_s * avel.x / f, m_s * avel.y / f, m_s * avel.z / f);
-                                S3 p = ordered_sum_others(zero3, term, gb, n, P.host);
+                                S3 p = ordered_sum_others(zero3, term, gb, n, PB_HOST(P));
                                 apos = s3(apos.x + hdt_s * (p.x - term.x), apos.y + hdt_s * (p.y - term.y), apos.z + hdt_s * (p.z - term.z));
                             }
                         }
@@ -473,7 +473,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         S3 s = et * spos, sv = et * svel;
                         S3 nr = q.r, nv = q.v;
                         for (int k = n - 1; k >= 0; k--) {
-                            if (k == P.host) continue;
+                            if (k == PB_HOST(P)) continue;
                             sd mk = sd(shfl(m_s.v, gb + k));
                             S3 pk = shfl3(apos, gb + k), wk = shfl3(avel, gb + k);
                             sd ei = one / et;
@@ -488,13 +488,13 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         // positions (whfast.rs:1128-1155); the host lane divides a dummy instead of its zero vector
                         S3 num = ro.planet ? apos * m_s : one3;
                         S3 term = num / mtot;
-                        S3 star_r = ordered_diff_others(spos, term, gb, n, P.host);
+                        S3 star_r = ordered_diff_others(spos, term, gb, n, PB_HOST(P));
                         S3 nr = ro.host ? star_r : apos + star_r;
                         if (alive) q.r = nr;
                         if (phase == 1) {
                             // velocities (whfast.rs:1090-1126); those of the first drift are dead (the kick overwrites them)
                             S3 nv = (COORD == PB200_COORD_WHDS ? avel / sd(cold.get(K_WHDSF)) : avel) + svel;
-                            S3 star_v = ordered_diff_others(svel, avel * sd(cold.get(K_BACKW)), gb, n, P.host);
+                            S3 star_v = ordered_diff_others(svel, avel * sd(cold.get(K_BACKW)), gb, n, PB_HOST(P));
                             if (ro.host) nv = star_v;
                             if (alive) q.v = nv;
                         }
@@ -530,4 +530,4 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
     if (alive) store_lane(P, ro, cold, sys, b, q, st);
 }
 
-}  // namespace pb200
+}  // namespace PB_NS
