@@ -115,7 +115,15 @@ typedef struct pb200_body {
     int32_t evolution_table;  /* index into the table pool, -1 when NonEvolving */
     int32_t evolution_left_index; /* Evolver.left_index cursor (evolution.rs:27), carried for recovery images */
     int32_t id;
-    int32_t reserved;
+    /* Inert on the GPU path, carried so that a recovery image round-trips through the reference's own reader:
+     * Reference (particle.rs:9-13): -1 = MostMassiveParticle, k >= 0 = Particle(k); wind (wind.rs:6-39) and
+     * disk (disk.rs:6-56) roles and parameters. */
+    int32_t reference;
+    int32_t wind_role;        /* 0 = Interaction, 1 = Disabled (WindEffect tag order) */
+    int32_t disk_role;        /* PB200_ROLE_* (DiskEffect tag order) */
+    double wind_k_factor;
+    double wind_rotation_saturation;
+    double disk_properties[6]; /* DiskProperties, only meaningful when disk_role == PB200_ROLE_CENTRAL */
 } pb200_body_t;
 
 /* One system: flattened `WHFast` (whfast.rs:98-120) + `Universe` (universe.rs:50-63). */
@@ -179,6 +187,21 @@ int pb200_device_count(void);
  * checks of output::restore_snapshot (output.rs:206-231) and
  * Universe::new (universe.rs:73-175) — no CPU fallback exists behind it. */
 int pb200_case_validate(const pb200_case_t* c, const pb200_table_t* tables, size_t n_tables);
+
+/* ---- case files (host side, no GPU needed) -------------------------------------------------------------------
+ * pb200_case_load replaces output::restore_snapshot's readers (output.rs:206-307): a path ending in ".json" is
+ * parsed as the serde_json image of `WHFast` (what posidonius' Python package writes and what
+ * write_recovery_snapshot writes for .json paths), anything else as the bincode 1.3.3 image. The WHFast image is
+ * the only one accepted: Ias15 / LeapFrog images and cases with effects outside the hot path return
+ * PB200_E_UNSUPPORTED. The evolution tables are owned by the returned store.
+ * pb200_case_save replaces write_recovery_snapshot (output.rs:56-82): bincode unless the path ends in ".json";
+ * an existing file is first renamed to a 12-hourly backup like the reference does (output.rs:63-69). */
+typedef struct pb200_table_store pb200_table_store_t;
+int pb200_case_load(const char* path, pb200_case_t* out, pb200_table_store_t** tables_out);
+int pb200_case_save(const char* path, const pb200_case_t* c, const pb200_table_t* tables, size_t n_tables);
+const pb200_table_t* pb200_table_store_tables(const pb200_table_store_t* s);
+size_t pb200_table_store_count(const pb200_table_store_t* s);
+void pb200_table_store_free(pb200_table_store_t* s);
 
 /* Replaces output::restore_snapshot + Universe ownership (output.rs:206-231):
  * builds a device-resident ensemble of n_systems systems on `device`.

@@ -17,6 +17,11 @@ _SIGNATURES = {
     "pb200_last_error": (C.c_char_p, []),
     "pb200_device_count": (C.c_int, []),
     "pb200_case_validate": (C.c_int, [C.POINTER(abi.Case), C.POINTER(abi.Table), C.c_size_t]),
+    "pb200_case_load": (C.c_int, [C.c_char_p, C.POINTER(abi.Case), C.POINTER(C.c_void_p)]),
+    "pb200_case_save": (C.c_int, [C.c_char_p, C.POINTER(abi.Case), C.POINTER(abi.Table), C.c_size_t]),
+    "pb200_table_store_tables": (C.POINTER(abi.Table), [C.c_void_p]),
+    "pb200_table_store_count": (C.c_size_t, [C.c_void_p]),
+    "pb200_table_store_free": (None, [C.c_void_p]),
     "pb200_ensemble_create": (C.c_int, [C.POINTER(abi.Case), C.c_size_t, C.c_size_t, C.POINTER(abi.Table), C.c_size_t,
                                         C.c_int, C.POINTER(C.c_void_p)]),
     "pb200_ensemble_destroy": (None, [C.c_void_p]),

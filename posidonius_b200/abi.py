@@ -67,7 +67,12 @@ class Body(C.Structure):
         ("evolution_table", C.c_int32),
         ("evolution_left_index", C.c_int32),
         ("id", C.c_int32),
-        ("reserved", C.c_int32),
+        ("reference", C.c_int32),
+        ("wind_role", C.c_int32),
+        ("disk_role", C.c_int32),
+        ("wind_k_factor", C.c_double),
+        ("wind_rotation_saturation", C.c_double),
+        ("disk_properties", C.c_double * 6),
     ]
 
 

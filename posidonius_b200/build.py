@@ -6,8 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libposidonius_b200.so")
-SOURCES = ["pb200_api.cu"]
-HEADERS = ["strict.cuh", "whfast_kernel.cuh", "forces_fast.cuh", "gr_variants.cuh", "strict_effects.cuh", "whfast_step.cuh"]
+SOURCES = ["pb200_api.cu", "host/case_io.cpp"]
+CLI = os.path.join(HERE, "bin", "posidonius-b200")
+HEADERS = ["host/json_min.hpp", "host/cli.cpp", "strict.cuh", "whfast_kernel.cuh", "forces_fast.cuh", "gr_variants.cuh", "strict_effects.cuh", "whfast_step.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--fmad=true", "-Xptxas", "-v",
@@ -15,7 +16,7 @@ NVCC_FLAGS = [
 
 
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(CLI):
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(HERE, "..", "include", "posidonius_b200.h"), __file__]
@@ -37,7 +38,22 @@ def build(force=False, verbose=False, out=None, defines=()):
         sys.stderr.write(proc.stdout)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building %s (see %s)" % (target, log))
+    if out is None:
+        build_cli()
     return target
+
+
+def build_cli():
+    """The `posidonius-b200 start|resume|ensemble` command line (host C++ over the C ABI)."""
+    os.makedirs(os.path.dirname(CLI), exist_ok=True)
+    cxx = os.environ.get("CXX", "g++")
+    cmd = [cxx, "-O2", "-std=c++17", "-o", CLI, os.path.join(CSRC, "host", "cli.cpp"), "-L" + HERE, "-lposidonius_b200",
+           "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath," + HERE]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+        raise RuntimeError("building the CLI failed")
+    return CLI
 
 
 if __name__ == "__main__":

@@ -75,6 +75,16 @@ class CaseTables:
         return self._ctypes
 
 
+def _set_dummy_body(b):
+    """Unused particle slots: Particle::new_dummy() (particle.rs:100-146) — every effect Disabled, NonEvolving."""
+    C.memset(C.byref(b), 0, C.sizeof(abi.Body))
+    b.tides_role = b.flattening_role = b.general_relativity_role = b.disk_role = abi.ROLE_DISABLED
+    b.wind_role = 1
+    b.evolution_type = abi.EVO_NONEVOLVING
+    b.evolution_table = -1
+    b.reference = -1
+
+
 def case_from_dict(d):
     """Flatten the serde JSON image of a WHFast integrator. Returns (abi.Case, CaseTables)."""
     if "alternative_coordinates_type" not in d or "universe" not in d:
@@ -173,10 +183,21 @@ def case_from_dict(d):
         role, impl = _effect_role_and_payload(p["general_relativity"]["effect"])
         b.general_relativity_role = abi.ROLES[role]
         b.general_relativity_factor = p["general_relativity"]["parameters"]["internal"]["factor"]
-        # wind / disk must be inert
+        # wind / disk must be inert; their description is carried for recovery images
         wrole, _ = _effect_role_and_payload(p["wind"]["effect"])
         if wrole != "Disabled" and c.consider_wind:
             raise UnsupportedCaseError("stellar wind is outside the B200 hot path")
+        b.wind_role = 0 if wrole == "Interaction" else 1
+        b.wind_k_factor = p["wind"]["parameters"]["input"]["k_factor"]
+        b.wind_rotation_saturation = p["wind"]["parameters"]["input"]["rotation_saturation"]
+        drole, dprops = _effect_role_and_payload(p["disk"]["effect"])
+        b.disk_role = abi.ROLES[drole]
+        if dprops is not None:
+            for k, key in enumerate(("inner_edge_distance", "outer_edge_distance", "lifetime", "alpha",
+                                     "surface_density_normalization", "mean_molecular_weight")):
+                b.disk_properties[k] = dprops[key]
+        ref = p.get("reference", "MostMassiveParticle")
+        b.reference = -1 if isinstance(ref, str) else int(ref["Particle"])
         # evolution
         etype, eparam = _effect_role_and_payload(p["evolution"])
         b.evolution_type = abi.EVOLUTION_TYPES[etype]
@@ -193,6 +214,8 @@ def case_from_dict(d):
                                            ev["inverse_tidal_q_factor"])
         c.inertial_velocity_errors[i][:] = _axes(d["inertial_velocity_errors"][i])
         c.particle_angular_momentum_errors[i][:] = _axes(d["particle_angular_momentum_errors"][i])
+    for i in range(n, abi.MAX_PARTICLES):
+        _set_dummy_body(c.bodies[i])
     rr = u["roche_radiuses"]
     for k in range(abi.MAX_PARTICLES * abi.MAX_PARTICLES):
         c.roche_radiuses[k] = rr[k]
@@ -208,3 +231,49 @@ def copy_case(c):
     out = abi.Case()
     C.memmove(C.byref(out), C.byref(c), C.sizeof(abi.Case))
     return out
+
+
+class NativeTables:
+    """Evolution tables owned by the C++ reader (pb200_table_store_t); same interface as CaseTables."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    def __len__(self):
+        from ._lib import lib
+        return lib().pb200_table_store_count(self._h)
+
+    def as_ctypes(self):
+        from ._lib import lib
+        p = lib().pb200_table_store_tables(self._h)
+        return p if len(self) else (abi.Table * 1)()
+
+    def __del__(self):
+        try:
+            from ._lib import lib
+            if self._h:
+                lib().pb200_table_store_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def load_case_file(path):
+    """pb200_case_load: the C++ reader of the library (JSON for *.json, bincode otherwise) — what the CLI uses."""
+    from ._lib import lib, last_error
+    c = abi.Case()
+    h = C.c_void_p()
+    rc = lib().pb200_case_load(str(path).encode(), C.byref(c), C.byref(h))
+    if rc == abi.E_UNSUPPORTED:
+        raise UnsupportedCaseError(last_error())
+    if rc != abi.OK:
+        raise InvalidCaseError(last_error())
+    return c, NativeTables(h)
+
+
+def save_case_file(path, case, tables):
+    """pb200_case_save: bincode recovery snapshot (or pretty JSON for *.json) in the reference's layout."""
+    from ._lib import lib, last_error
+    rc = lib().pb200_case_save(str(path).encode(), C.byref(case), tables.as_ctypes(), len(tables))
+    if rc != abi.OK:
+        raise InvalidCaseError(last_error())

@@ -38,6 +38,7 @@ using namespace pb200;
 
 static thread_local std::string g_last_error;
 static int set_error(int code, const std::string& msg) { g_last_error = msg; return code; }
+int pb200_set_error_message(int code, const std::string& msg) { return set_error(code, msg); }   // for host/case_io.cpp
 
 #define CUDA_TRY(expr)                                                                                         \
     do {                                                                                                        \

@@ -230,6 +230,9 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const C
     return acc;
 }
 
+#ifndef PB_STEP_BARRIER
+#define PB_STEP_BARRIER 1   // +2.3 % at block 128 x 3 (profiles/r1_variants.md)
+#endif
 #ifndef PB_MIN_BLOCKS
 #define PB_MIN_BLOCKS 3   // 168 registers/thread, 12 warps/SM, no spills (measured best: profiles/r1_variants.md)
 #endif
@@ -326,7 +329,13 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
 
 #pragma unroll 1
     for (unsigned long long step = 0; step < n_steps; step++) {
+#if PB_STEP_BARRIER
+        // one block-wide barrier per step keeps the warps of a block in the same region of the (large) loop body, so that
+        // they share instruction-cache lines; it also makes the loop exit block-uniform
+        if (!__syncthreads_or(alive)) break;
+#else
         if (!__any_sync(FULL, alive)) break;
+#endif
         // ---- historic snapshot (whfast.rs:237-261, output.rs:119-163)
         {
             bool first = st.last_hist < 0.;
