@@ -251,3 +251,78 @@ def test_run_host_roundtrip_equals_device_resident_run(E):
         ref = a.download()
         for k in ref:
             assert np.array_equal(ref[k], buf[k]), k
+
+
+def _ten_body_case():
+    """TRAPPIST-1 with two extra outer planets (copies of h moved outwards): N = MAX_PARTICLES = 10, 16 lanes per system."""
+    import copy
+    d = config_case("c4_trappist1")
+    u = d["universe"]
+    for k, scale in ((8, 1.35), (9, 1.8)):
+        p = copy.deepcopy(u["particles"][7])
+        p["id"] = k
+        for key in ("heliocentric_position", "inertial_position"):
+            for ax in "xyz":
+                p[key][ax] *= scale
+        for key in ("heliocentric_velocity", "inertial_velocity"):
+            for ax in "xyz":
+                p[key][ax] /= scale ** 0.5
+        u["particles"][k] = p
+    u["n_particles"] = 10
+    return d
+
+
+@pytest.mark.parametrize("arithmetic", [0, 1])
+def test_maximum_size_system_ten_bodies(E, arithmetic):
+    """MAX_PARTICLES bodies (src/constants.rs:3): 16 lanes per system, 6 of them padding. Strict mode: bit-identical."""
+    from oracle.binding import run_ensemble
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import make_ensemble_cases
+    case, tables = case_from_dict(_ten_body_case())
+    cases = make_ensemble_cases(case, 9, 99)
+    with E.Ensemble(cases, tables, arithmetic=arithmetic) as ens:
+        ens.initialize_physical_values()
+        ens.iterate(1500)
+        g = gpu_state_of(ens)
+        st, _, _ = ens.status()
+    oc, ost, _ = run_ensemble(cases, 9, tables, 1500, True, 4)
+    o = oracle_state_of(oc)
+    assert np.array_equal(st, ost)
+    for k in ("position", "velocity", "spin", "angular_momentum"):
+        if arithmetic:
+            assert np.array_equal(g[k], o[k]), k
+        else:
+            assert rel_err(g[k], o[k]) < TOL_1E3, (k, rel_err(g[k], o[k]))
+
+
+def test_full_size_ensemble_properties(E):
+    """BASELINE size (65536 TRAPPIST-1 systems): size-independent properties instead of an oracle run.
+    (1) replicas of one case stay bit-identical to each other and to a 1-system run (no cross-talk between groups/warps);
+    (2) two launches of n steps equal one launch of 2n steps (state round-trips through HBM exactly);
+    (3) the reference's (heliocentric, hence only approximately conserved) energy and angular momentum diagnostics of
+        every member of a perturbed ensemble stay inside the symplectic oscillation band over 2000 steps (no drift, no NaN)."""
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import make_ensemble_cases
+    case, tables = case_from_dict(config_case("c4_trappist1"))
+    with E.Ensemble(case, tables, n_systems=65536) as big, E.Ensemble(case, tables, n_systems=1) as one:
+        for ens in (big, one):
+            ens.initialize_physical_values()
+        big.iterate(300)
+        big.iterate(300)
+        one.iterate(600)
+        a = big.download(("position", "velocity", "angular_momentum"))
+        b = one.download(("position", "velocity", "angular_momentum"))
+        for k in a:
+            assert np.all(a[k] == a[k][..., :1]), k           # all replicas identical
+            assert np.array_equal(a[k][..., 0], b[k][..., 0]), k  # and equal to the single-system run in one launch
+    cases = make_ensemble_cases(case, 65536, 20261021)
+    with E.Ensemble(cases, tables) as ens:
+        ens.initialize_physical_values()
+        e0, l0 = ens.summary()
+        ens.iterate(2000)
+        e1, l1 = ens.summary()
+        st, w, _ = ens.status()
+        assert np.all(st == 0) and np.all(w == 0)
+        assert np.all(np.isfinite(e1)) and np.all(np.isfinite(l1))
+        assert np.max(np.abs((e1 - e0) / e0)) < 1e-3
+        assert np.max(np.abs((l1 - l0) / l0)) < 1e-4
