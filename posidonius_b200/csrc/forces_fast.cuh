@@ -20,15 +20,20 @@ __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, c
     const double sig_h = shfl(sigma, hl), k2t_h = shfl(k2t, hl), k2f_h = shfl(k2f, hl);
     const double m2 = m * m, M2 = M * M;
     cold.set(C_INVI, 1. / I);
-    cold.set(C_AS, 4.5 * m2 * (Rh5 * Rh5) * sig_h);               // 4.5 m^2 R*^10 sigma*   (constant_time_lag.rs:232-234)
-    cold.set(C_AP, 4.5 * M2 * (R5 * R5) * sigma);                 // 4.5 M^2 R^10 sigma     (constant_time_lag.rs:243-245)
-    cold.set(C_BK, 3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * k2t)); // 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2) (:283-285)
-    cold.set(C_KS, m * k2f_h * Rh5);                              // flattening: m k2f* R*^5 (oblate_spheroid.rs:37)
-    cold.set(C_KP, M * k2f * R5);                                 //             M k2f R^5   (oblate_spheroid.rs:42)
+    // Role gates are folded into the constants: a lane that is not an OrbitingBody of an effect (host slot, padding,
+    // Disabled role) carries zeros, so the force code needs no per-lane branches or selects.
+    const double gt = ro.t_on ? 1. : 0., gf = ro.f_on ? 1. : 0., gg = ro.g_on ? 1. : 0.;
+    const double gts = P.tides_host_central ? gt : 0., gfs = P.flat_host_central ? gf : 0.;
+    cold.set(C_AS, gts * (4.5 * m2 * (Rh5 * Rh5) * sig_h));         // 4.5 m^2 R*^10 sigma*   (constant_time_lag.rs:232-234)
+    cold.set(C_AP, gt * (4.5 * M2 * (R5 * R5) * sigma));            // 4.5 M^2 R^10 sigma     (constant_time_lag.rs:243-245)
+    cold.set(C_BK, gt * (3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * k2t))); // 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2) (:283-285)
+    cold.set(C_KS, gfs * (m * k2f_h * Rh5));                        // flattening: m k2f* R*^5 (oblate_spheroid.rs:37)
+    cold.set(C_KP, gf * (M * k2f * R5));                            //             M k2f R^5   (oblate_spheroid.rs:42)
     cold.set(C_IH, Ih);
     cold.set(C_INVM, 1. / m); cold.set(C_INVMH, 1. / M); cold.set(C_MH, M);
     const double mgs = Mg + mg;
-    cold.set(C_MGS, mgs);
+    cold.set(C_MGS, gg * mgs);                                     // gated: A = mgs / (r^2 c^2) vanishes for non-GR lanes
+    cold.set(C_FA, gg * (kG * kInvC2));                            // G / c^2 of the 1.5PN terms, gated
     cold.set(C_GRF, Mg * mg / (mgs * mgs));                       // general_relativity.rs:98
     cold.set(C_MURED, (M * m) / (M + m));                         // general_relativity.rs:383
     cold.set(C_MD, M - m);                                        // mass_factor * star_planet_mass (:319-321, 336)
@@ -79,7 +84,7 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         // constant_time_lag.rs:206-332, tides/common.rs:223-345
         double inv_d4 = inv_d2 * inv_d2;
         double inv_d7 = inv_d4 * inv_d2 * inv_d;
-        double Fos = P.tides_host_central ? cold.get(C_AS) * inv_d7 : 0.;
+        double Fos = cold.get(C_AS) * inv_d7;
         double Fop = cold.get(C_AP) * inv_d7;
         double Fsum = Fos + Fop;
         // radial: conservative + dissipative (-13.5 vr/r^8 (...) = -3 vr/r (Fos + Fop))
@@ -94,12 +99,10 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
                    Fop * (d * q.s.z - (rs_p * hr.z + rxv.z) * inv_d));
         V3 Ns = v3(Fos * (d * sh.x - (rs_s * hr.x + rxv.x) * inv_d), Fos * (d * sh.y - (rs_s * hr.y + rxv.y) * inv_d),
                    Fos * (d * sh.z - (rs_s * hr.z + rxv.z) * inv_d));
-        if (ro.t_on) {
-            a_p = a_p + inv_m * F;
-            a_h = a_h - inv_M * F;
-            dl_p = dl_p - Np;
-            dl_h = dl_h - Ns;
-        }
+        a_p = inv_m * F;
+        a_h = (-inv_M) * F;
+        dl_p = v3(-Np.x, -Np.y, -Np.z);
+        dl_h = v3(-Ns.x, -Ns.y, -Ns.z);
         if (tide_save) {
             // internals that calculate_denergy_dt (tides/common.rs:263-279) will read at the next snapshot
             tide_save[0] = hr.x; tide_save[1] = hr.y; tide_save[2] = hr.z;
@@ -113,7 +116,7 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         // oblate_spheroid.rs:12-97, rotational_flattening/common.rs:165-237
         double inv_d5 = inv_d2 * inv_d2 * inv_d;
         double inv_d7 = inv_d5 * inv_d2;
-        double Ks = P.flat_host_central ? cold.get(C_KS) : 0.;
+        double Ks = cold.get(C_KS);
         double Kp = cold.get(C_KP);
         double Fos = -Ks * rs_s * inv_d5;
         double Fop = -Kp * rs_p * inv_d5;
@@ -121,12 +124,10 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         V3 F = v3(Frad * hr.x + Fop * q.s.x + Fos * sh.x, Frad * hr.y + Fop * q.s.y + Fos * sh.y, Frad * hr.z + Fop * q.s.z + Fos * sh.z);
         V3 Np = Fop * cross(hr, q.s);
         V3 Ns = Fos * cross(hr, sh);
-        if (ro.f_on) {
-            a_p = a_p + inv_m * F;
-            a_h = a_h - inv_M * F;
-            dl_p = dl_p - Np;
-            dl_h = dl_h - Ns;
-        }
+        a_p = a_p + inv_m * F;
+        a_h = a_h - inv_M * F;
+        dl_p = dl_p - Np;
+        dl_h = dl_h - Ns;
     }
     if (GR == PB200_GR_KIDDER1995) {
         // general_relativity.rs:177-456
@@ -156,22 +157,19 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         V3 e2 = cross(hv, e7);
         V3 e3s = v3(3. * S.x + msf.x, 3. * S.y + msf.y, 3. * S.z + msf.z);
         V3 e3 = (3. * radvel) * cross(nn, e3s);
-        const double fa = kG * kInvC2;
+        const double fa = cold.get(C_FA);
         a = a + fa * (e1 - e2 + e3);
         // Kidder 1995 eqs 2.4a, 2.4b
         V3 Lo = cold.get(C_MURED) * rxv;
         V3 LpxLs = cross(Lp, Ls);
         V3 ds = cold.get(C_FMS) * cross(Lo, Ls) - LpxLs + (3. * dot(nn, Lp)) * cross(nn, Ls);
         V3 dp = cold.get(C_FMP) * cross(Lo, Lp) + LpxLs + (3. * dot(nn, Ls)) * cross(nn, Lp);
-        if (ro.g_on) {
-            a_p = a_p + a;
-            a_h = a_h - cold.get(C_MOM) * a;
-            dl_p = dl_p + fa * dp;
-            dl_h = dl_h + fa * ds;
-        }
+        a_p = a_p + a;
+        a_h = a_h - cold.get(C_MOM) * a;
+        dl_p = dl_p + fa * dp;
+        dl_h = dl_h + fa * ds;
     }
-    // zero out lanes that are not orbiting bodies, then reduce onto the host
-    if (!ro.planet) { a_h = v3(0., 0., 0.); dl_h = v3(0., 0., 0.); a_p = v3(0., 0., 0.); dl_p = v3(0., 0., 0.); }
+    // lanes that are not orbiting bodies carry zero constants (make_consts): their terms vanish; reduce onto the host
     a_h = group_sum3(a_h, W);
     dl_h = group_sum3(dl_h, W);
     a_out = ro.host ? a_h : a_p;

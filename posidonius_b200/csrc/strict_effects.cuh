@@ -10,7 +10,7 @@
 namespace PB_NS {
 using namespace pb200;
 
-// strict-mode constants overlay the fast-mode constant slots (C_INVI..C_FMP, 17 slots) plus Z_0, Z_1
+// strict-mode constants overlay the fast-mode constant slots (C_INVI..C_FA, 18 slots) plus Z_0
 enum StrictSlot : int {
     Z_CS = C_INVI, Z_CP, Z_KCONS, Z_T1, Z_T2, Z_INVM, Z_INVMH, Z_FS0, Z_FP0, Z_R5, Z_RH5, Z_MGS, Z_GRF, Z_MOM, Z_MFM, Z_MURED, Z_FMS,
     Z_FMP = Z_0, Z_IH = Z_1

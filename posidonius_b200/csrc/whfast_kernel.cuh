@@ -310,7 +310,7 @@ enum ColdSlot : int {
     // body parameters
     K_M, K_MG, K_R, K_I,
     // constants of the perturbation forces (every division with step-invariant operands is done once)
-    C_INVI, C_AS, C_AP, C_BK, C_KS, C_KP, C_IH, C_INVM, C_INVMH, C_MH, C_MGS, C_GRF, C_MURED, C_MD, C_MOM, C_FMS, C_FMP,
+    C_INVI, C_AS, C_AP, C_BK, C_KS, C_KP, C_IH, C_INVM, C_INVMH, C_MH, C_MGS, C_GRF, C_MURED, C_MD, C_MOM, C_FMS, C_FMP, C_FA,
     // constants of the coordinate transforms (strict)
     K_MH, K_MGH, K_MTOT, K_KMU, K_BACKW, K_WHDSF, K_ETAK,
     // strict arithmetic mode (strict_effects.cuh): two more constants and the 4-vector exchange buffer for the host sums

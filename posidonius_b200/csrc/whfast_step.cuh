@@ -204,7 +204,11 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const C
     const int n = PB_N(P);
     const int first_other = PB_HOST(P) == 0 ? 1 : 0;
     fail = 0;
+#if PB_FIXED_N
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int j = 0; j < n; j++) {
         S3 rj = shfl3(q.r, gb + j);
         sd mj = sd(shfl(q_m, gb + j));
