@@ -38,7 +38,7 @@ extern "C" {
 /* error codes */
 #define PB200_OK 0
 #define PB200_E_INVALID (-1)      /* bad argument / inconsistent case */
-#define PB200_E_UNSUPPORTED (-2)  /* effect/integrator outside the hot path (Kaula, creep, disk, wind, IAS15, LeapFrog...) */
+#define PB200_E_UNSUPPORTED (-2)  /* effect/integrator outside the hot path (Kaula, creep, disk, IAS15, LeapFrog...) */
 #define PB200_E_CUDA (-3)         /* CUDA runtime failure */
 #define PB200_E_NOMEM (-4)
 
@@ -115,9 +115,9 @@ typedef struct pb200_body {
     int32_t evolution_table;  /* index into the table pool, -1 when NonEvolving */
     int32_t evolution_left_index; /* Evolver.left_index cursor (evolution.rs:27), carried for recovery images */
     int32_t id;
-    /* Inert on the GPU path, carried so that a recovery image round-trips through the reference's own reader:
-     * Reference (particle.rs:9-13): -1 = MostMassiveParticle, k >= 0 = Particle(k); wind (wind.rs:6-39) and
-     * disk (disk.rs:6-56) roles and parameters. */
+    /* Reference (particle.rs:9-13): -1 = MostMassiveParticle, k >= 0 = Particle(k); wind (wind.rs:6-39) role and input
+     * parameters (dL/dt of wind.rs:72-91 is part of the hot path); the disk (disk.rs:6-56) role and parameters are inert
+     * on the GPU path, carried so that a recovery image round-trips through the reference's own reader. */
     int32_t reference;
     int32_t wind_role;        /* 0 = Interaction, 1 = Disabled (WindEffect tag order) */
     int32_t disk_role;        /* PB200_ROLE_* (DiskEffect tag order) */
@@ -160,6 +160,10 @@ typedef struct pb200_case {
     double inertial_velocity_errors[PB200_MAX_PARTICLES][3];         /* whfast.rs:117 */
     double particle_angular_momentum_errors[PB200_MAX_PARTICLES][3]; /* whfast.rs:119 */
     double roche_radiuses[PB200_MAX_PARTICLES * PB200_MAX_PARTICLES]; /* universe.rs:62, row stride = n_particles */
+    /* Universe.pair_dependent_scaled_dissipation_factor (universe.rs:61; tides/constant_time_lag.rs:152-165): the
+     * HashMap<usize, f64> keyed id * MAX_PARTICLES + depends_on_id, flattened; NaN = key absent. Only bodies whose
+     * EvolutionType drives dynamical tides (BolmontMathis2016, GalletBolmont2017, LeconteChabrier2013(true)) use it. */
+    double pair_dependent_scaled_dissipation_factor[PB200_MAX_PARTICLES * PB200_MAX_PARTICLES];
 } pb200_case_t;
 
 /* One evolution table = the vectors of `Evolver` (evolution.rs:19-28). Columns

@@ -107,7 +107,9 @@ struct Body {
     int g_role = PB200_ROLE_DISABLED;
     R g_factor = 0., g_dist = 0., g_radvel = 0., g_normv = 0., g_normv2 = 0.;
     V3<R> g_pos{0., 0., 0.}, g_vel{0., 0., 0.}, g_acc{0., 0., 0.}, g_dL{0., 0., 0.};
-    // wind / disk outputs stay zero (effects rejected by the product, kept for the sums of universe.rs:540-614)
+    // wind (wind.rs:6-39); the disk output stays zero (effect rejected by the product, kept for the sums of universe.rs:540-614)
+    int w_role = 1;  // WindEffect tag order: 0 = Interaction, 1 = Disabled
+    R w_k = 0., w_sat = 0., w_sat2 = 0.;
     V3<R> w_dL{0., 0., 0.}, d_acc{0., 0., 0.};
     int evo_type = PB200_EVO_NONEVOLVING;
     double evo_param = 0.;
@@ -472,7 +474,28 @@ struct System {
                 if (init_gr && !mm_gr) { gr_inertial_to_helio(h_gr); gr_initialize(h_gr); }
             }
         }
+        // wind::initialize (wind.rs:62-70; universe.rs:356-366)
+        if (dL && c_wind) for (int i = 0; i < n; i++) if (p[i].w_role == 0) p[i].w_dL = {0., 0., 0.};
         if (acc) for (int i = 0; i < n; i++) p[i].iadd = {0., 0., 0.};
+    }
+
+    // ------------------------------------------------------------------ wind.rs:72-91
+    void calculate_wind_factor() {
+        for (int i = 0; i < n; i++) {
+            Body<R>& b = p[i];
+            if (b.w_role != 0) continue;
+            R threshold = o_sqrt(b.norm_spin2);
+            if (o_val(threshold) >= o_val(b.w_sat)) {
+                // fast rotator
+                b.w_dL.x = -1. * b.w_k * b.spin.x * b.w_sat2 * o_sqrt(b.radius / R_SUN * 1. / b.mass);
+                b.w_dL.y = -1. * b.w_k * b.spin.y * b.w_sat2 * o_sqrt(b.radius / R_SUN * 1. / b.mass);
+                b.w_dL.z = -1. * b.w_k * b.spin.z * b.w_sat2 * o_sqrt(b.radius / R_SUN * 1. / b.mass);
+            } else {
+                b.w_dL.x = -1. * b.w_k * b.spin.x * b.norm_spin2 * o_sqrt(b.radius / R_SUN * 1. / b.mass);
+                b.w_dL.y = -1. * b.w_k * b.spin.y * b.norm_spin2 * o_sqrt(b.radius / R_SUN * 1. / b.mass);
+                b.w_dL.z = -1. * b.w_k * b.spin.z * b.norm_spin2 * o_sqrt(b.radius / R_SUN * 1. / b.mass);
+            }
+        }
     }
 
     // ------------------------------------------------------------------ constant-time-lag tides
@@ -1090,6 +1113,7 @@ struct System {
     void calculate_additional_effects(double time, bool evolution, bool dL, bool acc, Ignore ign) {
         initialize(dL, acc);
         calculate_spin_and_evolving_quantities(time, evolution);
+        if (dL && c_wind) calculate_wind_factor();
         if (c_tides || c_flat) {
             int host = h_tides;
             if (host >= 0 && host < n) {
@@ -1672,6 +1696,8 @@ struct System {
             b.t_sigma = s.tides_scaled_dissipation_factor; b.t_lag = s.tides_lag_angle; b.t_denergy = s.tides_denergy_dt;
             b.f_role = s.flattening_role; b.f_k2 = s.flattening_love_number;
             b.g_role = s.general_relativity_role; b.g_factor = s.general_relativity_factor;
+            b.w_role = s.wind_role; b.w_k = s.wind_k_factor; b.w_sat = s.wind_rotation_saturation;
+            b.w_sat2 = powi(b.w_sat, 2);   // wind.rs:52, recomputed from the input (the image stores both)
             b.evo_type = s.evolution_type; b.evo_param = s.evolution_parameter; b.evo_table = s.evolution_table;
             if (s.evolution_table >= 0 && (size_t)s.evolution_table < n_tables) {
                 const pb200_table_t& t = tables[s.evolution_table];
@@ -1689,6 +1715,10 @@ struct System {
         if (c_gr && h_gr >= 0 && h_gr < n && p[h_gr].g_role == PB200_ROLE_CENTRAL) gr_impl_of_host = gr_impl;
         std::memcpy(roche, c.roche_radiuses, sizeof(roche));
         pair_clear();
+        for (int k = 0; k < MAXP * MAXP; k++) {
+            double v = c.pair_dependent_scaled_dissipation_factor[k];
+            if (v == v) { pair_sigma[k] = v; pair_sigma_set[k] = true; }   // NaN = key absent
+        }
         status = PB200_STATUS_OK; warnings = 0; event_iteration = 0;
     }
     void store(pb200_case_t& c) const {
@@ -1714,6 +1744,7 @@ struct System {
             c.particle_angular_momentum_errors[i][0] = o_val(lerr[i].x); c.particle_angular_momentum_errors[i][1] = o_val(lerr[i].y); c.particle_angular_momentum_errors[i][2] = o_val(lerr[i].z);
         }
         std::memcpy(c.roche_radiuses, roche, sizeof(roche));
+        for (int k = 0; k < MAXP * MAXP; k++) c.pair_dependent_scaled_dissipation_factor[k] = pair_sigma_set[k] ? pair_sigma[k] : std::nan("");
     }
 };
 

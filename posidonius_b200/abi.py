@@ -108,6 +108,7 @@ class Case(C.Structure):
         ("inertial_velocity_errors", _d3 * MAX_PARTICLES),
         ("particle_angular_momentum_errors", _d3 * MAX_PARTICLES),
         ("roche_radiuses", C.c_double * (MAX_PARTICLES * MAX_PARTICLES)),
+        ("pair_dependent_scaled_dissipation_factor", C.c_double * (MAX_PARTICLES * MAX_PARTICLES)),
     ]
 
 

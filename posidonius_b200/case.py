@@ -4,7 +4,7 @@ Host-side mirror of `output::restore_snapshot` / `deserialize_json_snapshot`
 (reference src/integrator/output.rs:206-269): the reference tries WHFast, then Ias15,
 then LeapFrog; this reader accepts only the WHFast image and raises
 `UnsupportedCaseError` for everything the hot path does not cover (IAS15, LeapFrog,
-Kaula and creep tides, creep flattening, disk, wind) — there is no CPU fallback.
+Kaula and creep tides, creep flattening, disk) — there is no CPU fallback.
 """
 import ctypes as C
 import json
@@ -122,8 +122,6 @@ def case_from_dict(d):
     c.consider_evolution = int(ce["evolution"])
     if c.consider_disk:
         raise UnsupportedCaseError("disk interaction is outside the B200 hot path")
-    if c.consider_wind:
-        raise UnsupportedCaseError("stellar wind is outside the B200 hot path")
     c.general_relativity_implementation = abi.GR_IMPLEMENTATIONS[u["general_relativity_implementation"]]
     hi = u["hosts"]["index"]
     c.host_most_massive = hi["most_massive"]
@@ -131,8 +129,14 @@ def case_from_dict(d):
     c.host_rotational_flattening = hi["rotational_flattening"]
     c.host_general_relativity = hi["general_relativity"]
     c.host_disk = hi["disk"]
-    if u.get("pair_dependent_scaled_dissipation_factor"):
-        raise UnsupportedCaseError("pair-dependent dissipation factors (dynamical tides) are not supported")
+    # HashMap<usize, f64> (universe.rs:61), serde_json writes the keys as strings; NaN = absent
+    for k in range(abi.MAX_PARTICLES * abi.MAX_PARTICLES):
+        c.pair_dependent_scaled_dissipation_factor[k] = float("nan")
+    for key, value in (u.get("pair_dependent_scaled_dissipation_factor") or {}).items():
+        k = int(key)
+        if not (0 <= k < abi.MAX_PARTICLES * abi.MAX_PARTICLES):
+            raise InvalidCaseError("pair_dependent_scaled_dissipation_factor key %r out of range" % (key,))
+        c.pair_dependent_scaled_dissipation_factor[k] = float(value)
     tables = CaseTables()
     evolvers = u["particles_evolvers"]
     for i in range(n):
@@ -183,10 +187,8 @@ def case_from_dict(d):
         role, impl = _effect_role_and_payload(p["general_relativity"]["effect"])
         b.general_relativity_role = abi.ROLES[role]
         b.general_relativity_factor = p["general_relativity"]["parameters"]["internal"]["factor"]
-        # wind / disk must be inert; their description is carried for recovery images
+        # wind (wind.rs:6-39); the disk must be inert, its description is carried for recovery images
         wrole, _ = _effect_role_and_payload(p["wind"]["effect"])
-        if wrole != "Disabled" and c.consider_wind:
-            raise UnsupportedCaseError("stellar wind is outside the B200 hot path")
         b.wind_role = 0 if wrole == "Interaction" else 1
         b.wind_k_factor = p["wind"]["parameters"]["input"]["k_factor"]
         b.wind_rotation_saturation = p["wind"]["parameters"]["input"]["rotation_saturation"]
@@ -206,10 +208,6 @@ def case_from_dict(d):
         ev = evolvers[i]
         b.evolution_left_index = ev.get("left_index", 0)
         if b.evolution_type != abi.EVO_NONEVOLVING and c.consider_evolution:
-            if b.evolution_type in (abi.EVOLUTION_TYPES["GalletBolmont2017"], abi.EVOLUTION_TYPES["BolmontMathis2016"]) or (
-                    b.evolution_type == abi.EVOLUTION_TYPES["LeconteChabrier2013"] and b.evolution_parameter != 0.0):
-                raise UnsupportedCaseError(
-                    "evolution type %s drives dynamical-tide (pair-dependent) dissipation, which is outside the B200 hot path" % etype)
             b.evolution_table = tables.add(ev["time"], ev["radius"], ev["radius_of_gyration_2"], ev["love_number"],
                                            ev["inverse_tidal_q_factor"])
         c.inertial_velocity_errors[i][:] = _axes(d["inertial_velocity_errors"][i])

@@ -1,6 +1,7 @@
 // forces_fast.cuh — PB200_ARITH_FAST perturbation forces (tides, flattening, GR Kidder1995) and their per-system constants.
 // Included once per geometry specialisation (see pb200_api.cu), inside namespace PB_NS; no include guard on purpose.
 #include "whfast_kernel.cuh"
+#include "dyn_effects.cuh"
 
 namespace PB_NS {
 using namespace pb200;
@@ -27,6 +28,11 @@ __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, c
     cold.set(C_AS, gts * (4.5 * m2 * (Rh5 * Rh5) * sig_h));         // 4.5 m^2 R*^10 sigma*   (constant_time_lag.rs:232-234)
     cold.set(C_AP, gt * (4.5 * M2 * (R5 * R5) * sigma));            // 4.5 M^2 R^10 sigma     (constant_time_lag.rs:243-245)
     cold.set(C_BK, gt * (3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * k2t))); // 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2) (:283-285)
+#if !PB_FIXED_N
+    // dynamical tides: the same constants without sigma (the pair-dependent sigma multiplies them per evaluation)
+    cold.set(D_0, gts * (4.5 * m2 * (Rh5 * Rh5)));
+    cold.set(D_1, gt * (4.5 * M2 * (R5 * R5)));
+#endif
     cold.set(C_KS, gfs * (m * k2f_h * Rh5));                        // flattening: m k2f* R*^5 (oblate_spheroid.rs:37)
     cold.set(C_KP, gf * (M * k2f * R5));                            //             M k2f R^5   (oblate_spheroid.rs:42)
     cold.set(C_IH, Ih);
@@ -62,8 +68,9 @@ __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, c
 // (universe.rs:428-614). Returns the inertial additional acceleration and dL/dt of THIS body;
 // host-lane values are the group reductions.
 template <int GR>
-__device__ __forceinline__ void additional_effects(const KParams& P, const Roles& ro, const Cold& cold, int hl, Lane& q, V3 hr,
-                                                   double inv_d, V3 hv, V3& a_out, V3& dl_out, double* tide_save) {
+__device__ __forceinline__ void additional_effects(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys,
+                                                   double t, bool evolve_now, Lane& q, V3 hr, double inv_d, V3 hv, V3& a_out,
+                                                   V3& dl_out, double* tide_save) {
     const int W = PB_W(P);
     // Q3: r.omega uses the spins of the previous evaluation (universe.rs:429-430)
     V3 s_host_prev = shfl3(q.s, hl);
@@ -73,6 +80,10 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     double w2 = dot(q.s, q.s);
     V3 sh = shfl3(q.s, hl);
     double wh2 = shfl(w2, hl);
+#if !PB_FIXED_N
+    // lag angle of the dynamical-tide models, once per step like the other evolving quantities (evolution.rs:548-567)
+    if (evolve_now && (P.flags & FLAG_DYN) && (P.flags & FLAG_EVO)) { update_lag_angle(P, ro, b, sys, t, sd(w2), true); __syncwarp(); }
+#endif
     double inv_d2 = inv_d * inv_d;
     double d = dot(hr, hr) * inv_d;
     double radvel = dot(hr, hv) * inv_d;
@@ -86,6 +97,14 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         double inv_d7 = inv_d4 * inv_d2 * inv_d;
         double Fos = cold.get(C_AS) * inv_d7;
         double Fop = cold.get(C_AP) * inv_d7;
+#if !PB_FIXED_N
+        if (P.flags & FLAG_DYN) {
+            sd sig_h, sig_p;
+            pair_dependent_sigmas(P, ro, cold, hl, b, sys, strict(hr), strict(hv), sd(w2), sd(wh2), sig_h, sig_p);
+            Fos = cold.get(D_0) * sig_h.v * inv_d7;
+            Fop = cold.get(D_1) * sig_p.v * inv_d7;
+        }
+#endif
         double Fsum = Fos + Fop;
         // radial: conservative + dissipative (-13.5 vr/r^8 (...) = -3 vr/r (Fos + Fop))
         double f3 = -cold.get(C_BK) * inv_d7 - 2.0 * Fsum * radvel * inv_d;
@@ -174,6 +193,9 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     dl_h = group_sum3(dl_h, W);
     a_out = ro.host ? a_h : a_p;
     dl_out = ro.host ? dl_h : dl_p;
+#if !PB_FIXED_N
+    if (P.flags & FLAG_WIND) dl_out = dl_out + plain(wind_dangular_momentum_dt(P, ro, cold, b, sys, strict(q.s), sd(w2)));
+#endif
 }
 
 

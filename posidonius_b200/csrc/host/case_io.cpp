@@ -10,6 +10,8 @@
 // the bincode writer and the JSON writer; the JSON reader is key-based because the Python case generator writes sorted keys.
 // Scratch fields that the integrator recomputes before every use are written as zeros.
 #include <cerrno>
+#include <cmath>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -83,6 +85,7 @@ struct BinWriter {
     void begin_vec(const char*, uint64_t& n) { u64(nullptr, n); }
     void end_vec() {}
     void begin_map(const char*, uint64_t& n) { u64(nullptr, n); }
+    void map_entry(uint64_t& key, double& value) { u64(nullptr, key); f64(nullptr, value); }
     void end_map() {}
     int enum_begin(const char*, int tag, const char* const*, int, bool) { uint32_t t = (uint32_t)tag; out.append((const char*)&t, 4); return tag; }
     void enum_end(bool) {}
@@ -103,7 +106,8 @@ struct BinReader {
     void end_array() {}
     void begin_vec(const char*, uint64_t& n) { u64(nullptr, n); if (n > (1ull << 28)) throw std::runtime_error("bincode image: implausible length"); }
     void end_vec() {}
-    void begin_map(const char*, uint64_t& n) { u64(nullptr, n); }
+    void begin_map(const char*, uint64_t& n) { u64(nullptr, n); if (n > (1ull << 20)) throw std::runtime_error("bincode image: implausible map length"); }
+    void map_entry(uint64_t& key, double& value) { u64(nullptr, key); f64(nullptr, value); }
     void end_map() {}
     int enum_begin(const char* key, int, const char* const*, int nvariants, bool) {
         need(4);
@@ -130,6 +134,7 @@ struct JsonWriter {
     void begin_vec(const char* key, uint64_t&) { k(key); w.begin_array(); }
     void end_vec() { w.end_array(); }
     void begin_map(const char* key, uint64_t&) { k(key); w.begin_object(); }
+    void map_entry(uint64_t& key, double& value) { w.key(std::to_string(key).c_str()); w.number(value); }   // serde_json: integer keys as strings
     void end_map() { w.end_object(); }
     int enum_begin(const char* key, int tag, const char* const* names, int, bool payload) {
         k(key);
@@ -368,10 +373,29 @@ template <class V> void walk_image(V& v, Image& img) {
     v.boolean("all", all); v.boolean("general_relativity", mg); v.boolean("tides", mt); v.boolean("rotational_flattening", mf); v.boolean("disk", md);
     v.end_struct();
     v.end_struct();
-    uint64_t nmap = 0;
-    v.begin_map("pair_dependent_scaled_dissipation_factor", nmap);
-    if (nmap != 0) throw Unsupported("pair-dependent dissipation factors (dynamical tides) are outside the B200 hot path");
-    v.end_map();
+    {   // HashMap<usize, f64> (universe.rs:61): entries in key order (upstream's order is the hasher's, i.e. arbitrary)
+        const int nkeys = PB200_MAX_PARTICLES * PB200_MAX_PARTICLES;
+        uint64_t nmap = 0;
+        if (!V::reading) for (int k = 0; k < nkeys; k++) if (c.pair_dependent_scaled_dissipation_factor[k] == c.pair_dependent_scaled_dissipation_factor[k]) nmap++;
+        v.begin_map("pair_dependent_scaled_dissipation_factor", nmap);
+        if (V::reading) {
+            for (int k = 0; k < nkeys; k++) c.pair_dependent_scaled_dissipation_factor[k] = NAN;
+            for (uint64_t e = 0; e < nmap; e++) {
+                uint64_t key = 0; double value = 0.;
+                v.map_entry(key, value);
+                if (key >= (uint64_t)nkeys) throw std::runtime_error("image: pair_dependent_scaled_dissipation_factor key out of range");
+                c.pair_dependent_scaled_dissipation_factor[key] = value;
+            }
+        } else {
+            for (int k = 0; k < nkeys; k++) {
+                double value = c.pair_dependent_scaled_dissipation_factor[k];
+                if (value != value) continue;
+                uint64_t key = (uint64_t)k;
+                v.map_entry(key, value);
+            }
+        }
+        v.end_map();
+    }
     v.begin_array("roche_radiuses");
     for (int i = 0; i < PB200_MAX_PARTICLES * PB200_MAX_PARTICLES; i++) v.f64(nullptr, c.roche_radiuses[i]);
     v.end_array();
@@ -438,13 +462,20 @@ void image_from_json(const Value& d, Image& img) {
     c.consider_general_relativity = ce.at("general_relativity").boolean(); c.consider_disk = ce.at("disk").boolean();
     c.consider_wind = ce.at("wind").boolean(); c.consider_evolution = ce.at("evolution").boolean();
     if (c.consider_disk) throw Unsupported("disk interaction is outside the B200 hot path");
-    if (c.consider_wind) throw Unsupported("stellar wind is outside the B200 hot path");
     c.general_relativity_implementation = index_of(kGrNames, 4, u.at("general_relativity_implementation").str, "GR implementation");
     const Value& hi = u.at("hosts").at("index");
     c.host_most_massive = (int32_t)hi.at("most_massive").u; c.host_tides = (int32_t)hi.at("tides").u;
     c.host_rotational_flattening = (int32_t)hi.at("rotational_flattening").u; c.host_general_relativity = (int32_t)hi.at("general_relativity").u;
     c.host_disk = (int32_t)hi.at("disk").u;
-    if (!u.at("pair_dependent_scaled_dissipation_factor").obj.empty()) throw Unsupported("pair-dependent dissipation factors (dynamical tides) are outside the B200 hot path");
+    for (int k = 0; k < PB200_MAX_PARTICLES * PB200_MAX_PARTICLES; k++) c.pair_dependent_scaled_dissipation_factor[k] = NAN;
+    if (const Value* pm = u.find("pair_dependent_scaled_dissipation_factor")) {
+        for (const auto& kv : pm->obj) {
+            char* end = nullptr;
+            unsigned long long key = std::strtoull(kv.first.c_str(), &end, 10);
+            if (!end || *end || key >= (unsigned long long)(PB200_MAX_PARTICLES * PB200_MAX_PARTICLES)) throw std::runtime_error("pair_dependent_scaled_dissipation_factor key out of range");
+            c.pair_dependent_scaled_dissipation_factor[key] = kv.second->number();
+        }
+    }
     for (int i = 0; i < c.n_particles; i++) {
         const Value& p = u.at("particles").at(i);
         pb200_body_t& b = c.bodies[i];
@@ -548,9 +579,6 @@ void finish_case(Image& img, pb200_case_t* out, pb200_table_store_t* store) {
         b.evolution_table = -1;
         b.evolution_left_index = (int32_t)img.evo_left_index[i];
         if (b.evolution_type != PB200_EVO_NONEVOLVING && c.consider_evolution) {
-            bool dynamical = b.evolution_type == PB200_EVO_GALLETBOLMONT2017 || b.evolution_type == PB200_EVO_BOLMONTMATHIS2016 ||
-                             (b.evolution_type == PB200_EVO_LECONTECHABRIER2013 && b.evolution_parameter != 0.);
-            if (dynamical) throw Unsupported("evolution types with dynamical-tide (pair-dependent) dissipation are outside the B200 hot path");
             if (img.evo[i][0].empty()) throw std::runtime_error("evolving body with an empty time table");
             b.evolution_table = (int32_t)(store->columns.size() / 5);
             for (int k = 0; k < 5; k++) store->columns.push_back(img.evo[i][k]);
@@ -594,7 +622,6 @@ int pb200_case_load(const char* path, pb200_case_t* out, pb200_table_store_t** t
             walk_image(r, img);
             if (r.p != data.size()) throw Unsupported("the bincode image is not a WHFast image (IAS15 / LeapFrog or a different MAX_PARTICLES build)");
             if (img.c.consider_disk) throw Unsupported("disk interaction is outside the B200 hot path");
-            if (img.c.consider_wind) throw Unsupported("stellar wind is outside the B200 hot path");
         }
         finish_case(img, out, store);
     } catch (const Unsupported& e) {

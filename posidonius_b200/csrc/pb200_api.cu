@@ -74,8 +74,14 @@ __global__ void init_physical_kernel(const __grid_constant__ KParams P) {
     double R = R0, g = g0, I = P.moi[i];
     if (P.flags & FLAG_EVO) evolved_values(P, b, P.t[sys], R, g);
     if (R != R0 || g != g0) I = (sd(m) * sd(g) * (sd(R) * sd(R))).v;   // evolution.rs:527-531
-    double invI = 1. / I;
-    P.spin[i] = P.L[i] * invI; P.spin[i + cs] = P.L[i + cs] * invI; P.spin[i + 2 * cs] = P.L[i + 2 * cs] * invI;
+    // calculate_spin (particles/common.rs:9-12) and the spin-dependent evolving quantities (evolution.rs:548-567)
+    const sd sx = sd(P.L[i]) / sd(I), sy = sd(P.L[i + cs]) / sd(I), sz = sd(P.L[i + 2 * cs]) / sd(I);
+    P.spin[i] = sx.v; P.spin[i + cs] = sy.v; P.spin[i + 2 * cs] = sz.v;
+    if ((P.flags & FLAG_DYN) && (P.flags & FLAG_EVO)) {
+        pbgen::Roles ro{};
+        ro.valid = true;
+        pbgen::update_lag_angle(P, ro, b, sys, P.t[sys], (sx * sx) + (sy * sy) + (sz * sz), true);
+    }
     // Roche radii use the radii AFTER the evolution update (whfast.rs:231-232). Body j's evolved radius is recomputed here:
     // an evolving body's radius depends on t only and a non-evolving one is never rewritten, so it does not matter
     // whether j's thread has already stored its value — no ordering between threads is needed.
@@ -150,7 +156,7 @@ __global__ void pack_history_kernel(const __grid_constant__ KParams P, int n_sna
     w[4] = (unsigned int)b; // particle id (i32)
     const bool have = k < P.hist_count[sys];  // systems that stopped early have fewer snapshots: zero records
     for (int f = 0; f < 14; f++) put(5 + 2 * f, have ? h[(size_t)(1 + f) * cs] : 0.);  // pos, spin, vel, mass, radius, rg2, love, sigma
-    put(5 + 2 * 14, 0.);                                   // lag_angle (0 for the supported evolution types, evolution.rs:552-565)
+    put(5 + 2 * 14, have ? h[(size_t)16 * cs] : 0.);       // lag_angle (evolution.rs:552-565)
     put(5 + 2 * 15, have ? h[(size_t)15 * cs] : 0.);       // denergy_dt
     put(5 + 2 * 16, 0.);                                   // disk migration_timescale (disk out of scope)
     if (!have) { put(0, 0.); }
@@ -190,6 +196,7 @@ struct pb200_ensemble {
     // device arrays that are not part of KParams constness
     double *d_mass = nullptr, *d_mass_g = nullptr, *d_sigma = nullptr, *d_k2t = nullptr, *d_k2f = nullptr, *d_roche = nullptr;
     double *d_energy = nullptr, *d_angmom = nullptr;
+    double *d_wind_k = nullptr, *d_wind_sat = nullptr, *d_diss = nullptr, *d_diss_scale = nullptr;
     unsigned int* d_records = nullptr;
     size_t records_capacity = 0;
     double recovery_snapshot_period = 0.;
@@ -278,7 +285,6 @@ int pb200_case_validate(const pb200_case_t* c, const pb200_table_t* tables, size
     if (c->coordinates_type < 0 || c->coordinates_type > 2) return set_error(PB200_E_INVALID, "unknown coordinates type");
     if (!(c->time_step > 0.) || c->half_time_step != 0.5 * c->time_step) return set_error(PB200_E_INVALID, "time_step must be > 0 and half_time_step = time_step / 2");
     if (c->consider_disk) return set_error(PB200_E_UNSUPPORTED, "disk interaction is outside the B200 hot path (no CPU fallback)");
-    if (c->consider_wind) return set_error(PB200_E_UNSUPPORTED, "stellar wind is outside the B200 hot path (no CPU fallback)");
     const int h = c->host_most_massive;
     if (h < 0 || h >= n) return set_error(PB200_E_INVALID, "host_most_massive out of range");
     for (int i = 0; i < n; i++) {
@@ -309,8 +315,6 @@ int pb200_case_validate(const pb200_case_t* c, const pb200_table_t* tables, size
             if (b.general_relativity_role == PB200_ROLE_CENTRAL && c->consider_general_relativity) return set_error(PB200_E_INVALID, "only one central body is allowed for general relativity effects");
         }
         if (c->consider_evolution && b.evolution_type != PB200_EVO_NONEVOLVING) {
-            if (is_dynamical_tide_evolution(b))
-                return set_error(PB200_E_UNSUPPORTED, "evolution types with dynamical-tide (pair-dependent) dissipation are outside the B200 hot path");
             if (b.evolution_table < 0 || (size_t)b.evolution_table >= n_tables || !tables)
                 return set_error(PB200_E_INVALID, "evolving body without an evolution table");
             const pb200_table_t& t = tables[b.evolution_table];
@@ -318,6 +322,7 @@ int pb200_case_validate(const pb200_case_t* c, const pb200_table_t* tables, size
             bool need_rg2 = b.evolution_type == PB200_EVO_BARAFFE2015 || b.evolution_type == PB200_EVO_LECONTE2011 ||
                             b.evolution_type == PB200_EVO_LECONTECHABRIER2013;
             if (need_rg2 && !t.radius_of_gyration_2) return set_error(PB200_E_INVALID, "evolution table needs a radius_of_gyration_2 column");
+            if (is_dynamical_tide_evolution(b) && !t.inverse_tidal_q_factor) return set_error(PB200_E_INVALID, "evolution table needs an inverse_tidal_q_factor column");
         }
     }
     // Q4: universe.rs:335-337 reads the host's stale heliocentric velocity; the kernel takes it as zero.
@@ -332,13 +337,14 @@ static int same_structure(const pb200_case_t& a, const pb200_case_t& b) {
         a.time_limit != b.time_limit || a.historic_snapshot_period != b.historic_snapshot_period ||
         a.consider_tides != b.consider_tides || a.consider_rotational_flattening != b.consider_rotational_flattening ||
         a.consider_general_relativity != b.consider_general_relativity || a.consider_evolution != b.consider_evolution ||
+        a.consider_wind != b.consider_wind ||
         a.general_relativity_implementation != b.general_relativity_implementation || a.host_most_massive != b.host_most_massive)
         return 0;
     for (int i = 0; i < a.n_particles; i++) {
         const pb200_body_t &x = a.bodies[i], &y = b.bodies[i];
         if (x.tides_role != y.tides_role || x.flattening_role != y.flattening_role ||
             x.general_relativity_role != y.general_relativity_role || x.evolution_type != y.evolution_type ||
-            x.evolution_table != y.evolution_table)
+            x.evolution_table != y.evolution_table || x.wind_role != y.wind_role || x.evolution_parameter != y.evolution_parameter)
             return 0;
     }
     return 1;
@@ -406,6 +412,15 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
         P.evo_table[i] = (c0.consider_evolution && b.evolution_type != PB200_EVO_NONEVOLVING) ? b.evolution_table : -1;
     }
     for (int i = n; i < PB200_MAX_PARTICLES; i++) P.evo_table[i] = -1;
+    P.wind_on = P.dyn_evo = 0;
+    for (int i = 0; i < n; i++) {
+        const pb200_body_t& b = c0.bodies[i];
+        if (c0.consider_wind && b.wind_role == 0) P.wind_on |= 1u << i;
+        // the reference matches on Particle.evolution whatever consider_effects.evolution says (constant_time_lag.rs:27, 96)
+        if (c0.consider_tides && is_dynamical_tide_evolution(b) && (i == P.host || b.tides_role == PB200_ROLE_ORBITING)) P.dyn_evo |= 1u << i;
+    }
+    if (P.wind_on) P.flags |= FLAG_WIND;
+    if (P.dyn_evo) P.flags |= FLAG_DYN;
     P.tides_host_central = c0.bodies[P.host].tides_role == PB200_ROLE_CENTRAL;
     P.flat_host_central = c0.bodies[P.host].flattening_role == PB200_ROLE_CENTRAL;
 
@@ -415,7 +430,7 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     CUDA_TRY_E(cudaEventCreate(&e->ev0));
     CUDA_TRY_E(cudaEventCreate(&e->ev1));
     // evolution tables (replicated per GPU, read through the read-only path)
-    for (int i = 0; i < PB200_MAX_PARTICLES; i++) P.tables[i] = DevTable{nullptr, nullptr, nullptr, 0, 0, 0};
+    for (int i = 0; i < PB200_MAX_PARTICLES; i++) P.tables[i] = DevTable{nullptr, nullptr, nullptr, 0, 0, 0, nullptr};
     for (int i = 0; i < n; i++) {
         int ti = P.evo_table[i];
         if (ti < 0 || P.tables[ti].time) continue;
@@ -432,7 +447,12 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
             TRY(dev_alloc(e, &dg, t.n_rows));
             CUDA_TRY_E(cudaMemcpy(dg, t.radius_of_gyration_2, t.n_rows * sizeof(double), cudaMemcpyHostToDevice));
         }
-        P.tables[ti] = DevTable{dt_, dr, dg, (int)t.n_rows, 1, need_rg2};
+        double* dq = nullptr;
+        if (is_dynamical_tide_evolution(b)) {
+            TRY(dev_alloc(e, &dq, t.n_rows));
+            CUDA_TRY_E(cudaMemcpy(dq, t.inverse_tidal_q_factor, t.n_rows * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        P.tables[ti] = DevTable{dt_, dr, dg, (int)t.n_rows, 1, need_rg2, dq};
     }
     const size_t ns = n_systems, nb = (size_t)n;
     TRY(dev_alloc(e, &P.pos, 3 * nb * ns)); TRY(dev_alloc(e, &P.vel, 3 * nb * ns)); TRY(dev_alloc(e, &P.acc, 3 * nb * ns));
@@ -448,6 +468,12 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     TRY(dev_alloc(e, &P.hist_count, ns));
     TRY(dev_alloc(e, &P.tide_scratch, (size_t)PB_TIDE_SCRATCH * nb * ns));
     TRY(dev_alloc(e, &e->d_energy, ns)); TRY(dev_alloc(e, &e->d_angmom, ns));
+    if (P.flags & FLAG_WIND) { TRY(dev_alloc(e, &e->d_wind_k, nb * ns)); TRY(dev_alloc(e, &e->d_wind_sat, nb * ns)); }
+    if (P.flags & FLAG_DYN) {
+        TRY(dev_alloc(e, &e->d_diss, nb * ns)); TRY(dev_alloc(e, &e->d_diss_scale, nb * ns)); TRY(dev_alloc(e, &P.lag, nb * ns));
+        TRY(dev_alloc(e, &P.pair_h, nb * ns)); TRY(dev_alloc(e, &P.pair_p, nb * ns));
+    }
+    P.wind_k = e->d_wind_k; P.wind_sat = e->d_wind_sat; P.diss = e->d_diss; P.diss_scale = e->d_diss_scale;
     // history planes: keep the buffer below ~256 MB
     {
         size_t per_slot = (size_t)PB_HIST_FIELDS * nb * ns * sizeof(double);
@@ -494,6 +520,19 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
         TRY(up1(e->d_sigma, [](const pb200_case_t& c, int b) { return c.bodies[b].tides_scaled_dissipation_factor; }));
         TRY(up1(e->d_k2t, [](const pb200_case_t& c, int b) { return c.bodies[b].tides_role != PB200_ROLE_DISABLED ? c.bodies[b].tides_love_number : 0.; }));
         TRY(up1(e->d_k2f, [](const pb200_case_t& c, int b) { return c.bodies[b].flattening_role != PB200_ROLE_DISABLED ? c.bodies[b].flattening_love_number : 0.; }));
+        if (P.flags & FLAG_WIND) {
+            TRY(up1(e->d_wind_k, [](const pb200_case_t& c, int b) { return c.bodies[b].wind_k_factor; }));
+            TRY(up1(e->d_wind_sat, [](const pb200_case_t& c, int b) { return c.bodies[b].wind_rotation_saturation; }));
+        }
+        if (P.flags & FLAG_DYN) {
+            const int host = P.host;
+            TRY(up1(e->d_diss, [](const pb200_case_t& c, int b) { return c.bodies[b].tides_dissipation_factor; }));
+            TRY(up1(e->d_diss_scale, [](const pb200_case_t& c, int b) { return c.bodies[b].tides_dissipation_factor_scale; }));
+            TRY(up1(P.lag, [](const pb200_case_t& c, int b) { return c.bodies[b].tides_lag_angle; }));
+            // the HashMap entries (host, b) and (b, host), keyed by particle id (constant_time_lag.rs:152-160)
+            TRY(up1(P.pair_h, [host](const pb200_case_t& c, int b) { return c.pair_dependent_scaled_dissipation_factor[c.bodies[host].id * PB200_MAX_PARTICLES + c.bodies[b].id]; }));
+            TRY(up1(P.pair_p, [host](const pb200_case_t& c, int b) { return c.pair_dependent_scaled_dissipation_factor[c.bodies[b].id * PB200_MAX_PARTICLES + c.bodies[host].id]; }));
+        }
         // roche [i][j][s]
         {
             std::vector<double> rb(nb * nb * ns);
@@ -720,6 +759,14 @@ int pb200_ensemble_get_case(pb200_ensemble_t* e, size_t s, pb200_case_t* out) {
         size_t i = b * ns + s;
         CUDA_TRY(get(e->P.radius, i, &B.radius, 8)); CUDA_TRY(get(e->P.rg2, i, &B.radius_of_gyration_2, 8));
         CUDA_TRY(get(e->P.moi, i, &B.moment_of_inertia, 8));
+        if (e->P.flags & FLAG_DYN) {
+            CUDA_TRY(get(e->P.lag, i, &B.tides_lag_angle, 8));
+            const int hid = out->bodies[e->P.host].id;
+            if ((int)b != e->P.host && B.id >= 0 && B.id < PB200_MAX_PARTICLES && hid >= 0 && hid < PB200_MAX_PARTICLES) {
+                CUDA_TRY(get(e->P.pair_h, i, &out->pair_dependent_scaled_dissipation_factor[hid * PB200_MAX_PARTICLES + B.id], 8));
+                CUDA_TRY(get(e->P.pair_p, i, &out->pair_dependent_scaled_dissipation_factor[B.id * PB200_MAX_PARTICLES + hid], 8));
+            }
+        }
     }
     for (size_t i = 0; i < nb * nb; i++) CUDA_TRY(get(e->d_roche, i * ns + s, &out->roche_radiuses[i], 8));
     unsigned long long u;

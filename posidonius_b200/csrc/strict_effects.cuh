@@ -35,6 +35,10 @@ __device__ __forceinline__ void make_consts_strict(const KParams& P, const Roles
     cold.set(Z_KCONS, (m2 * Rh5 * k2t_h + M2 * R5 * sd(k2t)).v);  // :284-285
     cold.set(Z_T1, (m2 * Rh10 * sig_h).v);                      // :291-293
     cold.set(Z_T2, (M2 * R10 * sd(sigma)).v);                   // :294-296
+#if !PB_FIXED_N
+    cold.set(D_0, (sd(4.5) * m2 * Rh10).v); cold.set(D_1, (sd(4.5) * M2 * R10).v);   // the same products up to sigma
+    cold.set(D_2, (m2 * Rh10).v); cold.set(D_3, (M2 * R10).v);
+#endif
     cold.set(Z_INVM, (sd(1.) / m).v); cold.set(Z_INVMH, (sd(1.) / M).v);
     cold.set(Z_FS0, (m * k2f_h).v); cold.set(Z_FP0, (M * sd(k2f)).v);   // oblate_spheroid.rs:37, 42 leading products
     cold.set(Z_R5, R5.v); cold.set(Z_RH5, Rh5.v);
@@ -65,8 +69,9 @@ __device__ __forceinline__ S3 host_ordered_sum(const Cold& cold, int slot, int b
 __device__ __forceinline__ void put3(const Cold& cold, int slot, S3 v) { cold.set(slot, v.x.v); cold.set(slot + 1, v.y.v); cold.set(slot + 2, v.z.v); }
 
 template <int GR>
-__device__ __forceinline__ void additional_effects_strict(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, Lane& q,
-                                                          S3 hr, sd dist, S3 hv, V3& a_out, V3& dl_out, double* tide_save) {
+__device__ __forceinline__ void additional_effects_strict(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys,
+                                                          double t, bool evolve_now, Lane& q, S3 hr, sd dist, S3 hv, V3& a_out,
+                                                          V3& dl_out, double* tide_save) {
     const int n = PB_N(P);
     const sd zero = sd(0.);
     // Q3: r.omega with the spins of the previous evaluation (tides/common.rs:155-160 = rotational_flattening/common.rs:105-110)
@@ -81,6 +86,9 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
     q.s = plain(s);
     const S3 sh = shfl3(s, hl);
     const sd wh2 = shfl(w2, hl);
+#if !PB_FIXED_N
+    if (evolve_now && (P.flags & FLAG_DYN) && (P.flags & FLAG_EVO)) { update_lag_angle(P, ro, b, sys, t, w2, true); __syncwarp(); }
+#endif
     // inertial_to_heliocentric (universe.rs:331-338); the host's stale heliocentric velocity is zero (validated)
     const sd radvel = (hr.x * hv.x + hr.y * hv.y + hr.z * hv.z) / dist;
     const sd normv2 = hv.x * hv.x + hv.y * hv.y + hv.z * hv.z;
@@ -91,13 +99,23 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
     // terms for the host, exchanged through shared memory: X_0.. = tides F, tides -N_s, flattening F, flattening -N_s
     S3 xF_t = t_acc, xN_t = t_acc, xF_f = t_acc, xN_f = t_acc;
     if (P.flags & FLAG_TIDES) {
-        const sd orth_s = P.tides_host_central ? sd(cold.get(Z_CS)) / d7 : zero;
-        const sd orth_p = sd(cold.get(Z_CP)) / d7;
+        sd cs = sd(cold.get(Z_CS)), cp = sd(cold.get(Z_CP)), t1 = sd(cold.get(Z_T1)), t2 = sd(cold.get(Z_T2));
+#if !PB_FIXED_N
+        if (P.flags & FLAG_DYN) {
+            // sigma is the last factor of each product in the reference, so multiplying it in here rounds identically
+            sd sig_h, sig_p;
+            pair_dependent_sigmas(P, ro, cold, hl, b, sys, hr, hv, w2, wh2, sig_h, sig_p);
+            cs = sd(cold.get(D_0)) * sig_h; cp = sd(cold.get(D_1)) * sig_p;
+            t1 = sd(cold.get(D_2)) * sig_h; t2 = sd(cold.get(D_3)) * sig_p;
+        }
+#endif
+        const sd orth_s = P.tides_host_central ? cs / d7 : zero;
+        const sd orth_p = cp / d7;
         const sd host_k = sd(cold.get(Z_KCONS));
         const sd cons = sd(-3.0 * kK2) / d7 * host_k;
         const sd factor1 = sd(-13.5) * radvel / d8;
-        const sd diss_pm = factor1 * sd(cold.get(Z_T2));
-        const sd diss = diss_pm + factor1 * sd(cold.get(Z_T1));
+        const sd diss_pm = factor1 * t2;
+        const sd diss = diss_pm + factor1 * t1;
         const sd t_radial = cons + diss;
         const sd f3 = t_radial + (orth_s + orth_p) * radvel / dist;
         const sd osd = orth_s / dist, opd = orth_p / dist;
@@ -254,7 +272,11 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
     if (P.flags & FLAG_TIDES) a = a + ta;
     if (P.flags & FLAG_FLAT) a = a + fa_;
     if (P.flags & FLAG_GR) a = a + ga;
-    S3 dl = s3(td.x + fd.x + gd.x + zero, td.y + fd.y + gd.y + zero, td.z + fd.z + gd.z + zero);
+    S3 wd = s3(zero, zero, zero);
+#if !PB_FIXED_N
+    if (P.flags & FLAG_WIND) wd = wind_dangular_momentum_dt(P, ro, cold, b, sys, s, w2);
+#endif
+    S3 dl = s3(td.x + fd.x + gd.x + wd.x, td.y + fd.y + gd.y + wd.y, td.z + fd.z + gd.z + wd.z);
     if (!ro.valid) { a = s3(zero, zero, zero); dl = a; }
     a_out = plain(a);
     dl_out = plain(dl);

@@ -45,8 +45,14 @@ __device__ constexpr double kInvC2 = 1.0 / kC2;
 __device__ constexpr double kEps2 = 2.2204460492503131e-16 * 2.2204460492503131e-16;
 __device__ constexpr double kMaxDistance2 = 100. * 100.;
 __device__ constexpr double kPi = 3.14159265358979323846264338327950288;
+__device__ constexpr double kRSun = 6.957e8 / PB_AU;                      // constants.rs:52
+__device__ constexpr double kSunDynFreq2 = kK2 / (kRSun * kRSun * kRSun);  // constants.rs:66
+__device__ constexpr double kSmoothDynTide = 1.0e-5 * 86400.;              // constants.rs:67
 
-enum : int { FLAG_TIDES = 1, FLAG_FLAT = 2, FLAG_GR = 4, FLAG_EVO = 8 };
+// FLAG_WIND: some body has WindEffect::Interaction (wind.rs:72-91). FLAG_DYN: some body's EvolutionType drives dynamical
+// tides, i.e. pair-dependent dissipation factors (tides/constant_time_lag.rs:20-165). Both live in the run-time
+// geometry build of the kernel only (PB_FIXED_N == 0).
+enum : int { FLAG_TIDES = 1, FLAG_FLAT = 2, FLAG_GR = 4, FLAG_EVO = 8, FLAG_WIND = 16, FLAG_DYN = 32 };
 
 // Device-side description of one evolution table (effects/evolution.rs:19-28).
 struct DevTable {
@@ -56,6 +62,7 @@ struct DevTable {
     int n_rows;
     int interp_radius;  // 1 unless NonEvolving
     int interp_rg2;     // Baraffe2015 / Leconte2011 / LeconteChabrier2013
+    const double* qinv; // inverse tidal Q factor: BolmontMathis2016 / GalletBolmont2017 / LeconteChabrier2013(true), else null
 };
 
 // Kernel parameters: everything uniform across the ensemble + SoA pointers.
@@ -87,6 +94,13 @@ struct KParams {
     int* hist_count;            // per system: slots used
     // stale tidal internals for denergy_dt (tides/common.rs:263-279 reads the last evaluation), [k(13)][b][s]
     double* tide_scratch;
+    // wind (wind.rs) and dynamical tides (constant_time_lag.rs:20-165); arrays are null unless the flag is set
+    uint32_t wind_on;   // bit b: WindEffect::Interaction
+    uint32_t dyn_evo;   // bit b: the body's EvolutionType drives dynamical tides
+    const double *wind_k, *wind_sat;        // [b][s]
+    const double *diss, *diss_scale;        // [b][s] ConstantTimeLagParameters.dissipation_factor(_scale)
+    double* lag;                            // [b][s] tides.parameters.internal.lag_angle (evolution.rs:548-567)
+    double *pair_h, *pair_p;                // [b][s] map entries (host, b) and (b, host); NaN = absent
 };
 
 #define FULL 0xffffffffu
@@ -315,6 +329,8 @@ enum ColdSlot : int {
     K_MH, K_MGH, K_MTOT, K_KMU, K_BACKW, K_WHDSF, K_ETAK,
     // strict arithmetic mode (strict_effects.cuh): two more constants and the 4-vector exchange buffer for the host sums
     Z_0, Z_1, X_0, X_1, X_2, X_3, X_4, X_5, X_6, X_7, X_8, X_9, X_10, X_11,
+    // dynamical tides: the sigma-free parts of the tidal constants (the pair-dependent sigma multiplies them per evaluation)
+    D_0, D_1, D_2, D_3,
     N_COLD_SLOTS,
     // fast mode: 13 GR polynomial coefficients overlay the strict-mode slots (never live together)
     G_0 = Z_0

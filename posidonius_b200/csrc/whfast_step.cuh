@@ -13,7 +13,7 @@ using namespace pb200;
 #ifndef PB_BLOCK
 #define PB_BLOCK 128
 #endif
-#define PB_HIST_FIELDS 16  // time, pos3, spin3, vel3, mass, radius, rg2, love_number, sigma, denergy_dt
+#define PB_HIST_FIELDS 17  // time, pos3, spin3, vel3, mass, radius, rg2, love_number, sigma, denergy_dt, lag_angle
 #define PB_TIDE_SCRATCH 13
 
 struct SysState {
@@ -126,8 +126,9 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
         V3 hv = plain(hv_s);
         V3 a, dldt;
         double scratch[PB_TIDE_SCRATCH];
-        if (ARITH) additional_effects_strict<GR>(P, ro, cold, hl, b, q, hr_s, dist_s, hv_s, a, dldt, save_tides ? scratch : nullptr);
-        else additional_effects<GR>(P, ro, cold, hl, q, hr, inv_d, hv, a, dldt, save_tides ? scratch : nullptr);
+        const bool evolve_now = evolution && it == 0;
+        if (ARITH) additional_effects_strict<GR>(P, ro, cold, hl, b, sys, t, evolve_now, q, hr_s, dist_s, hv_s, a, dldt, save_tides ? scratch : nullptr);
+        else additional_effects<GR>(P, ro, cold, hl, b, sys, t, evolve_now, q, hr, inv_d, hv, a, dldt, save_tides ? scratch : nullptr);
         if (save_tides && (P.flags & FLAG_TIDES) && ro.valid && !done) {
             const size_t ns = (size_t)P.n_sys;
             const size_t i = (size_t)b * ns + sys, cs = (size_t)PB_N(P) * ns;
@@ -353,6 +354,12 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
                 }
                 if (snap) { sd I = sd(cold.get(K_I)); q.s = v3((sd(q.L.x) / I).v, (sd(q.L.y) / I).v, (sd(q.L.z) / I).v); }   // spin = L / I (common.rs:9-11)
+#if !PB_FIXED_N
+                if ((P.flags & FLAG_DYN) && (P.flags & FLAG_EVO)) {
+                    const S3 ss = strict(q.s);
+                    update_lag_angle(P, ro, b, sys, st.t, (ss.x * ss.x) + (ss.y * ss.y) + (ss.z * ss.z), snap);
+                }
+#endif
                 if (snap && ro.valid && st.hist_count < P.hist_capacity) {
                     const size_t ns = (size_t)P.n_sys;
                     const size_t i = (size_t)b * ns + sys, cs = (size_t)n * ns;
@@ -377,6 +384,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     h[7 * cs] = q.v.x.v; h[8 * cs] = q.v.y.v; h[9 * cs] = q.v.z.v;
                     h[10 * cs] = cold.get(K_M); h[11 * cs] = cold.get(K_R); h[12 * cs] = P.rg2[i];
                     h[13 * cs] = P.k2t[i]; h[14 * cs] = P.sigma[i]; h[15 * cs] = denergy;
+                    h[16 * cs] = (P.flags & FLAG_DYN) ? P.lag[i] : 0.;
                 }
                 if (snap) {
                     if (!first) st.last_hist = __dadd_rn(st.last_hist, P.hist_period); else st.last_hist = 0.;

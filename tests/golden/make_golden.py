@@ -39,14 +39,22 @@ FIXTURES = {
     "test_evolution-m_dwarf_non_evolving": None,
     "test_star_types-brown_dwarf": None,
     "test_star_types-m_dwarf": None,
+    # solar-like hosts: stellar wind (wind.rs) on every one, dynamical tides (pair-dependent dissipation factors,
+    # constant_time_lag.rs:20-165) for BolmontMathis2016 / GalletBolmont2017
+    "test_evolution-solar_like_baraffe1998": None,
+    "test_evolution-solar_like_baraffe2015": None,
+    "test_evolution-solar_like_bolmontmathis2016": None,
+    "test_evolution-solar_like_galletbolmont2017": None,
+    "test_evolution-solar_like_non_evolving": None,
+    "test_star_types-solar_like": None,
+    "test_disk-disabled_disk": None,
     "test_order-whfast_jacobi": "test_integrator-whfast_jacobi",
     "test_order-whfast_democraticheliocentric": "test_integrator-whfast_democraticheliocentric",
     "test_order-whfast_whds": "test_integrator-whfast_whds",
 }
 # Out-of-scope fixtures kept to test the rejection path (error, no fallback).
 # (Kaula / creep fixtures ship no case.json upstream; the tests synthesise those by editing a WHFast case.)
-REJECT = ["test_integrator-ias15", "test_integrator-leapfrog", "test_evolution-solar_like_baraffe1998",
-          "test_evolution-solar_like_bolmontmathis2016", "test_disk-enabled_disk"]
+REJECT = ["test_integrator-ias15", "test_integrator-leapfrog", "test_disk-enabled_disk"]
 
 
 def strip_tables(d):

@@ -108,7 +108,7 @@ def test_ensemble_subcommand(tmp_path):
 
 def test_unsupported_case_is_rejected_not_run_on_a_fallback(tmp_path):
     d = config_case("c4_trappist1")
-    d["universe"]["consider_effects"]["wind"] = True
+    d["universe"]["consider_effects"]["disk"] = True
     p = tmp_path / "case.json"
     p.write_text(json.dumps(d))
     out = run("start", p, tmp_path / "rec.bin", tmp_path / "hist.bin", expect=101)

@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_header_symbol():
 def test_ctypes_layout_matches_header_sizes():
     # sizes implied by the header: doubles/ints only, natural alignment
     assert C.sizeof(abi.Body) == 8 * (5 + 3 * 7 + 9) + 4 * 10 + 8 * 8
-    assert C.sizeof(abi.Case) == 8 * 9 + 8 * 3 + 4 * 14 + C.sizeof(abi.Body) * 10 + 8 * 30 * 2 + 8 * 100
+    assert C.sizeof(abi.Case) == 8 * 9 + 8 * 3 + 4 * 14 + C.sizeof(abi.Body) * 10 + 8 * 30 * 2 + 8 * 100 * 2
     assert C.sizeof(abi.StateView) == 8 * 11
 
 
