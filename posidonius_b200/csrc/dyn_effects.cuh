@@ -36,10 +36,10 @@ __device__ __forceinline__ void perihelion_and_eccentricity(sd gm, S3 r, S3 v, s
     const sd hx = r.y * v.z - r.z * v.y, hy = r.z * v.x - r.x * v.z, hz = r.x * v.y - r.y * v.x;
     const sd h2 = hx * hx + hy * hy + hz * hz;   // powf(2.) is folded to a product by LLVM
     const sd v2 = v.x * v.x + v.y * v.y + v.z * v.z;
-    const sd rr = ssqrt(r.x * r.x + r.y * r.y + r.z * r.z);
+    const sd rr = ssqrt_ieee(r.x * r.x + r.y * r.y + r.z * r.z);
     const sd s = h2 / gm;
     const sd temp = sd(1.) + s * (v2 / gm - sd(2.) / rr);
-    e = temp.v <= 0. ? sd(0.) : ssqrt(temp);
+    e = temp.v <= 0. ? sd(0.) : ssqrt_ieee(temp);
     q = s / (sd(1.) + e);
 }
 
@@ -61,11 +61,11 @@ __device__ __forceinline__ void pair_dependent_sigmas(const KParams& P, const Ro
     const sd gm = sd(cold.get(K_MGH)) + sd(cold.get(K_MG));
     sd q, e;
     perihelion_and_eccentricity(gm, hr, hv, q, e);
-    const sd mean_motion = ssqrt(gm) * sd(pow((q / (sd(1.0) - e)).v, -1.5));
+    const sd mean_motion = ssqrt_ieee(gm) * sd(pow((q / (sd(1.0) - e)).v, -1.5));
     bool set_h = false;
     sd val_h = sd(0.);
     if (host_dyn) {
-        const sd wn = ssqrt(wh2);
+        const sd wn = ssqrt_ieee(wh2);
         sd half = sabs(wn - mean_motion);
         if (half.v < wn.v) {
             if (half.v < kSmoothDynTide) half = sd(kSmoothDynTide);
@@ -76,7 +76,7 @@ __device__ __forceinline__ void pair_dependent_sigmas(const KParams& P, const Ro
         }
     }
     if (body_dyn) {
-        const sd wn = ssqrt(w2);
+        const sd wn = ssqrt_ieee(w2);
         sd half = sabs(wn - mean_motion);
         if (half.v < wn.v) {
             if (half.v < kSmoothDynTide) half = sd(kSmoothDynTide);
@@ -102,9 +102,9 @@ __device__ __forceinline__ S3 wind_dangular_momentum_dt(const KParams& P, const 
     const bool on = ro.valid && ((P.wind_on >> b) & 1u);
     double k = 0., sat = 1.;
     if (on) { const size_t i = (size_t)b * (size_t)P.n_sys + sys; k = P.wind_k[i]; sat = P.wind_sat[i]; }
-    const sd threshold = ssqrt(w2);
+    const sd threshold = ssqrt_ieee(w2);
     const sd factor = threshold.v >= sat ? sd(sat) * sd(sat) : w2;   // rotation_saturation_2 = powi(2) (wind.rs:52)
-    const sd root = ssqrt(sd(cold.get(K_R)) / sd(kRSun) * sd(1.) / sd(cold.get(K_M)));
+    const sd root = ssqrt_ieee(sd(cold.get(K_R)) / sd(kRSun) * sd(1.) / sd(cold.get(K_M)));
     const sd mk = sd(-1.) * sd(k);
     S3 out = s3(mk * s.x * factor * root, mk * s.y * factor * root, mk * s.z * factor * root);
     if (!on) out = s3(sd(0.), sd(0.), sd(0.));

@@ -137,7 +137,7 @@ __device__ __forceinline__ V3 sel(bool c, V3 a, V3 b) { return v3(c ? a.x : b.x,
 // Stumpff functions c0..c3 (whfast.rs:844-876) and Stiefel G-functions (whfast.rs:835-842), strict arithmetic
 __device__ __forceinline__ void stumpff_cs3(sd z, sd& c0, sd& c1, sd& c2, sd& c3) {
     int n = 0;
-    while (fabs(z.v) > 0.1) { z = z / sd(4.); n++; }
+    while (fabs(z.v) > 0.1) { z = z * sd(0.25); n++; }   // z / 4 (exact scaling, same value)
     sd c_odd = sd(1. / 6227020800.);   // 1/13!
     sd c_even = sd(1. / 479001600.);   // 1/12!
     c_odd = sd(1. / 39916800.) - z * c_odd;   c_even = sd(1. / 3628800.) - z * c_even;  // 11!, 10!
@@ -186,7 +186,7 @@ __device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu_i
         if (work && !tswarn) {
             double w = (dt.v * dt.v) * (beta.v * beta.v * beta.v), lim = (two_pi.v * mu.v) * (two_pi.v * mu.v);
             bool warn = w > 2. * lim;
-            if (!warn && w > 0.5 * lim) { sd ip = ssqrt(beta) * beta / (two_pi * mu); warn = fabs(dt.v) * ip.v > 1.; }
+            if (!warn && w > 0.5 * lim) { sd ip = div_ieee(ssqrt_ieee(beta) * beta, two_pi * mu); warn = fabs(dt.v) * ip.v > 1.; }
             if (warn) { tswarn = true; warnings |= PB200_WARN_TIMESTEP_GT_PERIOD; }
         }
         sd dtr0i = dt * r0i;
@@ -205,12 +205,12 @@ __device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu_i
         double dx = (x - old_x).v;
         double qv = dx * dx * beta.v, lim = (0.01 * two_pi.v) * (0.01 * two_pi.v);
         quartic = qv > 2. * lim;
-        if (!quartic && qv > 0.5 * lim) { sd xpp = two_pi / ssqrt(beta); quartic = fabs(dx) > (sd(0.01) * xpp).v; }
+        if (!quartic && qv > 0.5 * lim) { sd xpp = div_ieee(two_pi, ssqrt_ieee(beta)); quartic = fabs(dx) > (sd(0.01) * xpp).v; }
     }
     if (__any_sync(FULL, quartic)) {
         // Laguerre-like quartic solver (whfast.rs:732-755), rare: large steps only.
         if (quartic) {
-            x = beta * dt / mu;
+            x = div_ieee(beta * dt, mu);
             double prev_x[64];
             for (int k = 0; k < 64; k++) prev_x[k] = 0.;
             for (int n_lag = 1; n_lag < 64; n_lag++) {
@@ -218,14 +218,14 @@ __device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu_i
                 sd f = r0 * x + eta0 * g2 + zeta0 * g3 - dt;
                 sd fp = r0 + eta0 * g1 + zeta0 * g2;
                 sd fpp = eta0 * g0 + zeta0 * g1;
-                sd denom = fp + ssqrt(sabs(sd(16.) * fp * fp - sd(20.) * f * fpp));
-                x = (x * denom - sd(5.) * f) / denom;
+                sd denom = fp + ssqrt_ieee(sabs(sd(16.) * fp * fp - sd(20.) * f * fpp));
+                x = div_ieee(x * denom - sd(5.) * f, denom);
                 bool hit = false;
                 for (int k = 1; k < n_lag; k++) if (x.v == prev_x[k]) hit = true;
                 if (hit) { converged = true; break; }
                 prev_x[n_lag] = x.v;
             }
-            ri = sd(1.) / (r0 + (eta0 * g1 + zeta0 * g2));
+            ri = div_ieee(sd(1.), r0 + (eta0 * g1 + zeta0 * g2));
         }
     }
     {
@@ -251,27 +251,27 @@ __device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu_i
         if (bisect) {
             sd x_min, x_max;
             if (elliptic) {
-                sd sqrt_beta = ssqrt(beta);
-                sd invperiod = sqrt_beta * beta / (two_pi * mu);
-                sd x_per_period = two_pi / sqrt_beta;
+                sd sqrt_beta = ssqrt_ieee(beta);
+                sd invperiod = div_ieee(sqrt_beta * beta, two_pi * mu);
+                sd x_per_period = div_ieee(two_pi, sqrt_beta);
                 x_min = x_per_period * sd(floor((dt * invperiod).v));
                 x_max = x_min + x_per_period;
             } else {
                 sd h2 = r0 * r0 * v2 - eta0 * eta0;
-                sd q = h2 / mu / (sd(1.) + ssqrt(sd(1.) - h2 * beta / (mu * mu)));
-                sd vq = ssqrt(h2) / q;
-                x_min = sd(1.) / (vq + r0 / dt);
-                x_max = dt / q;
+                sd q = div_ieee(div_ieee(h2, mu), sd(1.) + ssqrt_ieee(sd(1.) - div_ieee(h2 * beta, mu * mu)));
+                sd vq = div_ieee(ssqrt_ieee(h2), q);
+                x_min = div_ieee(sd(1.), vq + div_ieee(r0, dt));
+                x_max = div_ieee(dt, q);
             }
-            x = (x_max + x_min) / sd(2.);
+            x = div_ieee(x_max + x_min, sd(2.));
             for (int guard = 0; guard < 200; guard++) {   // the reference's `loop {}` never ends on NaN input
                 stiefel_gs3(beta, x, g0, g1, g2, g3);
                 sd s = r0 * x + eta0 * g2 + zeta0 * g3 - dt;
                 if (s.v >= 0.) x_max = x; else x_min = x;
-                x = (x_max + x_min) / sd(2.);
-                if ((sabs(x_max - x_min) / x_max).v <= 1e-15) break;
+                x = div_ieee(x_max + x_min, sd(2.));
+                if (div_ieee(sabs(x_max - x_min), x_max).v <= 1e-15) break;
             }
-            ri = sd(1.) / (r0 + (eta0 * g1 + zeta0 * g2));
+            ri = div_ieee(sd(1.), r0 + (eta0 * g1 + zeta0 * g2));
         }
     }
     if (isnan(ri.v)) { ri = sd(0.); g1 = sd(0.); g2 = sd(0.); g3 = sd(0.); }
@@ -300,7 +300,7 @@ __device__ __forceinline__ double table_interp(const double* __restrict__ time, 
     if (i >= n) return __ldg(y + n - 1);
     // strict, in the order of tools.rs:853-855
     sd xl = sd(__ldg(time + i - 1)), xr = sd(__ldg(time + i));
-    sd pct = (sd(t) - xl) / (xr - xl);
+    sd pct = div_ieee(sd(t) - xl, xr - xl);
     return (sd(__ldg(y + i - 1)) * (sd(1.) - pct) + sd(__ldg(y + i)) * pct).v;
 }
 
@@ -327,6 +327,7 @@ enum ColdSlot : int {
     C_INVI, C_AS, C_AP, C_BK, C_KS, C_KP, C_IH, C_INVM, C_INVMH, C_MH, C_MGS, C_GRF, C_MURED, C_MD, C_MOM, C_FMS, C_FMP, C_FA,
     // constants of the coordinate transforms (strict)
     K_MH, K_MGH, K_MTOT, K_KMU, K_BACKW, K_WHDSF, K_ETAK,
+    K_YMH, K_YMTOT,              // refined reciprocals of the host mass and the total mass (strict.cuh, srcp)
     // strict arithmetic mode (strict_effects.cuh): two more constants and the 4-vector exchange buffer for the host sums
     Z_0, Z_1, X_0, X_1, X_2, X_3, X_4, X_5, X_6, X_7, X_8, X_9, X_10, X_11,
     // dynamical tides: the sigma-free parts of the tidal constants (the pair-dependent sigma multiplies them per evaluation)

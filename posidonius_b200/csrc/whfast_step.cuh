@@ -326,6 +326,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
         const sd kepler_mu = COORD == PB200_COORD_JACOBI ? mu_k : (COORD == PB200_COORD_WHDS ? Mg_s + mg_s : Mg_s);
         cold.set(K_MH, M_s.v); cold.set(K_MGH, Mg_s.v); cold.set(K_MTOT, mtot.v); cold.set(K_KMU, kepler_mu.v);
         cold.set(K_BACKW, back_w.v); cold.set(K_WHDSF, whds_f.v); cold.set(K_ETAK, eta_k.v);
+        cold.set(K_YMH, make_rcp(M_s).y); cold.set(K_YMTOT, make_rcp(mtot).y);
     }
     const int first_other = PB_HOST(P) == 0 ? 1 : 0;
     const sd zero = sd(0.), one = sd(1.);
@@ -403,6 +404,9 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
             if (half == 1) {
                 const sd m_s = sd(cold.get(K_M)), M_s = sd(cold.get(K_MH)), mtot = sd(cold.get(K_MTOT));
                 const sd dt_s = sd(P.dt), hdt_s = sd(P.half_dt);
+                // step-invariant divisors with their refined reciprocals (strict.cuh): 3 instructions per division
+                srcp rM, rT;
+                rM.b = M_s.v; rM.y = cold.get(K_YMH); rT.b = mtot.v; rT.y = cold.get(K_YMTOT);
                 S3 apos, avel;       // this body's alternative coordinates
                 S3 spos, svel;       // the host slot of the alternative coordinates (centre of mass), replicated in the group
                 S3 anew_s = zero3;
@@ -430,7 +434,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     S3 mr = q.r * m_s, mv = q.v * m_s;
                     S3 sr = ordered_sum_others(zero3 + shfl3(mr, hl), mr, gb, n, PB_HOST(P));
                     S3 sv = ordered_sum_others(zero3 + shfl3(mv, hl), mv, gb, n, PB_HOST(P));
-                    spos = sr / mtot; svel = sv / mtot;
+                    spos = sr / rT; svel = sv / rT;
                     apos = q.r - shfl3(q.r, hl);
                     avel = q.v - svel;
                     if (COORD == PB200_COORD_WHDS) avel = avel * sd(cold.get(K_WHDSF));
@@ -467,7 +471,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                             avel = avel + dt_s * anew_s;
                         } else {
                             sd f = M_s + m_s;
-                            avel = s3(avel.x + dt_s * f * anew_s.x / M_s, avel.y + dt_s * f * anew_s.y / M_s, avel.z + dt_s * f * anew_s.z / M_s);
+                            avel = s3(avel.x + dt_s * f * anew_s.x / rM, avel.y + dt_s * f * anew_s.y / rM, avel.z + dt_s * f * anew_s.z / rM);
                         }
                     }
                     // ---- jump (whfast.rs:495-556): before the Kepler drift in the second half, after it in the first
@@ -479,7 +483,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         if (COORD != PB200_COORD_JACOBI && jump_slot != phase) {
                             if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
                                 S3 p = ordered_sum_others(zero3, m_s * avel, gb, n, PB_HOST(P));
-                                apos = s3(apos.x + hdt_s * p.x / M_s, apos.y + hdt_s * p.y / M_s, apos.z + hdt_s * p.z / M_s);
+                                apos = s3(apos.x + hdt_s * p.x / rM, apos.y + hdt_s * p.y / rM, apos.z + hdt_s * p.z / rM);
                             } else {
                                 sd f = M_s + m_s;
                                 S3 term = s3(m_s * avel.x / f, m_s * avel.y / f, m_s * avel.z / f);
@@ -508,7 +512,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     } else {
                         // positions (whfast.rs:1128-1155); the host lane divides a dummy instead of its zero vector
                         S3 num = ro.planet ? apos * m_s : one3;
-                        S3 term = num / mtot;
+                        S3 term = num / rT;
                         S3 star_r = ordered_diff_others(spos, term, gb, n, PB_HOST(P));
                         S3 nr = ro.host ? star_r : apos + star_r;
                         if (alive) q.r = nr;
