@@ -337,13 +337,24 @@ enum ColdSlot : int {
     G_0 = Z_0
 };
 
+//
+// The same columns double as the exchange medium inside a group: a lane leaves a value in its own column of a slot,
+// __syncwarp(), and any lane of the group reads it with one LDS.64 (`getk`: column of body k). That replaces the
+// two 32-bit shuffles per double plus the moves ptxas needs to re-pair the halves under register pressure
+// (profiles/r1_variants.md). While the drift-kick-drift core runs, the midpoint's working set (S_VOX .. S_DLZ, S_RX..)
+// is dead and serves as exchange space (E_A .. E_R).
 struct Cold {
     volatile double* base;  // shared memory + threadIdx.x
+    volatile double* grp;   // base - b: the column of the group's body 0
+    __device__ __forceinline__ double getk(int k, int slot) const { return grp[k + slot * PB_BLOCK]; }
     __device__ __forceinline__ double get(int slot) const { return base[slot * PB_BLOCK]; }
     __device__ __forceinline__ void set(int slot, double v) const { base[slot * PB_BLOCK] = v; }
     __device__ __forceinline__ V3 get3(int slot) const { return v3(get(slot), get(slot + 1), get(slot + 2)); }
     __device__ __forceinline__ void set3(int slot, V3 v) const { set(slot, v.x); set(slot + 1, v.y); set(slot + 2, v.z); }
+    __device__ __forceinline__ V3 getk3(int k, int slot) const { return v3(getk(k, slot), getk(k, slot + 1), getk(k, slot + 2)); }
 };
+// exchange triples of the core (dead midpoint slots)
+enum : int { E_A = S_VOX, E_B = S_LOX, E_C = S_DVX, E_D = S_DLX, E_R = S_RX };
 
 // Per-lane register state.
 struct Lane {

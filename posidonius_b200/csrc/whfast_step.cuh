@@ -73,20 +73,21 @@ __device__ __forceinline__ bool evolve_lane(const KParams& P, const Roles& ro, c
 }
 
 // Running sum over the NON-HOST bodies in index order, as the reference's serial loops accumulate
-// (`particles_left.chain(particles_right)`); `x` is the lane's own term. All lanes get the same bits.
-__device__ __forceinline__ S3 ordered_sum_others(S3 init, S3 x, int gb, int n, int host) {
+// (`particles_left.chain(particles_right)`). Every lane has left its own term in the exchange triple `slot`
+// (cold.set3 + __syncwarp by the caller); all lanes get the same bits.
+__device__ __forceinline__ S3 ordered_sum_others(const Cold& cold, S3 init, int slot, int n, int host) {
     S3 acc = init;
     for (int k = 0; k < n; k++) {
         if (k == host) continue;
-        acc = acc + shfl3(x, gb + k);
+        acc = acc + strict(cold.getk3(k, slot));
     }
     return acc;
 }
-__device__ __forceinline__ S3 ordered_diff_others(S3 init, S3 x, int gb, int n, int host) {
+__device__ __forceinline__ S3 ordered_diff_others(const Cold& cold, S3 init, int slot, int n, int host) {
     S3 acc = init;
     for (int k = 0; k < n; k++) {
         if (k == host) continue;
-        acc = acc - shfl3(x, gb + k);
+        acc = acc - strict(cold.getk3(k, slot));
     }
     return acc;
 }
@@ -100,15 +101,17 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
     const int W = PB_W(P);
     const sd dt = sd(P.half_dt);
     // positions do not change inside the midpoint: heliocentric position and 1/r once (universe.rs:318-351)
-    const S3 rh_s = shfl3(q.r, hl);
+    __syncwarp();   // the core's last exchange reads are done before these slots are rewritten
+    cold.set3(S_RX, plain(q.r));
+    cold.set3(S_VOX, plain(q.v)); cold.set3(S_LOX, q.L);
+    cold.set3(S_DVX, v3(0., 0., 0.)); cold.set3(S_DLX, v3(0., 0., 0.));
+    __syncwarp();
+    const S3 rh_s = strict(cold.getk3(PB_HOST(P), S_RX));
     // idle lanes (host slot, padding) get a unit dummy so that rsqrt/div stay on their fast paths for the whole warp
     const S3 hr_s = ro.planet ? q.r - rh_s : s3(sd(1.), sd(0.), sd(0.));
     const V3 hr = plain(hr_s);
     const double inv_d = ARITH ? 0. : rsqrt(dot(hr, hr));
     const sd dist_s = ARITH ? ssqrt(hr_s.x * hr_s.x + hr_s.y * hr_s.y + hr_s.z * hr_s.z) : sd(1.);   // universe.rs:328-330
-    cold.set3(S_RX, plain(q.r));
-    cold.set3(S_VOX, plain(q.v)); cold.set3(S_LOX, q.L);
-    cold.set3(S_DVX, v3(0., 0., 0.)); cold.set3(S_DLX, v3(0., 0., 0.));
     bool done = !alive;  // group-uniform
     bool converged = false;
 #pragma unroll 1
@@ -211,10 +214,10 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const C
 #pragma unroll 1
 #endif
     for (int j = 0; j < n; j++) {
-        S3 rj = shfl3(q.r, gb + j);
-        sd mj = sd(shfl(q_m, gb + j));
-        double Rj = shfl(q_R, gb + j);
         if (j == b || !ro.valid) continue;
+        const S3 rj = strict(cold.getk3(j, E_R));   // published by the caller
+        const sd mj = sd(cold.getk(j, K_M));
+        const double Rj = cold.getk(j, K_R);
         S3 d = q.r - rj;
         sd d2 = d.x * d.x + d.y * d.y + d.z * d.z;
         if (b < j) {
@@ -270,6 +273,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
     ro.g_on = ro.planet && ((P.gr_orbiting >> b) & 1u);
     Cold cold;
     cold.base = pb_smem + threadIdx.x;
+    cold.grp = cold.base - b;
 
     Lane q;
     SysState st;
@@ -305,9 +309,10 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
 
     // constants of the transforms, all strict and in the reference's order; parked in the cold slots
     {
+        __syncwarp();
         const sd m_s = sd(cold.get(K_M)), mg_s = sd(cold.get(K_MG));
-        const sd M_s = sd(shfl(m_s.v, hl));       // m0
-        const sd Mg_s = sd(shfl(mg_s.v, hl));
+        const sd M_s = sd(cold.getk(PB_HOST(P), K_M));       // m0
+        const sd Mg_s = sd(cold.getk(PB_HOST(P), K_MG));
         // total mass as inertial_to_*_posvel accumulate it: host first, then the others in index order
         sd mtot = M_s;
         sd eta_k = sd(0.), mu_k = sd(0.);        // Jacobi: cumulative mass / mass_g up to and including this body
@@ -315,8 +320,8 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
         if (COORD != PB200_COORD_JACOBI) mtot = sd(0.) + M_s;
         for (int k = 0; k < n; k++) {
             if (k == PB_HOST(P)) continue;
-            mtot = mtot + sd(shfl(m_s.v, gb + k));
-            mu = mu + sd(shfl(mg_s.v, gb + k));
+            mtot = mtot + sd(cold.getk(k, K_M));
+            mu = mu + sd(cold.getk(k, K_MG));
             if (k == b) { eta_k = mtot; mu_k = mu; }
         }
         // per-body constants of the heliocentric transforms (whfast.rs:1015, 1101, 1112-1114), divided once
@@ -412,14 +417,17 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                 S3 anew_s = zero3;
                 const bool kwork = ro.planet && alive;
                 // ---- inertial -> alternative coordinates (whfast.rs:881-1023)
+                __syncwarp();   // the midpoint's reads of its slots are done: they become exchange space
                 if (COORD == PB200_COORD_JACOBI) {
+                    cold.set3(E_R, plain(q.r)); cold.set3(E_A, plain(q.v));
+                    __syncwarp();
                     sd eta = M_s;
-                    S3 s = eta * shfl3(q.r, hl), sv = eta * shfl3(q.v, hl);
+                    S3 s = eta * strict(cold.getk3(PB_HOST(P), E_R)), sv = eta * strict(cold.getk3(PB_HOST(P), E_A));
                     apos = one3; avel = zero3;
                     for (int k = 0; k < n; k++) {
                         if (k == PB_HOST(P)) continue;
-                        sd mk = sd(shfl(m_s.v, gb + k));
-                        S3 rk = shfl3(q.r, gb + k), vk = shfl3(q.v, gb + k);
+                        sd mk = sd(cold.getk(k, K_M));
+                        S3 rk = strict(cold.getk3(k, E_R)), vk = strict(cold.getk3(k, E_A));
                         sd ei = one / eta;
                         eta = eta + mk;
                         sd pme = eta * ei;
@@ -432,10 +440,12 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                 } else {
                     // host first, then the others (whfast.rs:986-995)
                     S3 mr = q.r * m_s, mv = q.v * m_s;
-                    S3 sr = ordered_sum_others(zero3 + shfl3(mr, hl), mr, gb, n, PB_HOST(P));
-                    S3 sv = ordered_sum_others(zero3 + shfl3(mv, hl), mv, gb, n, PB_HOST(P));
+                    cold.set3(E_A, plain(mr)); cold.set3(E_B, plain(mv)); cold.set3(E_R, plain(q.r));
+                    __syncwarp();
+                    S3 sr = ordered_sum_others(cold, zero3 + strict(cold.getk3(PB_HOST(P), E_A)), E_A, n, PB_HOST(P));
+                    S3 sv = ordered_sum_others(cold, zero3 + strict(cold.getk3(PB_HOST(P), E_B)), E_B, n, PB_HOST(P));
                     spos = sr / rT; svel = sv / rT;
-                    apos = q.r - shfl3(q.r, hl);
+                    apos = q.r - strict(cold.getk3(PB_HOST(P), E_R));
                     avel = q.v - svel;
                     if (COORD == PB200_COORD_WHDS) avel = avel * sd(cold.get(K_WHDSF));
                 }
@@ -445,13 +455,15 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         // ---- kick (whfast.rs:558-625)
                         if (COORD == PB200_COORD_JACOBI) {
                             // inertial_to_jacobi_acc (whfast.rs:935-963) + jacobi_interaction_step (:566-592)
+                            cold.set3(E_B, plain(anew_s));
+                            __syncwarp();
                             sd eta = M_s;
-                            S3 sa = eta * shfl3(anew_s, hl);
+                            S3 sa = eta * strict(cold.getk3(PB_HOST(P), E_B));
                             S3 aacc = zero3;
                             for (int k = 0; k < n; k++) {
                                 if (k == PB_HOST(P)) continue;
-                                sd mk = sd(shfl(m_s.v, gb + k));
-                                S3 ak = shfl3(anew_s, gb + k);
+                                sd mk = sd(cold.getk(k, K_M));
+                                S3 ak = strict(cold.getk3(k, E_B));
                                 sd ei = one / eta;
                                 eta = eta + mk;
                                 sd pme = eta * ei;
@@ -482,25 +494,31 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         }
                         if (COORD != PB200_COORD_JACOBI && jump_slot != phase) {
                             if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
-                                S3 p = ordered_sum_others(zero3, m_s * avel, gb, n, PB_HOST(P));
+                                cold.set3(E_C, plain(m_s * avel));
+                                __syncwarp();
+                                S3 p = ordered_sum_others(cold, zero3, E_C, n, PB_HOST(P));
                                 apos = s3(apos.x + hdt_s * p.x / rM, apos.y + hdt_s * p.y / rM, apos.z + hdt_s * p.z / rM);
                             } else {
                                 sd f = M_s + m_s;
                                 S3 term = s3(m_s * avel.x / f, m_s * avel.y / f, m_s * avel.z / f);
-                                S3 p = ordered_sum_others(zero3, term, gb, n, PB_HOST(P));
+                                cold.set3(E_C, plain(term));
+                                __syncwarp();
+                                S3 p = ordered_sum_others(cold, zero3, E_C, n, PB_HOST(P));
                                 apos = s3(apos.x + hdt_s * (p.x - term.x), apos.y + hdt_s * (p.y - term.y), apos.z + hdt_s * (p.z - term.z));
                             }
                         }
                     }
                     // ---- alternative -> inertial (whfast.rs:1026-1155)
                     if (COORD == PB200_COORD_JACOBI) {
+                        cold.set3(E_D, plain(apos)); cold.set3(E_C, plain(avel));
+                        __syncwarp();
                         sd et = mtot;
                         S3 s = et * spos, sv = et * svel;
                         S3 nr = q.r, nv = q.v;
                         for (int k = n - 1; k >= 0; k--) {
                             if (k == PB_HOST(P)) continue;
-                            sd mk = sd(shfl(m_s.v, gb + k));
-                            S3 pk = shfl3(apos, gb + k), wk = shfl3(avel, gb + k);
+                            sd mk = sd(cold.getk(k, K_M));
+                            S3 pk = strict(cold.getk3(k, E_D)), wk = strict(cold.getk3(k, E_C));
                             sd ei = one / et;
                             s = (s - mk * pk) * ei; sv = (sv - mk * wk) * ei;
                             if (b == k) { nr = pk + s; nv = wk + sv; }
@@ -513,13 +531,17 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         // positions (whfast.rs:1128-1155); the host lane divides a dummy instead of its zero vector
                         S3 num = ro.planet ? apos * m_s : one3;
                         S3 term = num / rT;
-                        S3 star_r = ordered_diff_others(spos, term, gb, n, PB_HOST(P));
+                        const S3 vterm = avel * sd(cold.get(K_BACKW));
+                        cold.set3(E_D, plain(term));
+                        if (phase == 1) cold.set3(E_A, plain(vterm));
+                        __syncwarp();
+                        S3 star_r = ordered_diff_others(cold, spos, E_D, n, PB_HOST(P));
                         S3 nr = ro.host ? star_r : apos + star_r;
                         if (alive) q.r = nr;
                         if (phase == 1) {
                             // velocities (whfast.rs:1090-1126); those of the first drift are dead (the kick overwrites them)
                             S3 nv = (COORD == PB200_COORD_WHDS ? avel / sd(cold.get(K_WHDSF)) : avel) + svel;
-                            S3 star_v = ordered_diff_others(svel, avel * sd(cold.get(K_BACKW)), gb, n, PB_HOST(P));
+                            S3 star_v = ordered_diff_others(cold, svel, E_A, n, PB_HOST(P));
                             if (ro.host) nv = star_v;
                             if (alive) q.v = nv;
                         }
@@ -527,6 +549,8 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     if (phase == 0) {
                         // ---- gravity (whfast.rs:281)
                         int fail;
+                        cold.set3(E_R, plain(q.r));
+                        __syncwarp();
                         anew_s = gravity<COORD>(P, ro, cold, gb, b, sys, q, fail);
                         // group-wide failure: lowest body index wins, like the reference's loop order
                         int code = (ro.valid && fail) ? ((b << 4) | fail) : 0x7fffffff;
