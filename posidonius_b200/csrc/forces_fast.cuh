@@ -70,7 +70,7 @@ __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, c
 template <int GR>
 __device__ __forceinline__ void additional_effects(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys,
                                                    double t, bool evolve_now, Lane& q, V3 hr, double inv_d, V3 hv, V3& a_out,
-                                                   V3& dl_out, double* tide_save) {
+                                                   V3& dl_out, bool tide_save) {
     const int W = PB_W(P);
     // Q3: r.omega uses the spins of the previous evaluation (universe.rs:429-430)
     V3 s_host_prev = shfl3(q.s, hl);
@@ -82,7 +82,7 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     double wh2 = shfl(w2, hl);
 #if !PB_FIXED_N
     // lag angle of the dynamical-tide models, once per step like the other evolving quantities (evolution.rs:548-567)
-    if (evolve_now && (P.flags & FLAG_DYN) && (P.flags & FLAG_EVO)) { update_lag_angle(P, ro, b, sys, t, sd(w2), true); __syncwarp(); }
+    if (evolve_now && (PB_FLAGS(P) & FLAG_DYN) && (PB_FLAGS(P) & FLAG_EVO)) { update_lag_angle(P, ro, b, sys, t, sd(w2), true); __syncwarp(); }
 #endif
     double inv_d2 = inv_d * inv_d;
     double d = dot(hr, hr) * inv_d;
@@ -91,14 +91,14 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     V3 a_p = v3(0., 0., 0.), dl_p = v3(0., 0., 0.);       // this body's own acceleration / torque
     V3 a_h = v3(0., 0., 0.), dl_h = v3(0., 0., 0.);       // contribution to the host
     const double inv_m = cold.get(C_INVM), inv_M = cold.get(C_INVMH);
-    if (P.flags & FLAG_TIDES) {
+    if (PB_FLAGS(P) & FLAG_TIDES) {
         // constant_time_lag.rs:206-332, tides/common.rs:223-345
         double inv_d4 = inv_d2 * inv_d2;
         double inv_d7 = inv_d4 * inv_d2 * inv_d;
         double Fos = cold.get(C_AS) * inv_d7;
         double Fop = cold.get(C_AP) * inv_d7;
 #if !PB_FIXED_N
-        if (P.flags & FLAG_DYN) {
+        if (PB_FLAGS(P) & FLAG_DYN) {
             sd sig_h, sig_p;
             pair_dependent_sigmas(P, ro, cold, hl, b, sys, strict(hr), strict(hv), sd(w2), sd(wh2), sig_h, sig_p);
             Fos = cold.get(D_0) * sig_h.v * inv_d7;
@@ -122,16 +122,20 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         a_h = (-inv_M) * F;
         dl_p = v3(-Np.x, -Np.y, -Np.z);
         dl_h = v3(-Ns.x, -Ns.y, -Ns.z);
-        if (tide_save) {
-            // internals that calculate_denergy_dt (tides/common.rs:263-279) will read at the next snapshot
-            tide_save[0] = hr.x; tide_save[1] = hr.y; tide_save[2] = hr.z;
-            tide_save[3] = hv.x; tide_save[4] = hv.y; tide_save[5] = hv.z;
-            tide_save[6] = d; tide_save[7] = radvel; tide_save[8] = Fop;
-            tide_save[9] = -3.0 * Fop * radvel * inv_d;  // dissipative radial part with the star as a point mass
-            tide_save[10] = -Np.x; tide_save[11] = -Np.y; tide_save[12] = -Np.z;
+        if (tide_save && ro.valid) {
+            // internals that calculate_denergy_dt (tides/common.rs:263-279) will read at the next snapshot; warp-uniform
+            // branch, taken on the last step before a snapshot or the end of a launch only
+            const size_t ns = (size_t)P.n_sys;
+            double* ts = P.tide_scratch + (size_t)b * ns + sys;
+            const size_t cs = (size_t)PB_N(P) * ns;
+            ts[0 * cs] = hr.x; ts[1 * cs] = hr.y; ts[2 * cs] = hr.z;
+            ts[3 * cs] = hv.x; ts[4 * cs] = hv.y; ts[5 * cs] = hv.z;
+            ts[6 * cs] = d; ts[7 * cs] = radvel; ts[8 * cs] = Fop;
+            ts[9 * cs] = -3.0 * Fop * radvel * inv_d;  // dissipative radial part with the star as a point mass
+            ts[10 * cs] = -Np.x; ts[11 * cs] = -Np.y; ts[12 * cs] = -Np.z;
         }
     }
-    if (P.flags & FLAG_FLAT) {
+    if (PB_FLAGS(P) & FLAG_FLAT) {
         // oblate_spheroid.rs:12-97, rotational_flattening/common.rs:165-237
         double inv_d5 = inv_d2 * inv_d2 * inv_d;
         double inv_d7 = inv_d5 * inv_d2;
@@ -194,7 +198,7 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     a_out = ro.host ? a_h : a_p;
     dl_out = ro.host ? dl_h : dl_p;
 #if !PB_FIXED_N
-    if (P.flags & FLAG_WIND) dl_out = dl_out + plain(wind_dangular_momentum_dt(P, ro, cold, b, sys, strict(q.s), sd(w2)));
+    if (PB_FLAGS(P) & FLAG_WIND) dl_out = dl_out + plain(wind_dangular_momentum_dt(P, ro, cold, b, sys, strict(q.s), sd(w2)));
 #endif
 }
 

@@ -16,23 +16,28 @@
 #define PB_FIXED_N 0
 #define PB_FIXED_W 0
 #define PB_FIXED_SHIFT 0
+#define PB_FIXED_FLAGS 0
 #include "whfast_step.cuh"
 #undef PB_NS
 #undef PB_FIXED_N
 #undef PB_FIXED_W
 #undef PB_FIXED_SHIFT
+#undef PB_FIXED_FLAGS
 #define PB_NS pbn8
 #define PB_FIXED_N 8
 #define PB_FIXED_W 8
 #define PB_FIXED_SHIFT 3
+#define PB_FIXED_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
 #include "whfast_step.cuh"
 #undef PB_NS
 #undef PB_FIXED_N
 #undef PB_FIXED_W
 #undef PB_FIXED_SHIFT
+#undef PB_FIXED_FLAGS
 #define PB_FIXED_N 0
 #define PB_FIXED_W 0
 #define PB_FIXED_SHIFT 0
+#define PB_FIXED_FLAGS 0
 
 using namespace pb200;
 
@@ -639,7 +644,8 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
     {
         cudaError_t err;
         const bool n8 = e->n_bodies == 8 && e->P.host == 0 && e->coord == PB200_COORD_DEMOCRATIC_HELIOCENTRIC &&
-                        e->gr == PB200_GR_KIDDER1995 && e->arithmetic == PB200_ARITH_FAST && !e->force_generic;
+                        e->gr == PB200_GR_KIDDER1995 && e->P.flags == (FLAG_TIDES | FLAG_FLAT | FLAG_GR) &&
+                        e->arithmetic == PB200_ARITH_FAST && !e->force_generic;
         if (n8) err = launch_n8(e, grid, n_steps);
         else switch (e->coord) {
             case PB200_COORD_JACOBI: err = launch_gr<PB200_COORD_JACOBI>(e, grid, n_steps); break;

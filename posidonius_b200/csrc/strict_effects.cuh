@@ -71,7 +71,7 @@ __device__ __forceinline__ void put3(const Cold& cold, int slot, S3 v) { cold.se
 template <int GR>
 __device__ __forceinline__ void additional_effects_strict(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys,
                                                           double t, bool evolve_now, Lane& q, S3 hr, sd dist, S3 hv, V3& a_out,
-                                                          V3& dl_out, double* tide_save) {
+                                                          V3& dl_out, bool tide_save) {
     const int n = PB_N(P);
     const sd zero = sd(0.);
     // Q3: r.omega with the spins of the previous evaluation (tides/common.rs:155-160 = rotational_flattening/common.rs:105-110)
@@ -87,7 +87,7 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
     const S3 sh = shfl3(s, hl);
     const sd wh2 = shfl(w2, hl);
 #if !PB_FIXED_N
-    if (evolve_now && (P.flags & FLAG_DYN) && (P.flags & FLAG_EVO)) { update_lag_angle(P, ro, b, sys, t, w2, true); __syncwarp(); }
+    if (evolve_now && (PB_FLAGS(P) & FLAG_DYN) && (PB_FLAGS(P) & FLAG_EVO)) { update_lag_angle(P, ro, b, sys, t, w2, true); __syncwarp(); }
 #endif
     // inertial_to_heliocentric (universe.rs:331-338); the host's stale heliocentric velocity is zero (validated)
     const sd radvel = (hr.x * hv.x + hr.y * hv.y + hr.z * hv.z) / dist;
@@ -98,10 +98,10 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
     S3 t_acc = s3(zero, zero, zero), t_dl = t_acc, f_acc = t_acc, f_dl = t_acc, g_acc = t_acc, g_dl = t_acc;
     // terms for the host, exchanged through shared memory: X_0.. = tides F, tides -N_s, flattening F, flattening -N_s
     S3 xF_t = t_acc, xN_t = t_acc, xF_f = t_acc, xN_f = t_acc;
-    if (P.flags & FLAG_TIDES) {
+    if (PB_FLAGS(P) & FLAG_TIDES) {
         sd cs = sd(cold.get(Z_CS)), cp = sd(cold.get(Z_CP)), t1 = sd(cold.get(Z_T1)), t2 = sd(cold.get(Z_T2));
 #if !PB_FIXED_N
-        if (P.flags & FLAG_DYN) {
+        if (PB_FLAGS(P) & FLAG_DYN) {
             // sigma is the last factor of each product in the reference, so multiplying it in here rounds identically
             sd sig_h, sig_p;
             pair_dependent_sigmas(P, ro, cold, hl, b, sys, hr, hv, w2, wh2, sig_h, sig_p);
@@ -138,14 +138,17 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
             xF_t = F;
             xN_t = s3(sd(-1.0) * Ns.x, sd(-1.0) * Ns.y, sd(-1.0) * Ns.z);
         }
-        if (tide_save) {
-            tide_save[0] = hr.x.v; tide_save[1] = hr.y.v; tide_save[2] = hr.z.v;
-            tide_save[3] = hv.x.v; tide_save[4] = hv.y.v; tide_save[5] = hv.z.v;
-            tide_save[6] = dist.v; tide_save[7] = radvel.v; tide_save[8] = orth_p.v; tide_save[9] = diss_pm.v;
-            tide_save[10] = t_dl.x.v; tide_save[11] = t_dl.y.v; tide_save[12] = t_dl.z.v;
+        if (tide_save && ro.valid) {
+            const size_t ns = (size_t)P.n_sys;
+            double* ts = P.tide_scratch + (size_t)b * ns + sys;
+            const size_t cs = (size_t)PB_N(P) * ns;
+            ts[0 * cs] = hr.x.v; ts[1 * cs] = hr.y.v; ts[2 * cs] = hr.z.v;
+            ts[3 * cs] = hv.x.v; ts[4 * cs] = hv.y.v; ts[5 * cs] = hv.z.v;
+            ts[6 * cs] = dist.v; ts[7 * cs] = radvel.v; ts[8 * cs] = orth_p.v; ts[9 * cs] = diss_pm.v;
+            ts[10 * cs] = t_dl.x.v; ts[11 * cs] = t_dl.y.v; ts[12 * cs] = t_dl.z.v;
         }
     }
-    if (P.flags & FLAG_FLAT) {
+    if (PB_FLAGS(P) & FLAG_FLAT) {
         const sd Rh5 = sd(cold.get(Z_RH5)), R5 = sd(cold.get(Z_R5));
         const sd ffs = P.flat_host_central ? sd(cold.get(Z_FS0)) * wh2 * Rh5 / sd(6.) : zero * wh2 * Rh5 / sd(6.);
         const sd orth_s = sd(-6.) * ffs * rs_s / (wh2 * d5);
@@ -168,7 +171,7 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
     }
     // ---- exchange round A: host sums of tides / flattening
     S3 h_t_acc = t_acc, h_t_dl = t_acc, h_f_acc = t_acc, h_f_dl = t_acc;
-    if (P.flags & (FLAG_TIDES | FLAG_FLAT)) {
+    if (PB_FLAGS(P) & (FLAG_TIDES | FLAG_FLAT)) {
         put3(cold, X_0, xF_t); put3(cold, X_0 + 3, xN_t); put3(cold, X_0 + 6, xF_f); put3(cold, X_0 + 9, xN_f);
         __syncwarp();
         if (ro.host) {
@@ -269,12 +272,12 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
     const S3 ta = ro.host ? h_t_acc : t_acc, fa_ = ro.host ? h_f_acc : f_acc, ga = ro.host ? h_g_acc : g_acc;
     const S3 td = ro.host ? h_t_dl : t_dl, fd = ro.host ? h_f_dl : f_dl, gd = ro.host ? h_g_dl : g_dl;
     S3 a = s3(zero, zero, zero);
-    if (P.flags & FLAG_TIDES) a = a + ta;
-    if (P.flags & FLAG_FLAT) a = a + fa_;
-    if (P.flags & FLAG_GR) a = a + ga;
+    if (PB_FLAGS(P) & FLAG_TIDES) a = a + ta;
+    if (PB_FLAGS(P) & FLAG_FLAT) a = a + fa_;
+    if (PB_FLAGS(P) & FLAG_GR) a = a + ga;
     S3 wd = s3(zero, zero, zero);
 #if !PB_FIXED_N
-    if (P.flags & FLAG_WIND) wd = wind_dangular_momentum_dt(P, ro, cold, b, sys, s, w2);
+    if (PB_FLAGS(P) & FLAG_WIND) wd = wind_dangular_momentum_dt(P, ro, cold, b, sys, s, w2);
 #endif
     S3 dl = s3(td.x + fd.x + gd.x + wd.x, td.y + fd.y + gd.y + wd.y, td.z + fd.z + gd.z + wd.z);
     if (!ro.valid) { a = s3(zero, zero, zero); dl = a; }

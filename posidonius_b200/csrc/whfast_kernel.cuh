@@ -112,6 +112,9 @@ struct KParams {
 #define PB_HOST(P) (PB_FIXED_N ? 0 : (P).host)
 #define PB_W(P) (PB_FIXED_N ? PB_FIXED_W : (P).W)
 #define PB_SHIFT(P) (PB_FIXED_N ? PB_FIXED_SHIFT : (P).shift)
+// the fixed-geometry build also fixes the effect set (tides + flattening + GR, no evolution: the TRAPPIST-1 case)
+#define PB_FLAGS(P) (PB_FIXED_N ? PB_FIXED_FLAGS : (P).flags)
+#define PB_SPIN(P) (PB_FIXED_N ? 1 : (P).spin_on)
 
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
 __device__ __forceinline__ double shfl_xor(double v, int m) { return __shfl_xor_sync(FULL, v, m); }
@@ -135,16 +138,21 @@ __device__ __forceinline__ V3 sel(bool c, V3 a, V3 b) { return v3(c ? a.x : b.x,
 
 // ---------------------------------------------------------------------------------------------
 // Stumpff functions c0..c3 (whfast.rs:844-876) and Stiefel G-functions (whfast.rs:835-842), strict arithmetic
+// 1/13!, 1/12!, ..., 1/2! for the series below. Deliberately NOT const: as constant-bank operands the coefficients cost
+// nothing (DADD R, -R, c[3][..]); as literals each one is materialised by two UMOVs before every use.
+__constant__ double kInvFactorial[12] = {1. / 6227020800., 1. / 479001600., 1. / 39916800., 1. / 3628800., 1. / 362880., 1. / 40320.,
+                                         1. / 5040., 1. / 720., 1. / 120., 1. / 24., 1. / 6., 1. / 2.};
 __device__ __forceinline__ void stumpff_cs3(sd z, sd& c0, sd& c1, sd& c2, sd& c3) {
     int n = 0;
     while (fabs(z.v) > 0.1) { z = z * sd(0.25); n++; }   // z / 4 (exact scaling, same value)
-    sd c_odd = sd(1. / 6227020800.);   // 1/13!
-    sd c_even = sd(1. / 479001600.);   // 1/12!
-    c_odd = sd(1. / 39916800.) - z * c_odd;   c_even = sd(1. / 3628800.) - z * c_even;  // 11!, 10!
-    c_odd = sd(1. / 362880.) - z * c_odd;     c_even = sd(1. / 40320.) - z * c_even;    // 9!, 8!
-    c_odd = sd(1. / 5040.) - z * c_odd;       c_even = sd(1. / 720.) - z * c_even;      // 7!, 6!
-    c_odd = sd(1. / 120.) - z * c_odd;        c_even = sd(1. / 24.) - z * c_even;       // 5!, 4!
-    c_odd = sd(1. / 6.) - z * c_odd;          c_even = sd(1. / 2.) - z * c_even;        // 3!, 2!
+    const double* F = kInvFactorial;
+    sd c_odd = sd(F[0]);    // 1/13!
+    sd c_even = sd(F[1]);   // 1/12!
+    c_odd = sd(F[2]) - z * c_odd;    c_even = sd(F[3]) - z * c_even;   // 11!, 10!
+    c_odd = sd(F[4]) - z * c_odd;    c_even = sd(F[5]) - z * c_even;   // 9!, 8!
+    c_odd = sd(F[6]) - z * c_odd;    c_even = sd(F[7]) - z * c_even;   // 7!, 6!
+    c_odd = sd(F[8]) - z * c_odd;    c_even = sd(F[9]) - z * c_even;   // 5!, 4!
+    c_odd = sd(F[10]) - z * c_odd;   c_even = sd(F[11]) - z * c_even;  // 3!, 2!
     c3 = c_odd; c2 = c_even;
     c1 = sd(1.) - z * c_odd;
     c0 = sd(1.) - z * c_even;

@@ -117,7 +117,7 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
 #pragma unroll 1
     for (int it = 0; it < 10; it++) {
         if (!__any_sync(FULL, !done)) break;
-        if (evolution && it == 0 && (P.flags & FLAG_EVO)) {
+        if (evolution && it == 0 && (PB_FLAGS(P) & FLAG_EVO)) {
             // once per step in evolving configurations: re-derive the constants unconditionally (warp-uniform control flow
             // around the shuffles inside make_consts*)
             (void)evolve_lane(P, ro, cold, b, sys, t, alive);
@@ -128,17 +128,14 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
         const S3 hv_s = ro.planet ? q.v - vh_s : s3(sd(0.), sd(1.), sd(0.));
         V3 hv = plain(hv_s);
         V3 a, dldt;
-        double scratch[PB_TIDE_SCRATCH];
+        // the tidal internals of a step's last evaluation are kept for the next snapshot's denergy_dt (`!done`: a converged
+        // system's later evaluations are discarded)
+        const bool save_now = save_tides && !done;
         const bool evolve_now = evolution && it == 0;
-        if (ARITH) additional_effects_strict<GR>(P, ro, cold, hl, b, sys, t, evolve_now, q, hr_s, dist_s, hv_s, a, dldt, save_tides ? scratch : nullptr);
-        else additional_effects<GR>(P, ro, cold, hl, b, sys, t, evolve_now, q, hr, inv_d, hv, a, dldt, save_tides ? scratch : nullptr);
-        if (save_tides && (P.flags & FLAG_TIDES) && ro.valid && !done) {
-            const size_t ns = (size_t)P.n_sys;
-            const size_t i = (size_t)b * ns + sys, cs = (size_t)PB_N(P) * ns;
-            for (int k = 0; k < PB_TIDE_SCRATCH; k++) P.tide_scratch[i + k * cs] = scratch[k];
-        }
+        if (ARITH) additional_effects_strict<GR>(P, ro, cold, hl, b, sys, t, evolve_now, q, hr_s, dist_s, hv_s, a, dldt, save_now);
+        else additional_effects<GR>(P, ro, cold, hl, b, sys, t, evolve_now, q, hr, inv_d, hv, a, dldt, save_now);
         if (GR == PB200_GR_ANDERSON1975 || GR == PB200_GR_NEWHALL1983) {
-            if (P.flags & FLAG_GR) {
+            if (PB_FLAGS(P) & FLAG_GR) {
                 V3 ag;
                 Lane qq = q;
                 qq.r = strict(cold.get3(S_RX));
@@ -158,7 +155,7 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
         S3 ndv = s3(dt * sd(a.x) - sd(ev.x), dt * sd(a.y) - sd(ev.y), dt * sd(a.z) - sd(ev.z));
         V3 ndl = v3((dt * sd(dldt.x) - sd(el.x)).v, (dt * sd(dldt.y) - sd(el.y)).v, (dt * sd(dldt.z) - sd(el.z)).v);
         S3 vf = vo + ndv;
-        V3 Lf = P.spin_on ? v3(__dadd_rn(Lo.x, ndl.x), __dadd_rn(Lo.y, ndl.y), __dadd_rn(Lo.z, ndl.z)) : Lo;
+        V3 Lf = PB_SPIN(P) ? v3(__dadd_rn(Lo.x, ndl.x), __dadd_rn(Lo.y, ndl.y), __dadd_rn(Lo.z, ndl.z)) : Lo;
         bool conv_now = false;
         if (it >= 2) {
             // whfast.rs:424-451 (sums over bodies by butterfly: only the branch decision depends on them)
@@ -168,7 +165,7 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
             // delta/total < eps^2 decided as delta < eps^2 * total (no division; NaN compares false either way)
             bool okv = s_dv < kEps2 * s_fv;
             bool okl = true;
-            if (P.spin_on) {
+            if (PB_SPIN(P)) {
                 double s_dl = ro.valid ? dot(ddl, ddl) : 0., s_fl = ro.valid ? dot(Lf, Lf) : 0.;
                 s_dl = group_sum(s_dl, W); s_fl = group_sum(s_fl, W);
                 okl = s_dl < kEps2 * s_fl;
@@ -176,12 +173,12 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
             conv_now = okv && okl;
         }
         if (!done) {
-            cold.set3(S_DVX, plain(ndv)); if (P.spin_on) cold.set3(S_DLX, ndl);
+            cold.set3(S_DVX, plain(ndv)); if (PB_SPIN(P)) cold.set3(S_DLX, ndl);
             if (conv_now) { done = true; converged = true; }
             else {
                 // average (whfast.rs:453-466)
                 q.v = s3(sd(0.5) * (vo.x + vf.x), sd(0.5) * (vo.y + vf.y), sd(0.5) * (vo.z + vf.z));
-                if (P.spin_on) q.L = v3(__dmul_rn(0.5, __dadd_rn(Lo.x, Lf.x)), __dmul_rn(0.5, __dadd_rn(Lo.y, Lf.y)), __dmul_rn(0.5, __dadd_rn(Lo.z, Lf.z)));
+                if (PB_SPIN(P)) q.L = v3(__dmul_rn(0.5, __dadd_rn(Lo.x, Lf.x)), __dmul_rn(0.5, __dadd_rn(Lo.y, Lf.y)), __dmul_rn(0.5, __dadd_rn(Lo.z, Lf.z)));
             }
         }
     }
@@ -191,7 +188,7 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
         const S3 vo = strict(cold.get3(S_VOX)), dv = strict(cold.get3(S_DVX));
         q.v = vo + dv;
         cold.set3(S_EVX, plain((q.v - vo) - dv));
-        if (P.spin_on) {
+        if (PB_SPIN(P)) {
             const V3 Lo = cold.get3(S_LOX), dl = cold.get3(S_DLX);
             q.L = v3(__dadd_rn(Lo.x, dl.x), __dadd_rn(Lo.y, dl.y), __dadd_rn(Lo.z, dl.z));
             cold.set3(S_ELX, v3(__dsub_rn(__dsub_rn(q.L.x, Lo.x), dl.x), __dsub_rn(__dsub_rn(q.L.y, Lo.y), dl.y), __dsub_rn(__dsub_rn(q.L.z, Lo.z), dl.z)));
@@ -354,14 +351,14 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
             bool snap = alive && (first || due);
             if (__any_sync(FULL, snap)) {
                 // refresh: evolving quantities and spin = L / I (universe.rs:305-316); it changes the live state too
-                if (P.flags & FLAG_EVO) {
+                if (PB_FLAGS(P) & FLAG_EVO) {
                     (void)evolve_lane(P, ro, cold, b, sys, st.t, snap);
                     __syncwarp();
                     if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
                 }
                 if (snap) { sd I = sd(cold.get(K_I)); q.s = v3((sd(q.L.x) / I).v, (sd(q.L.y) / I).v, (sd(q.L.z) / I).v); }   // spin = L / I (common.rs:9-11)
 #if !PB_FIXED_N
-                if ((P.flags & FLAG_DYN) && (P.flags & FLAG_EVO)) {
+                if ((PB_FLAGS(P) & FLAG_DYN) && (PB_FLAGS(P) & FLAG_EVO)) {
                     const S3 ss = strict(q.s);
                     update_lag_angle(P, ro, b, sys, st.t, (ss.x * ss.x) + (ss.y * ss.y) + (ss.z * ss.z), snap);
                 }
@@ -370,7 +367,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     const size_t ns = (size_t)P.n_sys;
                     const size_t i = (size_t)b * ns + sys, cs = (size_t)n * ns;
                     double denergy = 0.;
-                    if ((P.flags & FLAG_TIDES) && ro.t_on) {
+                    if ((PB_FLAGS(P) & FLAG_TIDES) && ro.t_on) {
                         // tides/common.rs:263-279 with the internals left by the last evaluation and the fresh spin
                         double ts[PB_TIDE_SCRATCH];
                         for (int k = 0; k < PB_TIDE_SCRATCH; k++) ts[k] = P.tide_scratch[i + k * cs];
@@ -390,7 +387,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     h[7 * cs] = q.v.x.v; h[8 * cs] = q.v.y.v; h[9 * cs] = q.v.z.v;
                     h[10 * cs] = cold.get(K_M); h[11 * cs] = cold.get(K_R); h[12 * cs] = P.rg2[i];
                     h[13 * cs] = P.k2t[i]; h[14 * cs] = P.sigma[i]; h[15 * cs] = denergy;
-                    h[16 * cs] = (P.flags & FLAG_DYN) ? P.lag[i] : 0.;
+                    h[16 * cs] = (PB_FLAGS(P) & FLAG_DYN) ? P.lag[i] : 0.;
                 }
                 if (snap) {
                     if (!first) st.last_hist = __dadd_rn(st.last_hist, P.hist_period); else st.last_hist = 0.;
