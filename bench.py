@@ -152,6 +152,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner on fd 1 when
+    # NCCL_DEBUG is set): send fd 1 to stderr for the run and keep the real stdout for the result line.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -249,7 +255,8 @@ def main():
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(case, tables)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     ens.close()
     if world > 1:
         dist.destroy_process_group()

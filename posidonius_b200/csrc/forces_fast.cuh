@@ -35,8 +35,7 @@ __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, c
 #endif
     cold.set(C_KS, gfs * (m * k2f_h * Rh5));                        // flattening: m k2f* R*^5 (oblate_spheroid.rs:37)
     cold.set(C_KP, gf * (M * k2f * R5));                            //             M k2f R^5   (oblate_spheroid.rs:42)
-    cold.set(C_IH, Ih);
-    cold.set(C_INVM, 1. / m); cold.set(C_INVMH, 1. / M); cold.set(C_MH, M);
+    cold.set(C_INVM, 1. / m);
     const double mgs = Mg + mg;
     cold.set(C_MGS, gg * mgs);                                     // gated: A = mgs / (r^2 c^2) vanishes for non-GR lanes
     cold.set(C_FA, gg * (kG * kInvC2));                            // G / c^2 of the 1.5PN terms, gated
@@ -61,6 +60,7 @@ __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, c
     cold.set(G_0 + 10, f * (15.0 + 4.0 * f));
     cold.set(G_0 + 11, 4.0 + 41.0 * f + 8.0 * f2);
     cold.set(G_0 + 12, 3.0 * f * (3.0 + 2.0 * f));
+    __syncwarp();   // the host's column (1/M, inertia) is read by the other lanes
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -73,13 +73,17 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
                                                    V3& dl_out, bool tide_save) {
     const int W = PB_W(P);
     // Q3: r.omega uses the spins of the previous evaluation (universe.rs:429-430)
-    V3 s_host_prev = shfl3(q.s, hl);
+    // (the host's spin travels through the exchange triple E_S: still the previous evaluation's here)
+    V3 s_host_prev = cold.getk3(PB_HOST(P), E_S);
     double rs_s = dot(hr, s_host_prev), rs_p = dot(hr, q.s);
     // calculate_spin (particles/common.rs:3-15)
     q.s = cold.get(C_INVI) * q.L;
     double w2 = dot(q.s, q.s);
-    V3 sh = shfl3(q.s, hl);
-    double wh2 = shfl(w2, hl);
+    __syncwarp();
+    cold.set3(E_S, q.s); cold.set(M_6, w2);
+    __syncwarp();
+    V3 sh = cold.getk3(PB_HOST(P), E_S);
+    double wh2 = cold.getk(PB_HOST(P), M_6);
 #if !PB_FIXED_N
     // lag angle of the dynamical-tide models, once per step like the other evolving quantities (evolution.rs:548-567)
     if (evolve_now && (PB_FLAGS(P) & FLAG_DYN) && (PB_FLAGS(P) & FLAG_EVO)) { update_lag_angle(P, ro, b, sys, t, sd(w2), true); __syncwarp(); }
@@ -90,7 +94,7 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     V3 rxv = cross(hr, hv);
     V3 a_p = v3(0., 0., 0.), dl_p = v3(0., 0., 0.);       // this body's own acceleration / torque
     V3 a_h = v3(0., 0., 0.), dl_h = v3(0., 0., 0.);       // contribution to the host
-    const double inv_m = cold.get(C_INVM), inv_M = cold.get(C_INVMH);
+    const double inv_m = cold.get(C_INVM), inv_M = cold.getk(PB_HOST(P), C_INVM);
     if (PB_FLAGS(P) & FLAG_TIDES) {
         // constant_time_lag.rs:206-332, tides/common.rs:223-345
         double inv_d4 = inv_d2 * inv_d2;
@@ -169,7 +173,7 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         double kr = rad * inv_d;
         V3 a = v3(kr * hr.x + orth * hv.x, kr * hr.y + orth * hv.y, kr * hr.z + orth * hv.z);
         // 1.5PN spin-orbit (:300-456); component-wise products exactly as the reference writes them
-        V3 Ls = cold.get(C_IH) * sh, Lp = cold.get(K_I) * q.s;
+        V3 Ls = cold.getk(PB_HOST(P), K_I) * sh, Lp = cold.get(K_I) * q.s;
         V3 nn = inv_d * hr;
         double md = cold.get(C_MD);
         V3 msf = v3(md * (Lp.x * inv_m - Ls.x * inv_M), md * (Lp.y * inv_m - Ls.y * inv_M), md * (Lp.z * inv_m - Ls.z * inv_M));
@@ -193,10 +197,30 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         dl_h = dl_h + fa * ds;
     }
     // lanes that are not orbiting bodies carry zero constants (make_consts): their terms vanish; reduce onto the host
-    a_h = group_sum3(a_h, W);
-    dl_h = group_sum3(dl_h, W);
-    a_out = ro.host ? a_h : a_p;
-    dl_out = ro.host ? dl_h : dl_p;
+    // Transposed reduction through the exchange columns: every lane leaves its six contributions, lane c adds component
+    // c over the group (columns visited in rotated order: conflict-free banks), the host lane collects the six totals.
+    __syncwarp();   // the totals of the previous evaluation have been read
+    cold.set3(M_0, a_h); cold.set3(M_3, dl_h);
+    __syncwarp();
+    for (int c = b; c < 6; c += W) {
+        double t;
+        if (PB_FIXED_N == 8) {
+            const double x0 = cold.getk(b, M_0 + c), x1 = cold.getk((b + 1) & 7, M_0 + c), x2 = cold.getk((b + 2) & 7, M_0 + c),
+                         x3 = cold.getk((b + 3) & 7, M_0 + c), x4 = cold.getk((b + 4) & 7, M_0 + c), x5 = cold.getk((b + 5) & 7, M_0 + c),
+                         x6 = cold.getk((b + 6) & 7, M_0 + c), x7 = cold.getk((b + 7) & 7, M_0 + c);
+            t = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+        } else {
+            t = 0.;
+            for (int j = 0; j < W; j++) t += cold.getk((j + b) & (W - 1), M_0 + c);
+        }
+        cold.set(M_0 + c, t);   // only this lane reads column b of slot M_0 + c: no hazard
+    }
+    __syncwarp();
+    a_out = a_p; dl_out = dl_p;
+    if (ro.host) {
+        a_out = v3(cold.getk(0, M_0), cold.getk(1 & (W - 1), M_1), cold.getk(2 & (W - 1), M_2));
+        dl_out = v3(cold.getk(3 & (W - 1), M_3), cold.getk(4 & (W - 1), M_4), cold.getk(5 & (W - 1), M_5));
+    }
 #if !PB_FIXED_N
     if (PB_FLAGS(P) & FLAG_WIND) dl_out = dl_out + plain(wind_dangular_momentum_dt(P, ro, cold, b, sys, strict(q.s), sd(w2)));
 #endif

@@ -10,10 +10,11 @@
 namespace PB_NS {
 using namespace pb200;
 
-// strict-mode constants overlay the fast-mode constant slots (C_INVI..C_FA, 18 slots) plus Z_0
+// strict-mode constants overlay the fast-mode constant slots (C_INVI..C_FA, 15 slots) plus Z_0; the host's 1/M, R^5 and
+// moment of inertia are read from the host's own column
 enum StrictSlot : int {
-    Z_CS = C_INVI, Z_CP, Z_KCONS, Z_T1, Z_T2, Z_INVM, Z_INVMH, Z_FS0, Z_FP0, Z_R5, Z_RH5, Z_MGS, Z_GRF, Z_MOM, Z_MFM, Z_MURED, Z_FMS,
-    Z_FMP = Z_0, Z_IH = Z_1
+    Z_CS = C_INVI, Z_CP, Z_KCONS, Z_T1, Z_T2, Z_INVM, Z_FS0, Z_FP0, Z_R5, Z_MGS, Z_GRF, Z_MOM, Z_MFM, Z_MURED, Z_FMS,
+    Z_FMP = Z_0
 };
 
 __device__ __forceinline__ sd spow5(sd x) { sd x2 = x * x; sd x4 = x2 * x2; return x * x4; }            // x * x^4
@@ -39,9 +40,9 @@ __device__ __forceinline__ void make_consts_strict(const KParams& P, const Roles
     cold.set(D_0, (sd(4.5) * m2 * Rh10).v); cold.set(D_1, (sd(4.5) * M2 * R10).v);   // the same products up to sigma
     cold.set(D_2, (m2 * Rh10).v); cold.set(D_3, (M2 * R10).v);
 #endif
-    cold.set(Z_INVM, (sd(1.) / m).v); cold.set(Z_INVMH, (sd(1.) / M).v);
+    cold.set(Z_INVM, (sd(1.) / m).v);
     cold.set(Z_FS0, (m * k2f_h).v); cold.set(Z_FP0, (M * sd(k2f)).v);   // oblate_spheroid.rs:37, 42 leading products
-    cold.set(Z_R5, R5.v); cold.set(Z_RH5, Rh5.v);
+    cold.set(Z_R5, R5.v);
     const sd mgs = Mg + mg;
     cold.set(Z_MGS, mgs.v);
     cold.set(Z_GRF, (Mg * mg / (mgs * mgs)).v);                 // general_relativity.rs:98
@@ -51,7 +52,7 @@ __device__ __forceinline__ void make_consts_strict(const KParams& P, const Roles
     cold.set(Z_MURED, ((M * m) / msum).v);                      // :383
     cold.set(Z_FMS, (sd(2.) + sd(3.) / sd(2.) * m / M).v);      // :390
     cold.set(Z_FMP, (sd(2.) + sd(3.) / sd(2.) * M / m).v);      // :419
-    cold.set(Z_IH, shfl(cold.get(K_I), hl));
+    __syncwarp();   // the host's column is read by the other lanes
 }
 
 // The host lane accumulates, in body order, the terms that the other lanes left in the exchange slots.
@@ -94,7 +95,7 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
     const sd normv2 = hv.x * hv.x + hv.y * hv.y + hv.z * hv.z;
     const sd d2 = dist * dist, d4 = d2 * d2;
     const sd d5 = dist * d4, d7 = (dist * d2) * d4, d8 = d4 * d4;   // powi as LLVM expands it
-    const sd inv_m = sd(cold.get(Z_INVM)), inv_M = sd(cold.get(Z_INVMH));
+    const sd inv_m = sd(cold.get(Z_INVM)), inv_M = sd(cold.getk(PB_HOST(P), Z_INVM));
     S3 t_acc = s3(zero, zero, zero), t_dl = t_acc, f_acc = t_acc, f_dl = t_acc, g_acc = t_acc, g_dl = t_acc;
     // terms for the host, exchanged through shared memory: X_0.. = tides F, tides -N_s, flattening F, flattening -N_s
     S3 xF_t = t_acc, xN_t = t_acc, xF_f = t_acc, xN_f = t_acc;
@@ -149,7 +150,7 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
         }
     }
     if (PB_FLAGS(P) & FLAG_FLAT) {
-        const sd Rh5 = sd(cold.get(Z_RH5)), R5 = sd(cold.get(Z_R5));
+        const sd Rh5 = sd(cold.getk(PB_HOST(P), Z_R5)), R5 = sd(cold.get(Z_R5));
         const sd ffs = P.flat_host_central ? sd(cold.get(Z_FS0)) * wh2 * Rh5 / sd(6.) : zero * wh2 * Rh5 / sd(6.);
         const sd orth_s = sd(-6.) * ffs * rs_s / (wh2 * d5);
         const sd ffp = sd(cold.get(Z_FP0)) * w2 * R5 / sd(6.);
@@ -217,8 +218,8 @@ __device__ __forceinline__ void additional_effects_strict(const KParams& P, cons
         a2.y = radial2 * hr.y / dist + orth2 * hv.y;
         a2.z = radial2 * hr.z / dist + orth2 * hv.z;
         // 1.5PN spin-orbit
-        const sd Ih = sd(cold.get(Z_IH));
-        const sd M = sd(cold.get(K_MH)), m = sd(cold.get(K_M));
+        const sd Ih = sd(cold.getk(PB_HOST(P), K_I));
+        const sd M = sd(cold.getk(PB_HOST(P), K_M)), m = sd(cold.get(K_M));
         const S3 Ls = s3(Ih * sh.x, Ih * sh.y, Ih * sh.z), Lp = s3(I * s.x, I * s.y, I * s.z);
         const S3 nn = s3(hr.x / dist, hr.y / dist, hr.z / dist);
         const sd mfm = sd(cold.get(Z_MFM));

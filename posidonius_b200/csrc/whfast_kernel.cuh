@@ -332,15 +332,22 @@ enum ColdSlot : int {
     // body parameters
     K_M, K_MG, K_R, K_I,
     // constants of the perturbation forces (every division with step-invariant operands is done once)
-    C_INVI, C_AS, C_AP, C_BK, C_KS, C_KP, C_IH, C_INVM, C_INVMH, C_MH, C_MGS, C_GRF, C_MURED, C_MD, C_MOM, C_FMS, C_FMP, C_FA,
+    // (host-body quantities — its mass, inertia, 1/M — are read from the host's own column with getk, they have no slot)
+    C_INVI, C_AS, C_AP, C_BK, C_KS, C_KP, C_INVM, C_MGS, C_GRF, C_MURED, C_MD, C_MOM, C_FMS, C_FMP, C_FA,
     // constants of the coordinate transforms (strict)
-    K_MH, K_MGH, K_MTOT, K_KMU, K_BACKW, K_WHDSF, K_ETAK,
-    K_YMH, K_YMTOT,              // refined reciprocals of the host mass and the total mass (strict.cuh, srcp)
+    // The host's columns of the last three are meaningless for the host body itself and carry the per-system values:
+    // K_ETAK <- total mass, K_BACKW <- refined reciprocal of the total mass, K_WHDSF <- refined reciprocal of the host
+    // mass (strict.cuh, srcp).
+    K_KMU, K_BACKW, K_WHDSF, K_ETAK,
     // strict arithmetic mode (strict_effects.cuh): two more constants and the 4-vector exchange buffer for the host sums
     Z_0, Z_1, X_0, X_1, X_2, X_3, X_4, X_5, X_6, X_7, X_8, X_9, X_10, X_11,
-    // dynamical tides: the sigma-free parts of the tidal constants (the pair-dependent sigma multiplies them per evaluation)
-    D_0, D_1, D_2, D_3,
+    // dynamical tides: the sigma-free parts of the tidal constants (the pair-dependent sigma multiplies them per evaluation);
+    // D_2, D_3 are used by the strict mode only
+    D_2, D_3, D_0, D_1,
+    // exchange space of the fast-mode midpoint: six contributions to the host sums / their totals, spare
+    M_0, M_1, M_2, M_3, M_4, M_5, M_6, M_7,
     N_COLD_SLOTS,
+    E_S = X_11,   // fast mode: X_11, D_2, D_3 as a triple (host spin exchange)
     // fast mode: 13 GR polynomial coefficients overlay the strict-mode slots (never live together)
     G_0 = Z_0
 };

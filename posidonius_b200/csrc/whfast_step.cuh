@@ -105,6 +105,7 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
     cold.set3(S_RX, plain(q.r));
     cold.set3(S_VOX, plain(q.v)); cold.set3(S_LOX, q.L);
     cold.set3(S_DVX, v3(0., 0., 0.)); cold.set3(S_DLX, v3(0., 0., 0.));
+    if (!ARITH) { cold.set3(M_0, plain(q.v)); cold.set3(E_S, q.s); }   // fast mode: the host's current v and last spin for the group
     __syncwarp();
     const S3 rh_s = strict(cold.getk3(PB_HOST(P), S_RX));
     // idle lanes (host slot, padding) get a unit dummy so that rsqrt/div stay on their fast paths for the whole warp
@@ -124,7 +125,7 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
             __syncwarp();
             if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
         }
-        const S3 vh_s = shfl3(q.v, hl);   // every lane takes part in the shuffle; the select comes after
+        const S3 vh_s = ARITH ? shfl3(q.v, hl) : strict(cold.getk3(PB_HOST(P), M_0));
         const S3 hv_s = ro.planet ? q.v - vh_s : s3(sd(0.), sd(1.), sd(0.));
         V3 hv = plain(hv_s);
         V3 a, dldt;
@@ -180,6 +181,12 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
                 q.v = s3(sd(0.5) * (vo.x + vf.x), sd(0.5) * (vo.y + vf.y), sd(0.5) * (vo.z + vf.z));
                 if (PB_SPIN(P)) q.L = v3(__dmul_rn(0.5, __dadd_rn(Lo.x, Lf.x)), __dmul_rn(0.5, __dadd_rn(Lo.y, Lf.y)), __dmul_rn(0.5, __dadd_rn(Lo.z, Lf.z)));
             }
+        }
+        if (!ARITH) {
+            // publish the (possibly averaged) velocity for the next evaluation; the host has collected its totals by now
+            __syncwarp();
+            cold.set3(M_0, plain(q.v));
+            __syncwarp();
         }
     }
     q.r = strict(cold.get3(S_RX));
@@ -326,9 +333,12 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
         if (COORD == PB200_COORD_WHDS) { whds_f = (M_s + m_s) / M_s; back_w = m_s / (M_s + m_s); }
         if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) back_w = m_s / M_s;
         const sd kepler_mu = COORD == PB200_COORD_JACOBI ? mu_k : (COORD == PB200_COORD_WHDS ? Mg_s + mg_s : Mg_s);
-        cold.set(K_MH, M_s.v); cold.set(K_MGH, Mg_s.v); cold.set(K_MTOT, mtot.v); cold.set(K_KMU, kepler_mu.v);
-        cold.set(K_BACKW, back_w.v); cold.set(K_WHDSF, whds_f.v); cold.set(K_ETAK, eta_k.v);
-        cold.set(K_YMH, make_rcp(M_s).y); cold.set(K_YMTOT, make_rcp(mtot).y);
+        cold.set(K_KMU, kepler_mu.v);
+        // the host's own columns of these three carry the per-system values (see ColdSlot)
+        cold.set(K_ETAK, b == PB_HOST(P) ? mtot.v : eta_k.v);
+        cold.set(K_BACKW, b == PB_HOST(P) ? make_rcp(mtot).y : back_w.v);
+        cold.set(K_WHDSF, b == PB_HOST(P) ? make_rcp(M_s).y : whds_f.v);
+        __syncwarp();
     }
     const int first_other = PB_HOST(P) == 0 ? 1 : 0;
     const sd zero = sd(0.), one = sd(1.);
@@ -404,11 +414,11 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             if (half == 1) {
-                const sd m_s = sd(cold.get(K_M)), M_s = sd(cold.get(K_MH)), mtot = sd(cold.get(K_MTOT));
+                const sd m_s = sd(cold.get(K_M)), M_s = sd(cold.getk(PB_HOST(P), K_M)), mtot = sd(cold.getk(PB_HOST(P), K_ETAK));
                 const sd dt_s = sd(P.dt), hdt_s = sd(P.half_dt);
                 // step-invariant divisors with their refined reciprocals (strict.cuh): 3 instructions per division
                 srcp rM, rT;
-                rM.b = M_s.v; rM.y = cold.get(K_YMH); rT.b = mtot.v; rT.y = cold.get(K_YMTOT);
+                rM.b = M_s.v; rM.y = cold.getk(PB_HOST(P), K_WHDSF); rT.b = mtot.v; rT.y = cold.getk(PB_HOST(P), K_BACKW);
                 S3 apos, avel;       // this body's alternative coordinates
                 S3 spos, svel;       // the host slot of the alternative coordinates (centre of mass), replicated in the group
                 S3 anew_s = zero3;
