@@ -53,7 +53,7 @@ __device__ __forceinline__ void pair_dependent_sigmas(const KParams& P, const Ro
     const bool host_dyn = (P.dyn_evo >> PB_HOST(P)) & 1u;
     const bool body_dyn = ro.t_on && ((P.dyn_evo >> b) & 1u);
     double base = 0., lag = 0., diss = 0., scale = 0., stale = __longlong_as_double(0x7ff8000000000000LL);
-    if (ro.valid) { base = P.sigma[i]; lag = P.lag[i]; diss = P.diss[i]; scale = P.diss_scale[i]; stale = P.pair_p[i]; }
+    if (ro.valid) { base = P.sigma[i]; lag = ldm(P.lag + i); diss = P.diss[i]; scale = P.diss_scale[i]; stale = ldm(P.pair_p + i); }
     const sd base_h = sd(shfl(base, hl)), lag_h = sd(shfl(lag, hl));
     // (0, 0) unless the host is TidesEffect::CentralBody (constant_time_lag.rs:33-41)
     const sd diss_h = sd(P.tides_host_central ? shfl(diss, hl) : 0.), scale_h = sd(P.tides_host_central ? shfl(scale, hl) : 0.);

@@ -206,6 +206,7 @@ struct pb200_ensemble {
     size_t records_capacity = 0;
     double recovery_snapshot_period = 0.;
     int arithmetic = PB200_ARITH_FAST;
+    int sm_count = 0;
     bool force_generic = false;   // PB200_FORCE_GENERIC=1 in the environment: bypass the 8-body specialisation (A/B tests)
     // host mirror of the ensemble clock (exact snapshot counting without a device round trip)
     bool uniform_clock = true;
@@ -230,30 +231,54 @@ static bool is_dynamical_tide_evolution(const pb200_body_t& b) {
            (b.evolution_type == PB200_EVO_LECONTECHABRIER2013 && b.evolution_parameter != 0.);
 }
 
-template <int COORD, int GR, int ARITH>
-static cudaError_t launch_one(pb200_ensemble* e, unsigned grid, unsigned long long n) {
-    // the cold slots need more than the default 48 KB of dynamic shared memory
-    static thread_local int configured_device = -1;
+// Wave quantisation: `grid` CTAs of equal length on `slots` resident CTAs leave the last wave partly empty (65536
+// TRAPPIST-1 systems = 4096 CTAs on 444 slots = 9.23 waves: 7.7 % of the GPU-time idle). Cutting every CTA's steps into k
+// consecutive pieces makes the unit of scheduling k times shorter: 36.9 waves of quarter-length CTAs lose 0.3 %.
+// Returns the number of pieces (1 = plain launch). PB200_PIECES in the environment overrides (experiments).
+static unsigned plan_pieces(unsigned grid, unsigned slots, unsigned long long n_steps) {
+    if (const char* f = getenv("PB200_PIECES")) { int k = atoi(f); if (k >= 1 && (unsigned long long)k <= n_steps) return (unsigned)k; }
+    if (slots == 0 || grid <= slots) return 1;   // everything is resident at once: pieces of a group would only serialise
+    auto eff = [&](unsigned k) { double w = (double)grid * k / slots; return w / std::ceil(w); };
+    unsigned best = 1;
+    double best_eff = eff(1);
+    for (unsigned k = 2; k <= 8; k++) {
+        if (n_steps / k < 50) break;              // keep the per-piece state hand-over through HBM negligible
+        if (eff(k) > best_eff + 0.01) { best = k; best_eff = eff(k); }
+    }
+    return best;
+}
+
+template <class K>
+static cudaError_t launch_sliced(pb200_ensemble* e, K kernel, int& configured_device, int& blocks_per_sm, unsigned grid, unsigned long long n) {
     if (configured_device != e->device) {
-        cudaError_t err = cudaFuncSetAttribute(pbgen::whfast_steps_kernel<COORD, GR, ARITH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
+        // the cold slots need more than the default 48 KB of dynamic shared memory
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
+        if (err != cudaSuccess) return err;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, PB_BLOCK, PB_SMEM_BYTES);
         if (err != cudaSuccess) return err;
         configured_device = e->device;
     }
-    pbgen::whfast_steps_kernel<COORD, GR, ARITH><<<grid, PB_BLOCK, PB_SMEM_BYTES, e->stream>>>(e->P, n);
+    e->P.n_groups = grid;
+    e->P.n_pieces = plan_pieces(grid, (unsigned)(blocks_per_sm * e->sm_count), n);
+    if (e->P.n_pieces > 1) {
+        cudaError_t err = cudaMemsetAsync(e->P.sched, 0, (size_t)(grid + 1) * sizeof(unsigned int), e->stream);
+        if (err != cudaSuccess) return err;
+    }
+    kernel<<<grid * e->P.n_pieces, PB_BLOCK, PB_SMEM_BYTES, e->stream>>>(e->P, n);
     return cudaGetLastError();
 }
 
-// 8 bodies, host at index 0, democratic heliocentric, Kidder1995, fast arithmetic: the specialised instance
+template <int COORD, int GR, int ARITH>
+static cudaError_t launch_one(pb200_ensemble* e, unsigned grid, unsigned long long n) {
+    static thread_local int configured_device = -1, blocks_per_sm = 0;
+    return launch_sliced(e, pbgen::whfast_steps_kernel<COORD, GR, ARITH>, configured_device, blocks_per_sm, grid, n);
+}
+
+// 8 bodies, host at index 0, democratic heliocentric, tides + flattening + Kidder1995, fast arithmetic: the specialised instance
 static cudaError_t launch_n8(pb200_ensemble* e, unsigned grid, unsigned long long n) {
-    static thread_local int configured_device = -1;
-    auto kernel = pbn8::whfast_steps_kernel<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995, 0>;
-    if (configured_device != e->device) {
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
-        if (err != cudaSuccess) return err;
-        configured_device = e->device;
-    }
-    kernel<<<grid, PB_BLOCK, PB_SMEM_BYTES, e->stream>>>(e->P, n);
-    return cudaGetLastError();
+    static thread_local int configured_device = -1, blocks_per_sm = 0;
+    return launch_sliced(e, pbn8::whfast_steps_kernel<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995, 0>, configured_device,
+                         blocks_per_sm, grid, n);
 }
 
 template <int COORD>
@@ -395,6 +420,7 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     e->recovery_snapshot_period = c0.recovery_snapshot_period;
     e->clock_t = c0.current_time; e->clock_last_hist = c0.last_historic_snapshot_time;
     { const char* fg = getenv("PB200_FORCE_GENERIC"); e->force_generic = fg && fg[0] == '1'; }
+    if (cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) e->sm_count = 0;
     for (size_t s = 1; s < n_cases; s++)
         if (cases[s].current_time != c0.current_time || cases[s].last_historic_snapshot_time != c0.last_historic_snapshot_time) e->uniform_clock = false;
     KParams& P = e->P;
@@ -473,6 +499,8 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     TRY(dev_alloc(e, &P.hist_count, ns));
     TRY(dev_alloc(e, &P.tide_scratch, (size_t)PB_TIDE_SCRATCH * nb * ns));
     TRY(dev_alloc(e, &e->d_energy, ns)); TRY(dev_alloc(e, &e->d_angmom, ns));
+    TRY(dev_alloc(e, &P.sched, (ns * (size_t)P.W + PB_BLOCK - 1) / PB_BLOCK + 1));
+    P.n_groups = 0; P.n_pieces = 1;
     if (P.flags & FLAG_WIND) { TRY(dev_alloc(e, &e->d_wind_k, nb * ns)); TRY(dev_alloc(e, &e->d_wind_sat, nb * ns)); }
     if (P.flags & FLAG_DYN) {
         TRY(dev_alloc(e, &e->d_diss, nb * ns)); TRY(dev_alloc(e, &e->d_diss_scale, nb * ns)); TRY(dev_alloc(e, &P.lag, nb * ns));

@@ -101,7 +101,15 @@ struct KParams {
     const double *diss, *diss_scale;        // [b][s] ConstantTimeLagParameters.dissipation_factor(_scale)
     double* lag;                            // [b][s] tides.parameters.internal.lag_angle (evolution.rs:548-567)
     double *pair_h, *pair_p;                // [b][s] map entries (host, b) and (b, host); NaN = absent
+    // Time slicing of a launch (whfast_step.cuh): the n_steps of a call are cut into n_pieces consecutive pieces per block of
+    // systems ("group"); a CTA takes a ticket, runs one piece of one group and hands the state over through HBM.
+    // sched[0] = ticket counter, sched[1 + g] = pieces of group g completed. n_pieces = 1: plain one-CTA-per-group launch.
+    unsigned int* sched;
+    unsigned int n_groups, n_pieces;
 };
+
+// Loads of state that another CTA of the same launch may have written (time slicing): L2, never a stale L1 line.
+template <class T> __device__ __forceinline__ T ldm(const T* p) { return __ldcg(p); }
 
 #define FULL 0xffffffffu
 

@@ -42,9 +42,9 @@ __device__ __forceinline__ void store_lane(const KParams& P, const Roles& ro, co
     // radius / radius of gyration / moment of inertia are written when they evolve (evolve_lane)
     if (b == 0) {
         P.t[sys] = st.t; P.last_hist[sys] = st.last_hist;
-        unsigned long long it0 = P.iteration[sys];
+        unsigned long long it0 = ldm(P.iteration + sys);
         P.iteration[sys] = it0 + st.steps_done;
-        P.n_hist[sys] += st.n_hist_new;
+        P.n_hist[sys] = ldm(P.n_hist + sys) + st.n_hist_new;
         if (st.status != PB200_STATUS_OK) P.event_iteration[sys] = it0 + st.event_step;
         P.tswarn[sys] = st.tswarn ? 1ull : 0ull;
         P.status[sys] = st.status; P.warnings[sys] = st.warnings; P.hist_count[sys] = st.hist_count;
@@ -59,7 +59,7 @@ __device__ __forceinline__ bool evolve_lane(const KParams& P, const Roles& ro, c
     if (ti < 0) return false;
     const DevTable& T = P.tables[ti];
     const size_t idx = (size_t)b * (size_t)P.n_sys + sys;
-    const double R = cold.get(K_R), rg2 = P.rg2[idx];
+    const double R = cold.get(K_R), rg2 = ldm(P.rg2 + idx);
     int i = table_upper(T.time, T.n_rows, t);
     double nr = T.interp_radius ? table_interp(T.time, T.radius, T.n_rows, i, t) : R;
     double ng = T.interp_rg2 ? table_interp(T.time, T.rg2, T.n_rows, i, t) : rg2;
@@ -261,7 +261,25 @@ template <int COORD, int GR, int ARITH>
 __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
     const int W = PB_W(P);
     const int n = PB_N(P);
-    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // ---- time slicing: which piece of which group of systems this CTA runs (KParams::sched). Tickets are handed out in
+    // the order CTAs actually start, so the piece a CTA waits for has always started already: no deadlock.
+    __shared__ unsigned int s_ticket;
+    unsigned int piece = 0, group = blockIdx.x;
+    if (P.n_pieces > 1) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(P.sched, 1u);
+        __syncthreads();
+        piece = s_ticket / P.n_groups; group = s_ticket % P.n_groups;
+        if (piece > 0) {
+            if (threadIdx.x == 0) {
+                const volatile unsigned int* flag = P.sched + 1 + group;
+                while (*flag < piece) __nanosleep(500);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
+    const unsigned long long step_begin = n_steps * piece / P.n_pieces, step_end = n_steps * (piece + 1ull) / P.n_pieces;
+    const size_t gtid = (size_t)group * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int b = (int)(gtid & (size_t)(W - 1));
     const size_t sys = gtid >> PB_SHIFT(P);
@@ -285,14 +303,11 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
         const size_t ns = (size_t)P.n_sys;
         const size_t i = (size_t)b * ns + sys, cs = (size_t)n * ns;
         if (ro.valid) {
-            q.r = s3(sd(P.pos[i]), sd(P.pos[i + cs]), sd(P.pos[i + 2 * cs]));
-            q.v = s3(sd(P.vel[i]), sd(P.vel[i + cs]), sd(P.vel[i + 2 * cs]));
-            q.L = v3(P.L[i], P.L[i + cs], P.L[i + 2 * cs]);
-            q.s = v3(P.spin[i], P.spin[i + cs], P.spin[i + 2 * cs]);
-            cold.set3(S_EVX, v3(P.verr[i], P.verr[i + cs], P.verr[i + 2 * cs]));
-            cold.set3(S_ELX, v3(P.lerr[i], P.lerr[i + cs], P.lerr[i + 2 * cs]));
-            cold.set3(S_AX, v3(P.acc[i], P.acc[i + cs], P.acc[i + 2 * cs]));
-            cold.set(K_M, P.mass[i]); cold.set(K_MG, P.mass_g[i]); cold.set(K_R, P.radius[i]); cold.set(K_I, P.moi[i]);
+            auto ld3 = [&](const double* a) { return v3(ldm(a + i), ldm(a + i + cs), ldm(a + i + 2 * cs)); };
+            q.r = strict(ld3(P.pos)); q.v = strict(ld3(P.vel));
+            q.L = ld3(P.L); q.s = ld3(P.spin);
+            cold.set3(S_EVX, ld3(P.verr)); cold.set3(S_ELX, ld3(P.lerr)); cold.set3(S_AX, ld3(P.acc));
+            cold.set(K_M, P.mass[i]); cold.set(K_MG, P.mass_g[i]); cold.set(K_R, ldm(P.radius + i)); cold.set(K_I, ldm(P.moi + i));
         } else {
             // padding lanes: finite, non-zero dummies (never read by live lanes, never stored)
             q.r = s3(sd(1. + b), sd(0.), sd(0.)); q.v = s3(sd(0.), sd(0.), sd(0.));
@@ -301,8 +316,8 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
             cold.set(K_M, 1.); cold.set(K_MG, 1.); cold.set(K_R, 1.); cold.set(K_I, 1.);
         }
         if (sys_ok) {
-            st.t = P.t[sys]; st.last_hist = P.last_hist[sys];
-            st.tswarn = P.tswarn[sys] != 0; st.status = P.status[sys]; st.warnings = P.warnings[sys]; st.hist_count = P.hist_count[sys];
+            st.t = ldm(P.t + sys); st.last_hist = ldm(P.last_hist + sys);
+            st.tswarn = ldm(P.tswarn + sys) != 0; st.status = ldm(P.status + sys); st.warnings = ldm(P.warnings + sys); st.hist_count = ldm(P.hist_count + sys);
         } else {
             st.t = 0.; st.last_hist = 0.; st.tswarn = true; st.status = PB200_STATUS_COMPLETED; st.warnings = 0; st.hist_count = 0;
         }
@@ -346,7 +361,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
     const S3 one3 = s3(one, one, one);
 
 #pragma unroll 1
-    for (unsigned long long step = 0; step < n_steps; step++) {
+    for (unsigned long long step = step_begin; step < step_end; step++) {
 #if PB_STEP_BARRIER
         // one block-wide barrier per step keeps the warps of a block in the same region of the (large) loop body, so that
         // they share instruction-cache lines; it also makes the loop exit block-uniform
@@ -380,7 +395,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     if ((PB_FLAGS(P) & FLAG_TIDES) && ro.t_on) {
                         // tides/common.rs:263-279 with the internals left by the last evaluation and the fresh spin
                         double ts[PB_TIDE_SCRATCH];
-                        for (int k = 0; k < PB_TIDE_SCRATCH; k++) ts[k] = P.tide_scratch[i + k * cs];
+                        for (int k = 0; k < PB_TIDE_SCRATCH; k++) ts[k] = ldm(P.tide_scratch + i + k * cs);
                         V3 tp = v3(ts[0], ts[1], ts[2]), tv = v3(ts[3], ts[4], ts[5]);
                         double dist = ts[6], radvel = ts[7], orth_p = ts[8], diss_pm = ts[9];
                         V3 tdl = v3(ts[10], ts[11], ts[12]);
@@ -395,9 +410,9 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     h[1 * cs] = q.r.x.v; h[2 * cs] = q.r.y.v; h[3 * cs] = q.r.z.v;
                     h[4 * cs] = q.s.x; h[5 * cs] = q.s.y; h[6 * cs] = q.s.z;
                     h[7 * cs] = q.v.x.v; h[8 * cs] = q.v.y.v; h[9 * cs] = q.v.z.v;
-                    h[10 * cs] = cold.get(K_M); h[11 * cs] = cold.get(K_R); h[12 * cs] = P.rg2[i];
+                    h[10 * cs] = cold.get(K_M); h[11 * cs] = cold.get(K_R); h[12 * cs] = ldm(P.rg2 + i);
                     h[13 * cs] = P.k2t[i]; h[14 * cs] = P.sigma[i]; h[15 * cs] = denergy;
-                    h[16 * cs] = (PB_FLAGS(P) & FLAG_DYN) ? P.lag[i] : 0.;
+                    h[16 * cs] = (PB_FLAGS(P) & FLAG_DYN) ? ldm(P.lag + i) : 0.;
                 }
                 if (snap) {
                     if (!first) st.last_hist = __dadd_rn(st.last_hist, P.hist_period); else st.last_hist = 0.;
@@ -407,7 +422,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
             }
         }
         // internals needed by the NEXT snapshot's denergy_dt are those of this step's last evaluation
-        const bool save_tides = (step + 1 == n_steps) || (__dadd_rn(st.last_hist, P.hist_period) <= __dadd_rn(st.t, P.dt));
+        const bool save_tides = (step + 1 == step_end) || (__dadd_rn(st.last_hist, P.hist_period) <= __dadd_rn(st.t, P.dt));
 
         // One code instance of the midpoint serves both halves of the step (whfast.rs:278 and :293); the drift-kick-drift
         // core runs between them. Likewise one instance of the Kepler solver serves both drifts.
@@ -584,6 +599,12 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
         }
     }
     if (alive) store_lane(P, ro, cold, sys, b, q, st);
+    if (P.n_pieces > 1) {
+        // hand the group over to the CTA that runs its next piece: state first, then the flag
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) { volatile unsigned int* flag = P.sched + 1 + group; *flag = piece + 1; }
+    }
 }
 
 }  // namespace PB_NS

@@ -390,3 +390,32 @@ def test_wind_spins_the_star_down(E):
             ens.iterate(199)
             out.append(ens.download(("spin",))["spin"][2, 0, 0])
     assert out[0] < out[1]
+
+
+@pytest.mark.parametrize("pieces", ["2", "5"])
+def test_time_sliced_launch_is_bit_identical(E, pieces, monkeypatch):
+    """A launch cut into consecutive pieces per block of systems (wave-quantisation fix, pb200_api.cu plan_pieces) hands
+    the state from CTA to CTA through HBM: results, clocks, iteration counters and history must equal the plain launch."""
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import make_ensemble_cases
+    d = config_case("c4_trappist1")
+    d["historic_snapshot_period"] = 4.0   # every 50 steps: snapshots fall inside several pieces
+    case, tables = case_from_dict(d)
+    cases = make_ensemble_cases(case, 3000, 77)   # 375 CTAs: more than one piece boundary per SM
+    out = []
+    for k in ("1", pieces):
+        monkeypatch.setenv("PB200_PIECES", k)
+        with E.Ensemble(cases, tables) as ens:
+            ens.initialize_physical_values()
+            ens.iterate(333)
+            state = ens.download()
+            st, w, it = ens.status()
+            hist = ens.history_drain()
+            c = ens.get_case(2999)
+        out.append((state, st, w, it, hist, c.current_iteration, c.n_historic_snapshots))
+    a, b = out
+    for key in a[0]:
+        assert np.array_equal(a[0][key], b[0][key]), key
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert np.array_equal(a[4], b[4]) and a[4].shape[1] == 7
+    assert a[5:] == b[5:] == (333, 7)
