@@ -243,7 +243,7 @@ static unsigned plan_pieces(unsigned grid, unsigned slots, unsigned long long n_
     double best_eff = eff(1);
     for (unsigned k = 2; k <= 8; k++) {
         if (n_steps / k < 50) break;              // keep the per-piece state hand-over through HBM negligible
-        if (eff(k) > best_eff + 0.01) { best = k; best_eff = eff(k); }
+        if (eff(k) > best_eff + 0.005) { best = k; best_eff = eff(k); }
     }
     return best;
 }
