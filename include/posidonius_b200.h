@@ -216,6 +216,15 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
                           pb200_ensemble_t** out);
 void pb200_ensemble_destroy(pb200_ensemble_t* e);
 
+/* Synthetic perturbed ensemble built ON THE DEVICE (no per-member case images on the host): member 0 is
+ * `base`; member k > 0 has every non-host body's heliocentric position and velocity multiplied component-wise by
+ * (1 + delta), delta uniform in (-amplitude, amplitude) from a SplitMix64 stream seeded with seed * 0x100000001b3 + k
+ * (drawn in the order [body][x, y, z, vx, vy, vz]), and the barycentric coordinates recomputed as Universe::new does
+ * (universe.rs:95-105, 663-697). Masses, radii, spins and parameters are those of `base`. Bit-identical to building the
+ * members on the host with the same recipe (posidonius-b200 ensemble, posidonius_b200/perturb.py::splitmix_cases). */
+int pb200_ensemble_create_perturbed(const pb200_case_t* base, size_t n_systems, uint64_t seed, double amplitude,
+                                    const pb200_table_t* tables, size_t n_tables, int device, pb200_ensemble_t** out);
+
 /* Integrator::get_n_particles / get_current_time / get_n_historic_snapshots (mod.rs:18-20). */
 int pb200_ensemble_n_particles(const pb200_ensemble_t* e);
 size_t pb200_ensemble_n_systems(const pb200_ensemble_t* e);

@@ -24,6 +24,8 @@ _SIGNATURES = {
     "pb200_table_store_free": (None, [C.c_void_p]),
     "pb200_ensemble_create": (C.c_int, [C.POINTER(abi.Case), C.c_size_t, C.c_size_t, C.POINTER(abi.Table), C.c_size_t,
                                         C.c_int, C.POINTER(C.c_void_p)]),
+    "pb200_ensemble_create_perturbed": (C.c_int, [C.POINTER(abi.Case), C.c_size_t, C.c_uint64, C.c_double, C.POINTER(abi.Table),
+                                                  C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "pb200_ensemble_destroy": (None, [C.c_void_p]),
     "pb200_ensemble_n_particles": (C.c_int, [C.c_void_p]),
     "pb200_ensemble_n_systems": (C.c_size_t, [C.c_void_p]),

@@ -186,41 +186,8 @@ static int run_single(const Args& a, bool resume) {
     return 0;
 }
 
-// ---- ensemble: N perturbed members of one case, deterministic SplitMix64 stream
-static inline uint64_t splitmix64(uint64_t& s) {
-    uint64_t z = (s += 0x9e3779b97f4a7c15ull);
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    return z ^ (z >> 31);
-}
-static inline double uniform(uint64_t& s, double a) { return (2.0 * ((splitmix64(s) >> 11) * (1.0 / 9007199254740992.0)) - 1.0) * a; }
-
-static void perturb(const pb200_case_t& base, pb200_case_t& out, uint64_t member, uint64_t seed, double amp) {
-    out = base;
-    if (member == 0) return;   // member 0 is the base case
-    const int n = base.n_particles, h = base.host_most_massive;
-    uint64_t s = seed * 0x100000001b3ull + member;
-    for (int b = 0; b < n; b++) {
-        if (b == h) continue;
-        for (int c = 0; c < 3; c++) out.bodies[b].heliocentric_position[c] = base.bodies[b].heliocentric_position[c] * (1.0 + uniform(s, amp));
-        for (int c = 0; c < 3; c++) out.bodies[b].heliocentric_velocity[c] = base.bodies[b].heliocentric_velocity[c] * (1.0 + uniform(s, amp));
-    }
-    // barycentric coordinates as Universe::new computes them (universe.rs:95-105, 663-697)
-    double cp[3] = {0, 0, 0}, cv[3] = {0, 0, 0}, cm = 0.;
-    for (int b = 0; b < n; b++) {
-        const double m = out.bodies[b].mass;
-        for (int c = 0; c < 3; c++) { cp[c] = cp[c] * cm + out.bodies[b].heliocentric_position[c] * m; cv[c] = cv[c] * cm + out.bodies[b].heliocentric_velocity[c] * m; }
-        double nm = cm + m;
-        if (nm > 0.) for (int c = 0; c < 3; c++) { cp[c] /= nm; cv[c] /= nm; }
-        cm = nm;
-    }
-    for (int b = 0; b < n; b++)
-        for (int c = 0; c < 3; c++) {
-            out.bodies[b].inertial_position[c] = out.bodies[b].heliocentric_position[c] - cp[c];
-            out.bodies[b].inertial_velocity[c] = out.bodies[b].heliocentric_velocity[c] - cv[c];
-        }
-}
-
+// ---- ensemble: N perturbed members of one case, built on the device from a deterministic SplitMix64
+// stream (pb200_ensemble_create_perturbed): no per-member images on the host
 static int run_ensemble(const Args& a) {
     if (a.pos.size() < 2 || a.systems <= 0) panic("usage: posidonius-b200 ensemble <case.json> <out_dir> --systems N [--seed S] [--amplitude A] [--steps K] [--device D] [--strict]");
     const std::string out_dir = a.pos[1];
@@ -229,10 +196,9 @@ static int run_ensemble(const Args& a) {
     check(pb200_case_load(a.pos[0].c_str(), &base, &store), "cannot read the case");
     mkdir(out_dir.c_str(), 0777);
     const size_t S = (size_t)a.systems;
-    std::vector<pb200_case_t> cases(S);
-    for (size_t k = 0; k < S; k++) perturb(base, cases[k], k, (uint64_t)a.seed, a.amplitude);
     pb200_ensemble_t* e = nullptr;
-    check(pb200_ensemble_create(cases.data(), S, S, pb200_table_store_tables(store), pb200_table_store_count(store), a.device, &e), "cannot create the ensemble");
+    check(pb200_ensemble_create_perturbed(&base, S, (uint64_t)a.seed, a.amplitude, pb200_table_store_tables(store), pb200_table_store_count(store), a.device, &e),
+          "cannot create the ensemble");
     if (a.strict) check(pb200_ensemble_set_arithmetic(e, PB200_ARITH_STRICT), "strict arithmetic");
     if (base.current_time == 0.) check(pb200_ensemble_initialize_physical_values(e), "initialize_physical_values");
     const int n = base.n_particles;

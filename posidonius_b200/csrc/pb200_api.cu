@@ -167,6 +167,51 @@ __global__ void pack_history_kernel(const __grid_constant__ KParams P, int n_sna
     if (!have) { put(0, 0.); }
 }
 
+// Device-side construction of a perturbed ensemble (pb200_ensemble_create_perturbed): one thread per member.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& s) {
+    unsigned long long z = (s += 0x9e3779b97f4a7c15ull);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+struct PerturbBase { double hpos[PB200_MAX_PARTICLES][3], hvel[PB200_MAX_PARTICLES][3], mass[PB200_MAX_PARTICLES]; };
+__global__ void perturb_kernel(const __grid_constant__ KParams P, const __grid_constant__ PerturbBase B, unsigned long long seed, double amp) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t ns = (size_t)P.n_sys;
+    if (k == 0 || k >= ns) return;   // member 0 is the base case (already uploaded)
+    const int n = P.n_bodies;
+    unsigned long long s = seed * 0x100000001b3ull + (unsigned long long)k;
+    sd hp[PB200_MAX_PARTICLES][3], hv[PB200_MAX_PARTICLES][3];
+    for (int b = 0; b < n; b++) {
+        for (int c = 0; c < 3; c++) { hp[b][c] = sd(B.hpos[b][c]); hv[b][c] = sd(B.hvel[b][c]); }
+        if (b == P.host) continue;
+        // (2 u - 1) a with u = (z >> 11) 2^-53, then x (1 + delta): every product and sum rounded like the host's doubles
+        for (int c = 0; c < 3; c++) {
+            const sd u = sd((double)(splitmix64(s) >> 11)) * sd(1.0 / 9007199254740992.0);
+            hp[b][c] = hp[b][c] * (sd(1.0) + (sd(2.0) * u - sd(1.0)) * sd(amp));
+        }
+        for (int c = 0; c < 3; c++) {
+            const sd u = sd((double)(splitmix64(s) >> 11)) * sd(1.0 / 9007199254740992.0);
+            hv[b][c] = hv[b][c] * (sd(1.0) + (sd(2.0) * u - sd(1.0)) * sd(amp));
+        }
+    }
+    // calculate_center_of_mass (universe.rs:663-697): running pairwise centre of mass in body order
+    sd cp[3] = {sd(0.), sd(0.), sd(0.)}, cv[3] = {sd(0.), sd(0.), sd(0.)}, cm = sd(0.);
+    for (int b = 0; b < n; b++) {
+        const sd m = sd(B.mass[b]);
+        for (int c = 0; c < 3; c++) { cp[c] = cp[c] * cm + hp[b][c] * m; cv[c] = cv[c] * cm + hv[b][c] * m; }
+        const sd nm = cm + m;
+        if (nm.v > 0.) for (int c = 0; c < 3; c++) { cp[c] = div_ieee(cp[c], nm); cv[c] = div_ieee(cv[c], nm); }
+        cm = nm;
+    }
+    const size_t cs = (size_t)n * ns;
+    for (int b = 0; b < n; b++)
+        for (int c = 0; c < 3; c++) {
+            P.pos[(size_t)c * cs + (size_t)b * ns + k] = (hp[b][c] - cp[c]).v;
+            P.vel[(size_t)c * cs + (size_t)b * ns + k] = (hv[b][c] - cv[c]).v;
+        }
+}
+
 // DFMA chain microbenchmark: 8 independent chains per thread.
 __global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-9, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
@@ -207,6 +252,7 @@ struct pb200_ensemble {
     double recovery_snapshot_period = 0.;
     int arithmetic = PB200_ARITH_FAST;
     int sm_count = 0;
+    bool perturbed = false;       // built by pb200_ensemble_create_perturbed: heliocentric fields of the image are per member
     bool force_generic = false;   // PB200_FORCE_GENERIC=1 in the environment: bypass the 8-body specialisation (A/B tests)
     // host mirror of the ensemble clock (exact snapshot counting without a device round trip)
     bool uniform_clock = true;
@@ -594,6 +640,28 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     return PB200_OK;
 }
 
+int pb200_ensemble_create_perturbed(const pb200_case_t* base, size_t n_systems, uint64_t seed, double amplitude,
+                                    const pb200_table_t* tables, size_t n_tables, int device, pb200_ensemble_t** out) {
+    if (!base || !out) return set_error(PB200_E_INVALID, "null argument");
+    pb200_ensemble_t* e = nullptr;
+    int rc = pb200_ensemble_create(base, 1, n_systems, tables, n_tables, device, &e);   // every member starts as the base case
+    if (rc != PB200_OK) return rc;
+    PerturbBase B;
+    std::memset(&B, 0, sizeof B);
+    for (int b = 0; b < base->n_particles; b++) {
+        for (int c = 0; c < 3; c++) { B.hpos[b][c] = base->bodies[b].heliocentric_position[c]; B.hvel[b][c] = base->bodies[b].heliocentric_velocity[c]; }
+        B.mass[b] = base->bodies[b].mass;
+    }
+    perturb_kernel<<<(unsigned)((n_systems + 127) / 128), 128, 0, e->stream>>>(e->P, B, (unsigned long long)seed, amplitude);
+    e->launches++;
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) { pb200_ensemble_destroy(e); return set_error(PB200_E_CUDA, std::string("perturb kernel: ") + cudaGetErrorString(err)); }
+    e->perturbed = true;
+    *out = e;
+    return PB200_OK;
+}
+
 int pb200_ensemble_n_particles(const pb200_ensemble_t* e) { return e ? e->n_bodies : 0; }
 size_t pb200_ensemble_n_systems(const pb200_ensemble_t* e) { return e ? e->n_sys : 0; }
 
@@ -801,6 +869,16 @@ int pb200_ensemble_get_case(pb200_ensemble_t* e, size_t s, pb200_case_t* out) {
                 CUDA_TRY(get(e->P.pair_p, i, &out->pair_dependent_scaled_dissipation_factor[B.id * PB200_MAX_PARTICLES + hid], 8));
             }
         }
+    }
+    if (e->perturbed) {
+        // members built on the device have no host image of their own: heliocentric coordinates as inertial_to_heliocentric
+        // (universe.rs:318-351) leaves them
+        const pb200_body_t& H = out->bodies[e->P.host];
+        for (size_t b = 0; b < nb; b++)
+            for (int c = 0; c < 3; c++) {
+                out->bodies[b].heliocentric_position[c] = (int)b == e->P.host ? 0. : out->bodies[b].inertial_position[c] - H.inertial_position[c];
+                out->bodies[b].heliocentric_velocity[c] = (int)b == e->P.host ? 0. : out->bodies[b].inertial_velocity[c] - H.inertial_velocity[c];
+            }
     }
     for (size_t i = 0; i < nb * nb; i++) CUDA_TRY(get(e->d_roche, i * ns + s, &out->roche_radiuses[i], 8));
     unsigned long long u;

@@ -56,6 +56,22 @@ class Ensemble:
         if arithmetic != abi.ARITH_FAST:
             self.set_arithmetic(arithmetic)
 
+    @classmethod
+    def perturbed(cls, base, tables, n_systems, seed, amplitude=1e-3, device=0, arithmetic=abi.ARITH_FAST):
+        """pb200_ensemble_create_perturbed: the synthetic ensemble of SURVEY §8d built on the device (member 0 = base,
+        member k = SplitMix64-perturbed copy); the host never holds per-member case images."""
+        self = cls.__new__(cls)
+        self._tables = tables
+        self._h = C.c_void_p()
+        _check(lib().pb200_ensemble_create_perturbed(C.byref(base), n_systems, seed, amplitude, tables.as_ctypes(), len(tables),
+                                                     device, C.byref(self._h)))
+        self.n_systems = n_systems
+        self.n_particles = lib().pb200_ensemble_n_particles(self._h)
+        self.device = device
+        if arithmetic != abi.ARITH_FAST:
+            self.set_arithmetic(arithmetic)
+        return self
+
     def set_arithmetic(self, mode):
         _check(lib().pb200_ensemble_set_arithmetic(self._h, mode))
 

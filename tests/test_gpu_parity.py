@@ -419,3 +419,30 @@ def test_time_sliced_launch_is_bit_identical(E, pieces, monkeypatch):
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     assert np.array_equal(a[4], b[4]) and a[4].shape[1] == 7
     assert a[5:] == b[5:] == (333, 7)
+
+
+def test_device_built_ensemble_equals_host_recipe(E):
+    """pb200_ensemble_create_perturbed builds the members on the device: initial state bit-identical to
+    the host statement of the same SplitMix64 recipe, and the same trajectories afterwards; get_case gives a member's image."""
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import splitmix_cases
+    case, tables = case_from_dict(config_case("c4_trappist1"))
+    n_sys = 777
+    host_cases = splitmix_cases(case, n_sys, 20261017, 1e-3)
+    with E.Ensemble.perturbed(case, tables, n_sys, 20261017, 1e-3) as dev, E.Ensemble(host_cases, tables) as ref:
+        a, b = dev.download(("position", "velocity")), ref.download(("position", "velocity"))
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        assert not np.array_equal(a["position"][..., 1], a["position"][..., 2])     # members differ
+        for ens in (dev, ref):
+            ens.initialize_physical_values()
+            ens.iterate(200)
+        a, b = dev.download(), ref.download()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+        got, want = dev.get_case(776), ref.get_case(776)
+        for i in range(case.n_particles):
+            assert list(got.bodies[i].inertial_position[:]) == list(want.bodies[i].inertial_position[:])
+            if i != case.host_most_massive:
+                hp = np.array(got.bodies[i].heliocentric_position[:])
+                assert np.allclose(hp, np.array(got.bodies[i].inertial_position[:]) - np.array(got.bodies[0].inertial_position[:]), rtol=0, atol=0)
