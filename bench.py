@@ -246,9 +246,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / (fp64_peak / 1e12) if fp64_peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 65536 systems, ncu --set full
-                         # (profiles/r1_ncu_step_kernel_summary.txt); independent of the steps per launch
-                         "traffic": 350.9e6 * n_sys / 65536.0,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one bench launch (65536 systems, 1000 steps cut into
+                         # 4 time slices: the state crosses HBM once per slice), ncu, profiles/r1_traffic_bench_launch.csv
+                         "traffic": 1092.8e6 * n_sys / 65536.0,
                          "peak_source": "measured here: DFMA-chain microbenchmark (pb200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                          "frac_of_theoretical_37.2": achieved / FP64_THEORETICAL_TFLOPS,
                          "flops_per_system_step": FLOPS_PER_SYSTEM_STEP},

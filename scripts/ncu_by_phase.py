@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Executed warp-instructions of the step kernel by CALL SITE in the kernel body (outermost frame of nvdisasm's inline
+chains) and by the innermost function, split into FP64 and other instructions.
+
+usage: ncu_by_phase.py report.ncu-rep libposidonius_b200.so 'kernel-substring' warp_steps
+"""
+import collections
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+
+def main():
+    rep, so, kern = sys.argv[1:4]
+    warp_steps = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
+    tmp = tempfile.mkdtemp()
+    subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
+    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin") and "case_io" not in f][0]
+    dis = subprocess.run(["nvdisasm", "-gi", cubin], stdout=subprocess.PIPE, text=True).stdout
+    addr2 = {}
+    in_k = False
+    chain = []
+    pending = []
+    for line in dis.splitlines():
+        if line.startswith("//--------------------- .text."):
+            in_k = kern in line
+            continue
+        if not in_k:
+            continue
+        m = re.search(r'//## File "([^"]+)", line (\d+)', line)
+        if m:
+            pending.append((os.path.basename(m.group(1)), int(m.group(2))))
+            continue
+        m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
+        if m:
+            if pending:
+                chain = pending
+                pending = []
+            addr2[int(m.group(1), 16)] = (chain, m.group(2))
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], stdout=subprocess.PIPE, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = rows[1]
+    ia, ie, isrc = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Source")
+    base = None
+    outer = collections.defaultdict(lambda: [0, 0])
+    inner = collections.defaultdict(lambda: [0, 0])
+    tot = [0, 0]
+    for r in rows[2:]:
+        try:
+            a = int(r[ia], 16) if r[ia].startswith("0x") else int(r[ia])
+            ex = int(r[ie])
+        except Exception:
+            continue
+        if base is None:
+            base = a
+        ch, _ = addr2.get(a - base, ([("?", 0)], ""))
+        m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[isrc])
+        op = m.group(2) if m else "?"
+        f64 = 1 if op.split(".")[0] in ("DADD", "DMUL", "DFMA", "DSETP", "MUFU") else 0
+        # outermost frame that lies in whfast_step.cuh (the kernel body / midpoint / gravity)
+        step_frames = [c for c in ch if c[0] == "whfast_step.cuh"]
+        o = step_frames[-1] if step_frames else ch[-1]
+        o2 = step_frames[0] if step_frames else ch[0]
+        outer["%s:%d" % o][f64] += ex
+        inner["%s:%d" % o2][f64] += ex
+        tot[f64] += ex
+    print("per warp-step: %.0f instructions, %.0f FP64" % ((tot[0] + tot[1]) / warp_steps, tot[1] / warp_steps))
+    for name, table in (("kernel-body call site (outermost whfast_step.cuh frame)", outer), ("innermost whfast_step.cuh frame", inner)):
+        print("\n%s: FP64 / other per warp-step" % name)
+        for k, v in sorted(table.items(), key=lambda kv: -(kv[1][0] + kv[1][1]))[:40]:
+            print("  %-28s %8.1f %8.1f" % (k, v[1] / warp_steps, v[0] / warp_steps))
+
+
+if __name__ == "__main__":
+    main()
