@@ -144,7 +144,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--systems", type=int, default=65536, help="systems per GPU")
-    ap.add_argument("--steps-per-call", type=int, default=1000, help="WHFast steps per launch (one bench step)")
+    ap.add_argument("--steps-per-call", type=int, default=2000,
+                    help="WHFast steps per launch (one bench step); the default times 5 x 2000 = 10^4 steps (SURVEY §8d horizon)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--arithmetic", default="fast", choices=["fast", "strict"],
                     help="fast (default): FMA/reciprocal forces; strict: forces bit-reproducible against the reference arithmetic")
@@ -246,7 +247,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / (fp64_peak / 1e12) if fp64_peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one bench launch (65536 systems, 1000 steps cut into
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one bench launch (65536 systems, its steps cut into
                          # 4 time slices: the state crosses HBM once per slice), ncu, profiles/r1_traffic_bench_launch.csv
                          "traffic": 1092.8e6 * n_sys / 65536.0,
                          "peak_source": "measured here: DFMA-chain microbenchmark (pb200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",

@@ -150,16 +150,17 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
         const S3 vo = strict(cold.get3(S_VOX));
         const V3 Lo = cold.get3(S_LOX);
         const V3 ev = cold.get3(S_EVX), el = cold.get3(S_ELX);
-        S3 vf_old = vo + strict(cold.get3(S_DVX));
-        V3 dl_old = cold.get3(S_DLX);
-        V3 Lf_old = v3(__dadd_rn(Lo.x, dl_old.x), __dadd_rn(Lo.y, dl_old.y), __dadd_rn(Lo.z, dl_old.z));
         S3 ndv = s3(dt * sd(a.x) - sd(ev.x), dt * sd(a.y) - sd(ev.y), dt * sd(a.z) - sd(ev.z));
         V3 ndl = v3((dt * sd(dldt.x) - sd(el.x)).v, (dt * sd(dldt.y) - sd(el.y)).v, (dt * sd(dldt.z) - sd(el.z)).v);
         S3 vf = vo + ndv;
         V3 Lf = PB_SPIN(P) ? v3(__dadd_rn(Lo.x, ndl.x), __dadd_rn(Lo.y, ndl.y), __dadd_rn(Lo.z, ndl.z)) : Lo;
         bool conv_now = false;
         if (it >= 2) {
-            // whfast.rs:424-451 (sums over bodies by butterfly: only the branch decision depends on them)
+            // whfast.rs:424-451 (sums over bodies by butterfly: only the branch decision depends on them); the previous
+            // iterate's final values are rebuilt from the stored increments
+            const S3 vf_old = vo + strict(cold.get3(S_DVX));
+            const V3 dl_old = cold.get3(S_DLX);
+            const V3 Lf_old = v3(__dadd_rn(Lo.x, dl_old.x), __dadd_rn(Lo.y, dl_old.y), __dadd_rn(Lo.z, dl_old.z));
             V3 ddv = plain(vf - vf_old), ddl = Lf - Lf_old, vfp = plain(vf);
             double s_dv = ro.valid ? dot(ddv, ddv) : 0., s_fv = ro.valid ? dot(vfp, vfp) : 0.;
             s_dv = group_sum(s_dv, W); s_fv = group_sum(s_fv, W);

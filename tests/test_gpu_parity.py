@@ -446,3 +446,47 @@ def test_device_built_ensemble_equals_host_recipe(E):
             if i != case.host_most_massive:
                 hp = np.array(got.bodies[i].heliocentric_position[:])
                 assert np.allclose(hp, np.array(got.bodies[i].inertial_position[:]) - np.array(got.bodies[0].inertial_position[:]), rtol=0, atol=0)
+
+
+def test_mixed_fates_inside_one_ensemble(E):
+    """Members that are destroyed, ejected or completed early share warps with members that keep running: every member's
+    status, event iteration and state equals the oracle's for that member (no cross-talk, dead systems frozen)."""
+    from oracle.binding import run_ensemble
+    from posidonius_b200 import abi
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import cases_as_numpy, make_ensemble_cases
+    case, tables = case_from_dict(config_case("c4_trappist1"))
+    n_sys = 40
+    cases = make_ensemble_cases(case, n_sys, 31)
+    arr = cases_as_numpy(cases)
+    h = case.host_most_massive
+    for s, body, factor in ((3, 1, 0.3), (4, 7, 2.0e4), (17, 2, 0.5), (18, 5, 3.0e4), (39, 3, 0.25)):
+        rel = arr["bodies"]["inertial_position"][s, body] - arr["bodies"]["inertial_position"][s, h]
+        arr["bodies"]["inertial_position"][s, body] = arr["bodies"]["inertial_position"][s, h] + factor * rel
+    steps = 400
+    with E.Ensemble(cases, tables) as ens:
+        ens.initialize_physical_values()
+        ens.iterate(150)
+        ens.iterate(steps - 150)
+        g = gpu_state_of(ens)
+        st, w, it = ens.status()
+    oc, ost, _ = run_ensemble(cases, n_sys, tables, steps, True, 4)
+    o = oracle_state_of(oc)
+    assert np.array_equal(st, ost)
+    assert set(st.tolist()) >= {abi.STATUS_OK, abi.STATUS_ROCHE_DESTROYED, abi.STATUS_EJECTED}
+    alive = st == abi.STATUS_OK
+    for k in ("position", "velocity", "spin", "angular_momentum"):
+        assert rel_err(g[k][alive], o[k][alive]) < TOL_1E3, (k, rel_err(g[k][alive], o[k][alive]))
+    assert np.array_equal(g["current_time"], o["current_time"])
+    assert (~alive).sum() == 5
+    for s in np.where(~alive)[0]:
+        assert it[s] == oc[s].current_iteration   # the step at which the reference would have panicked
+
+
+def test_empty_and_invalid_ensembles_are_rejected(E):
+    from posidonius_b200.case import InvalidCaseError, case_from_dict
+    case, tables = case_from_dict(config_case("c2_case3"))
+    with pytest.raises(InvalidCaseError):
+        E.Ensemble(case, tables, n_systems=0)
+    with pytest.raises(InvalidCaseError):
+        E.Ensemble(case, tables, n_systems=4, device=99)
