@@ -139,32 +139,48 @@ __global__ void summary_kernel(const __grid_constant__ KParams P, double* energy
 }
 
 // SoA history planes -> the reference's 156-byte records (output.rs:119-163), system-major.
-// One thread per (system, snapshot, body); 4-byte stores because the doubles sit at offset 20 (unaligned).
+// One CTA = 32 consecutive systems x one snapshot: the planes are read with the system index fastest (every load a full
+// 256-byte row), the records are assembled in shared memory and written out as each system's contiguous run of
+// n_bodies x 156 bytes (the doubles of a record sit at byte 20, hence 4-byte words throughout).
+#define PB_REC_WORDS (PB200_HISTORIC_RECORD_BYTES / 4)
 __global__ void pack_history_kernel(const __grid_constant__ KParams P, int n_snap, double dt, unsigned int* out) {
-    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ unsigned int tile[];   // [32 systems][row] words, row = n_bodies * 39 padded to an odd count
     const size_t ns = (size_t)P.n_sys;
     const int n = P.n_bodies;
-    const size_t total = ns * (size_t)n_snap * (size_t)n;
-    if (gtid >= total) return;
-    const int b = (int)(gtid % n);
-    const int k = (int)((gtid / n) % n_snap);
-    const size_t sys = gtid / ((size_t)n * n_snap);
+    const int row = (n * PB_REC_WORDS) | 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const size_t sys = (size_t)blockIdx.x * 32 + lane;
+    const int k = blockIdx.y;
+    const bool ok = sys < ns;
+    const bool have = ok && k < P.hist_count[sys];   // systems that stopped early have fewer snapshots: zero records
     const size_t cs = (size_t)n * ns;
-    const double* h = P.hist + (size_t)k * PB_HIST_FIELDS * cs + (size_t)b * ns + sys;
-    unsigned int* w = out + gtid * (PB200_HISTORIC_RECORD_BYTES / 4);
-    auto put = [&](int word, double v) {
-        unsigned long long u = (unsigned long long)__double_as_longlong(v);
-        w[word] = (unsigned int)(u & 0xffffffffull); w[word + 1] = (unsigned int)(u >> 32);
-    };
-    put(0, h[0]);           // current_time
-    put(2, dt);             // time_step
-    w[4] = (unsigned int)b; // particle id (i32)
-    const bool have = k < P.hist_count[sys];  // systems that stopped early have fewer snapshots: zero records
-    for (int f = 0; f < 14; f++) put(5 + 2 * f, have ? h[(size_t)(1 + f) * cs] : 0.);  // pos, spin, vel, mass, radius, rg2, love, sigma
-    put(5 + 2 * 14, have ? h[(size_t)16 * cs] : 0.);       // lag_angle (evolution.rs:552-565)
-    put(5 + 2 * 15, have ? h[(size_t)15 * cs] : 0.);       // denergy_dt
-    put(5 + 2 * 16, 0.);                                   // disk migration_timescale (disk out of scope)
-    if (!have) { put(0, 0.); }
+    const double* h = P.hist + (size_t)k * PB_HIST_FIELDS * cs;
+    unsigned int* mine = tile + lane * row;
+    // (body, plane) pairs over the warps; plane -> word of the record: time | pos, spin, vel, mass, radius, rg2, love, sigma |
+    // denergy_dt | lag_angle (record order: ..., sigma, lag_angle, denergy_dt, migration_timescale)
+    for (int item = warp; item < n * PB_HIST_FIELDS; item += n_warps) {
+        const int b = item / PB_HIST_FIELDS, p = item % PB_HIST_FIELDS;
+        const double v = have ? h[(size_t)p * cs + (size_t)b * ns + sys] : 0.;
+        const int word = p == 0 ? 0 : (p <= 14 ? 5 + 2 * (p - 1) : (p == 15 ? 5 + 2 * 15 : 5 + 2 * 14));
+        const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+        mine[b * PB_REC_WORDS + word] = (unsigned int)(u & 0xffffffffull);
+        mine[b * PB_REC_WORDS + word + 1] = (unsigned int)(u >> 32);
+    }
+    for (int b = warp; b < n; b += n_warps) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong(dt);
+        mine[b * PB_REC_WORDS + 2] = (unsigned int)(u & 0xffffffffull); mine[b * PB_REC_WORDS + 3] = (unsigned int)(u >> 32);   // time_step
+        mine[b * PB_REC_WORDS + 4] = (unsigned int)b;                                                                     // particle id (i32)
+        mine[b * PB_REC_WORDS + 5 + 2 * 16] = 0u; mine[b * PB_REC_WORDS + 5 + 2 * 16 + 1] = 0u;                            // disk migration_timescale
+    }
+    __syncthreads();
+    // each warp writes whole systems: n * 39 consecutive words
+    for (int s = warp; s < 32; s += n_warps) {
+        const size_t gs = (size_t)blockIdx.x * 32 + s;
+        if (gs >= ns) break;
+        unsigned int* dst = out + ((gs * (size_t)n_snap + (size_t)k) * (size_t)n) * PB_REC_WORDS;
+        const unsigned int* src = tile + s * row;
+        for (int w = lane; w < n * PB_REC_WORDS; w += 32) dst[w] = src[w];
+    }
 }
 
 // Device-side construction of a perturbed ensemble (pb200_ensemble_create_perturbed): one thread per member.
@@ -915,7 +931,16 @@ int pb200_ensemble_history_drain(pb200_ensemble_t* e, void* dst, size_t dst_byte
         if (rc != PB200_OK) return rc;
         e->records_capacity = bytes;
     }
-    pack_history_kernel<<<(unsigned)((nrec + 127) / 128), 128, 0, e->stream>>>(e->P, (int)n_snap, e->P.dt, e->d_records);
+    {
+        const size_t smem = 32 * (size_t)((e->n_bodies * PB_REC_WORDS) | 1) * sizeof(unsigned int);   // <= 50 KB (10 bodies)
+        static thread_local int configured_device = -1;
+        if (configured_device != e->device) {
+            CUDA_TRY(cudaFuncSetAttribute(pack_history_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            configured_device = e->device;
+        }
+        dim3 grid((unsigned)((e->n_sys + 31) / 32), (unsigned)n_snap);
+        pack_history_kernel<<<grid, 256, smem, e->stream>>>(e->P, (int)n_snap, e->P.dt, e->d_records);
+    }
     e->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(dst, e->d_records, bytes, cudaMemcpyDeviceToHost, e->stream));

@@ -1,10 +1,12 @@
 // whfast_kernel.cuh — the ensemble WHFast step for sm_100a (fp64 vector pipe, no tensor cores).
 //
 // Mapping: one body per lane, one system per aligned group of W lanes (W = 2,4,8,16), 32/W systems
-// per warp. Dynamic state lives in registers for all n_steps of a launch; the host body's
-// quantities reach the other lanes with warp shuffles, the pairwise sums onto the host are
-// xor-butterfly reductions inside the group. HBM is touched only when a launch starts and ends
-// (coalesced SoA [field][body][system]) and when a historic snapshot falls due.
+// per warp. Dynamic state lives in registers (and per-thread shared-memory columns, `Cold`) for all
+// the steps a CTA runs; the lanes of a group exchange values through those columns (one LDS.64 per
+// double after a __syncwarp) — the host body's quantities, the terms of the ordered sums, the
+// contributions to the host sums; warp shuffles remain in the cold paths and the GR variants.
+// HBM is touched only when a CTA starts and ends (coalesced SoA [field][body][system]) and when a
+// historic snapshot falls due.
 //
 // Reference path restated here (file:line under /root/reference/src):
 //   WHFast::iterate                          integrator/whfast.rs:235-305
@@ -21,7 +23,7 @@
 //
 // Arithmetic: the WHFast core (transforms, Kepler drift, jump, kick, gravity, compensated v/L updates) is
 // strict IEEE in the reference's association order (strict.cuh) and reproduces the CPU oracle's roundings;
-// the perturbation forces use FMA contraction, reciprocal reuse, hoisted powers and butterfly reductions.
+// the perturbation forces use FMA contraction, reciprocal reuse, hoisted powers and a transposed reduction.
 // Parity is asserted against the CPU oracle at 1e-10 relative after 10^4 steps.
 #pragma once
 #include <cuda_runtime.h>
@@ -141,8 +143,6 @@ __device__ __forceinline__ V3 operator*(double s, V3 a) { return v3(s * a.x, s *
 __device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 __device__ __forceinline__ V3 shfl3(V3 a, int src) { return v3(shfl(a.x, src), shfl(a.y, src), shfl(a.z, src)); }
-__device__ __forceinline__ V3 group_sum3(V3 a, int W) { return v3(group_sum(a.x, W), group_sum(a.y, W), group_sum(a.z, W)); }
-__device__ __forceinline__ V3 sel(bool c, V3 a, V3 b) { return v3(c ? a.x : b.x, c ? a.y : b.y, c ? a.z : b.z); }
 
 // ---------------------------------------------------------------------------------------------
 // Stumpff functions c0..c3 (whfast.rs:844-876) and Stiefel G-functions (whfast.rs:835-842), strict arithmetic
