@@ -327,7 +327,7 @@ __device__ __forceinline__ double table_interp(const double* __restrict__ time, 
 // [slot][thread] so that a warp's access is one conflict-free 256-byte row. `volatile` keeps the compiler from
 // forwarding the stored values back into registers.
 #ifndef PB_BLOCK
-#define PB_BLOCK 128
+#define PB_BLOCK 64
 #endif
 
 enum ColdSlot : int {

@@ -11,7 +11,7 @@ namespace PB_NS {
 using namespace pb200;
 
 #ifndef PB_BLOCK
-#define PB_BLOCK 128
+#define PB_BLOCK 64
 #endif
 #define PB_HIST_FIELDS 17  // time, pos3, spin3, vel3, mass, radius, rg2, love_number, sigma, denergy_dt, lag_angle
 #define PB_TIDE_SCRATCH 13
@@ -244,10 +244,10 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const C
 }
 
 #ifndef PB_STEP_BARRIER
-#define PB_STEP_BARRIER 1   // +2.3 % at block 128 x 3 (profiles/r1_variants.md)
+#define PB_STEP_BARRIER 1   // +2 % at block 64 x 5, +5 % at 128 x 3 (profiles/r1_variants.md)
 #endif
 #ifndef PB_MIN_BLOCKS
-#define PB_MIN_BLOCKS 3   // 168 registers/thread, 12 warps/SM, no spills (measured best: profiles/r1_variants.md)
+#define PB_MIN_BLOCKS 5   // 64 x 5: 167 registers/thread, 10 warps/SM, no spills (measured best: profiles/r1_variants.md)
 #endif
 #ifdef PB_MAXNREG
 #define PB_KERNEL_ATTR __launch_bounds__(PB_BLOCK) __maxnreg__(PB_MAXNREG)
