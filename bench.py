@@ -99,9 +99,13 @@ def cpu_baseline(case, tables, steps_per_system=1000, target_seconds=12.0):
     n_sys = (n_sys // cores) * cores or cores
     cases = make_ensemble_cases(case, n_sys, 20261017 + CONFIG_INDEX)
     _, status, secs = run_ensemble(cases, n_sys, tables, steps_per_system, True, cores)
+    import shutil
+    rust = [x for x in ("cargo", "rustc", "posidonius") if shutil.which(x)]
     return {"value": n_sys * steps_per_system / secs, "unit": "system-steps/s", "cores": cores, "kind": "port",
             "sample": "%d perturbed TRAPPIST-1 systems x %d steps on %d host threads (%.1f s); CPU restatement of the "
-                      "reference (oracle/, bit-exact vs the reference goldens), not the Rust binary" % (n_sys, steps_per_system, cores, secs)}
+                      "reference (oracle/, bit-exact vs the reference goldens), not the Rust binary (%s)"
+                      % (n_sys, steps_per_system, cores, secs,
+                         "found on this box but not used: " + ", ".join(rust) if rust else "no cargo / rustc / posidonius binary on this box")}
 
 
 def run_reference(args):
@@ -192,6 +196,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    e_start, l_start = ens.summary()   # Universe::compute_total_energy / angular momentum of every member (untimed)
     for _ in range(args.warmup):
         ens.iterate(spc, synchronize=True)
     fp64_peak = measure_fp64_peak(local, 30.0) if rank == 0 else 0.0
@@ -221,6 +226,15 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - t1
 
+    # ---- after the timed regions: per-system summaries {status, t, dE/E, dL/L}, gathered on rank 0 (the one gather of
+    # ensemble data; NCCL when there are several ranks)
+    from posidonius_b200.shard import gather_summaries
+    e_end, l_end = ens.summary()
+    t_end = ens.get_current_time()
+    rows = torch.from_numpy(np.stack([st.astype(np.float64), t_end, (e_end - e_start) / np.abs(e_start),
+                                      (l_end - l_start) / np.abs(l_start)], axis=1)).to("cuda")
+    rows = gather_summaries(rows, dist if world > 1 else None)
+
     from posidonius_b200.shard import reduce_timing
     elapsed = torch.tensor([kernel_ms * 1e-3, wall, e2e_wall], dtype=torch.float64, device="cuda")
     counts = torch.tensor([alive, n_sys], dtype=torch.int64, device="cuda")
@@ -241,7 +255,10 @@ def main():
                        "effects": "tides(CTL)+rotational_flattening(oblate)+GR(Kidder1995)", "coordinates": "DemocraticHeliocentric",
                        "time_step_days": case.time_step, "arithmetic": args.arithmetic, "parallelism": "ensemble-sharded x%d, no collective" % world,
                        "l2": "state (%.0f MB/GPU) larger than L2; registers hold it between launch start and end" % (io_bytes / 1e6),
-                       "wall_clock_value": units / wall_s, "systems_alive": int(counts[0]), "systems_total": int(counts[1])},
+                       "wall_clock_value": units / wall_s, "systems_alive": int(counts[0]), "systems_total": int(counts[1]),
+                       "ensemble_summary": {"gathered_systems": int(rows.shape[0]), "max_abs_dE_over_E": float(rows[:, 2].abs().max()),
+                                            "max_abs_dL_over_L": float(rows[:, 3].abs().max()), "t_days_min": float(rows[:, 1].min()),
+                                            "t_days_max": float(rows[:, 1].max())}},
             "clocks": clocks,
             "e2e": {"value": units / e2e_s, "unit": "system-steps/s", "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes},
             "gpu_launches": int(launches),

@@ -17,3 +17,18 @@ def reduce_timing(elapsed_seconds, counts, dist=None):
         dist.all_reduce(elapsed_seconds, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     return elapsed_seconds, counts
+
+
+def gather_summaries(rows, dist=None):
+    """Final gather of the per-system summaries (BASELINE north_star: the one place NCCL moves ensemble data).
+
+    rows: [n_local_systems, k] tensor on the rank's device (status, time, dE/E, dL/L ...), the same shape on every rank.
+    Returns the [world * n_local_systems, k] tensor in rank order on rank 0, None on the other ranks."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return rows
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    out = torch.empty((world,) + tuple(rows.shape), dtype=rows.dtype, device=rows.device) if rank == 0 else None
+    parts = list(out.unbind(0)) if rank == 0 else None
+    dist.gather(rows.contiguous(), gather_list=parts, dst=0)
+    return out.reshape((-1,) + tuple(rows.shape[1:])) if rank == 0 else None

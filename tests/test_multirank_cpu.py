@@ -32,7 +32,10 @@ def _worker(rank, world, port, out):
     counts = torch.tensor([b - a, 1], dtype=torch.int64)
     dist.barrier()
     elapsed, counts = reduce_timing(elapsed, counts, dist)
-    out.put((rank, elapsed.tolist(), counts.tolist()))
+    from posidonius_b200.shard import gather_summaries
+    rows = torch.arange(12, dtype=torch.float64).reshape(4, 3) + 100.0 * rank
+    g = gather_summaries(rows, dist)
+    out.put((rank, elapsed.tolist(), counts.tolist(), None if g is None else g.tolist()))
     dist.destroy_process_group()
 
 
@@ -52,6 +55,11 @@ def test_reduce_timing_gloo_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, elapsed, counts in results:
+    for rank, elapsed, counts, gathered in results:
         assert elapsed == [1.5, 2.0]      # max over ranks
         assert counts == [1001, 2]        # all systems accounted for exactly once
+        if rank == 0:
+            # per-system summaries of both ranks, in rank order, on rank 0 only
+            assert gathered == [[float(3 * i + c + 100 * r) for c in range(3)] for r in range(2) for i in range(4)]
+        else:
+            assert gathered is None
