@@ -117,11 +117,11 @@ def run_reference(args):
     from posidonius_b200.perturb import make_ensemble_cases
     case, tables = load_case()
     cores = os.cpu_count() or 1
-    n_sys = 32 * cores
-    spc = 500
+    n_sys = 128 * cores   # about a second of work per step for all host threads
+    spc = 1000
     cases = make_ensemble_cases(case, n_sys, 20261017 + CONFIG_INDEX)
     for _ in range(args.warmup):
-        run_ensemble(cases, n_sys, tables, 50, True, cores)
+        run_ensemble(cases, n_sys, tables, 100, True, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         run_ensemble(cases, n_sys, tables, spc, True, cores)
@@ -266,7 +266,7 @@ def main():
                          "frac": achieved / (fp64_peak / 1e12) if fp64_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one bench launch (65536 systems, its steps cut into
                          # 4 time slices: the state crosses HBM once per slice), ncu, profiles/r1_traffic_bench_launch.csv
-                         "traffic": 1092.8e6 * n_sys / 65536.0,
+                         "traffic": 1109.2e6 * n_sys / 65536.0,
                          "peak_source": "measured here: DFMA-chain microbenchmark (pb200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                          "frac_of_theoretical_37.2": achieved / FP64_THEORETICAL_TFLOPS,
                          "flops_per_system_step": FLOPS_PER_SYSTEM_STEP},
