@@ -490,3 +490,57 @@ def test_empty_and_invalid_ensembles_are_rejected(E):
         E.Ensemble(case, tables, n_systems=0)
     with pytest.raises(InvalidCaseError):
         E.Ensemble(case, tables, n_systems=4, device=99)
+
+
+def _permuted_case_dict(d, order):
+    """The same universe with its particles listed in another order (the reference's tests/test_order.rs builds such
+    universes in code): particles, evolvers and Kahan residuals move together, ids and host indices follow."""
+    import copy
+    d = copy.deepcopy(d)
+    u = d["universe"]
+    n = u["n_particles"]
+    assert sorted(order) == list(range(n))
+    for key in ("particles", "particles_evolvers"):
+        u[key][:n] = [u[key][i] for i in order]
+    for key in ("inertial_velocity_errors", "particle_angular_momentum_errors", "particles_alternative_coordinates"):
+        d[key][:n] = [d[key][i] for i in order]
+    for new, p in enumerate(u["particles"][:n]):
+        p["id"] = new
+    inv = {old: new for new, old in enumerate(order)}
+    for key, v in list(u["hosts"]["index"].items()):
+        if v < n:
+            u["hosts"]["index"][key] = inv[v]
+    return d
+
+
+@pytest.mark.parametrize("fixture", ["test_integrator-whfast_jacobi", "test_integrator-whfast_democraticheliocentric",
+                                     "test_integrator-whfast_whds"])
+@pytest.mark.parametrize("order", [(1, 2, 0, 3, 4), (4, 3, 2, 1, 0)])
+def test_host_not_at_index_zero(E, fixture, order):
+    """the most massive body anywhere in the particle list (reference tests/test_order.rs). The Jacobi
+    hierarchy, the 'first planet' of the ignored gravity terms and the ordered sums all follow the list order with the
+    host removed. Strict mode: bit-identical to the oracle; fast mode: 1e-12 after the fixture's 199 steps."""
+    from oracle.binding import OracleSystem
+    from posidonius_b200 import abi
+    from posidonius_b200.case import case_from_dict
+    d = _permuted_case_dict(load_json_gz(_MANIFEST["fixtures"][fixture]["case"]), order)
+    case, tables = case_from_dict(d)
+    assert case.host_most_massive == order.index(0) != 0
+    o = OracleSystem(case, tables)
+    assert o.initialize_physical_values() == 0
+    assert o.iterate(10 ** 6) == 199
+    want = o.case()
+    for arithmetic in (abi.ARITH_STRICT, abi.ARITH_FAST):
+        with E.Ensemble(case, tables, n_systems=6, arithmetic=arithmetic) as ens:
+            ens.initialize_physical_values()
+            ens.iterate(10 ** 6)
+            st, w, it = ens.status()
+            assert np.all(st == abi.STATUS_COMPLETED) and np.all(it == 199)
+            got = ens.get_case(5)
+        for i in range(case.n_particles):
+            for key in ("inertial_position", "inertial_velocity", "angular_momentum", "spin"):
+                a, b = np.array(getattr(got.bodies[i], key)[:]), np.array(getattr(want.bodies[i], key)[:])
+                if arithmetic == abi.ARITH_STRICT:
+                    assert np.array_equal(a, b), (fixture, order, i, key, a, b)
+                else:
+                    assert np.all(np.abs(a - b) <= 1e-12 * max(np.linalg.norm(b), 1e-300)), (fixture, order, i, key, a, b)
