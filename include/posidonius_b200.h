@@ -237,7 +237,7 @@ int pb200_ensemble_set_snapshot_periods(pb200_ensemble_t* e, double historic_sna
  * reference's operation order. PB200_ARITH_FAST (default): FMA contraction, reciprocal reuse, hoisted constants —
  * results agree with the reference to roundoff-growth level. PB200_ARITH_STRICT: the forces too are
  * evaluated operation by operation as the reference writes them; the whole step is then bit-reproducible against the
- * CPU restatement of the reference, at about half the throughput. */
+ * CPU restatement of the reference (every GR variant, any particle order), at about 0.3x the throughput. */
 #define PB200_ARITH_FAST 0
 #define PB200_ARITH_STRICT 1
 int pb200_ensemble_set_arithmetic(pb200_ensemble_t* e, int mode);

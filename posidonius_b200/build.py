@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libposidonius_b200.so")
 SOURCES = ["pb200_api.cu", "host/case_io.cpp"]
 CLI = os.path.join(HERE, "bin", "posidonius-b200")
-HEADERS = ["host/json_min.hpp", "host/cli.cpp", "strict.cuh", "whfast_kernel.cuh", "dyn_effects.cuh", "forces_fast.cuh", "gr_variants.cuh", "strict_effects.cuh", "whfast_step.cuh"]
+HEADERS = ["host/json_min.hpp", "host/cli.cpp", "strict.cuh", "whfast_kernel.cuh", "dyn_effects.cuh", "forces_fast.cuh", "gr_variants.cuh", "strict_effects.cuh", "strict_gr_variants.cuh", "whfast_step.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--fmad=true", "-Xptxas", "-v",

@@ -346,9 +346,12 @@ static cudaError_t launch_n8(pb200_ensemble* e, unsigned grid, unsigned long lon
 template <int COORD>
 static cudaError_t launch_gr(pb200_ensemble* e, unsigned grid, unsigned long long n) {
     if (e->arithmetic == PB200_ARITH_STRICT) {
-        // the strict forces exist for Kidder1995 / no GR (pb200_ensemble_set_arithmetic rejects the other variants)
-        if (e->gr == PB200_GR_KIDDER1995) return launch_one<COORD, PB200_GR_KIDDER1995, 1>(e, grid, n);
-        return launch_one<COORD, PB200_GR_DISABLED, 1>(e, grid, n);
+        switch (e->gr) {
+            case PB200_GR_KIDDER1995: return launch_one<COORD, PB200_GR_KIDDER1995, 1>(e, grid, n);
+            case PB200_GR_ANDERSON1975: return launch_one<COORD, PB200_GR_ANDERSON1975, 1>(e, grid, n);
+            case PB200_GR_NEWHALL1983: return launch_one<COORD, PB200_GR_NEWHALL1983, 1>(e, grid, n);
+            default: return launch_one<COORD, PB200_GR_DISABLED, 1>(e, grid, n);
+        }
     }
     switch (e->gr) {
         case PB200_GR_KIDDER1995: return launch_one<COORD, PB200_GR_KIDDER1995, 0>(e, grid, n);
@@ -697,8 +700,6 @@ int pb200_ensemble_set_snapshot_periods(pb200_ensemble_t* e, double historic, do
 int pb200_ensemble_set_arithmetic(pb200_ensemble_t* e, int mode) {
     if (!e) return set_error(PB200_E_INVALID, "null ensemble");
     if (mode != PB200_ARITH_FAST && mode != PB200_ARITH_STRICT) return set_error(PB200_E_INVALID, "unknown arithmetic mode");
-    if (mode == PB200_ARITH_STRICT && (e->gr == PB200_GR_ANDERSON1975 || e->gr == PB200_GR_NEWHALL1983))
-        return set_error(PB200_E_UNSUPPORTED, "PB200_ARITH_STRICT covers GR Kidder1995 (or no GR); Anderson1975 / Newhall1983 run in PB200_ARITH_FAST");
     e->arithmetic = mode;
     return PB200_OK;
 }

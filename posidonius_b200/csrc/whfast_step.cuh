@@ -6,6 +6,7 @@
 // shuffles (every lane carries the running sum, so all lanes hold bit-identical copies).
 #include "gr_variants.cuh"
 #include "strict_effects.cuh"
+#include "strict_gr_variants.cuh"
 
 namespace PB_NS {
 using namespace pb200;
@@ -141,9 +142,15 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
                 Lane qq = q;
                 qq.r = strict(cold.get3(S_RX));
                 V3 acc_newton = cold.get3(S_AX);
-                if (GR == PB200_GR_ANDERSON1975) gr_anderson1975(P, ro, cold, gb, hl, b, qq, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
-                else gr_newhall1983(P, ro, cold, gb, hl, b, qq, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
-                a = a + ag;
+                if (ARITH) {
+                    if (GR == PB200_GR_ANDERSON1975) gr_anderson1975_strict(P, ro, cold, b, qq, hr_s, strict(acc_newton), COORD == PB200_COORD_JACOBI, ag);
+                    else gr_newhall1983_strict(P, ro, cold, b, qq, hr_s, strict(acc_newton), COORD == PB200_COORD_JACOBI, ag);
+                    a = plain(strict(a) + strict(ag));
+                } else {
+                    if (GR == PB200_GR_ANDERSON1975) gr_anderson1975(P, ro, cold, gb, hl, b, qq, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
+                    else gr_newhall1983(P, ro, cold, gb, hl, b, qq, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
+                    a = a + ag;
+                }
             }
         }
         // final = orig + (dt * a - err)   (whfast.rs:353-378), with the previous final for the convergence test

@@ -117,13 +117,35 @@ def test_strict_mode_golden_fixtures_bit_exact(E):
                     assert got == want, (name, i, key, got, want)
 
 
-def test_strict_mode_rejects_unported_gr_variants(E):
+@pytest.mark.parametrize("name", ["test_general_relativity-anderson1975", "test_general_relativity-newhall1983"])
+def test_strict_mode_gr_variants_bit_identical(E, name):
+    """Anderson1975 / Newhall1983 in PB200_ARITH_STRICT (strict_gr_variants.cuh): the golden vectors and the oracle's whole
+    state bit for bit, also for perturbed members over 1000 steps."""
+    from oracle.binding import run_ensemble
     from posidonius_b200 import abi
-    from posidonius_b200.case import UnsupportedCaseError, case_from_dict
-    fx = _MANIFEST["fixtures"]["test_general_relativity-newhall1983"]
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import make_ensemble_cases
+    fx = _MANIFEST["fixtures"][name]
     case, tables = case_from_dict(load_json_gz(fx["case"]))
-    with pytest.raises(UnsupportedCaseError):
-        E.Ensemble(case, tables, arithmetic=abi.ARITH_STRICT)
+    with E.Ensemble(case, tables, n_systems=3, arithmetic=abi.ARITH_STRICT) as ens:
+        ens.initialize_physical_values()
+        ens.iterate(10 ** 6)
+        out = ens.get_case(2)
+        for i, exp in enumerate(fx["particles"]):
+            for key in ("inertial_position", "inertial_velocity", "inertial_acceleration"):
+                got = list(getattr(out.bodies[i], key)[:])
+                want = [exp[key]["x"], exp[key]["y"], exp[key]["z"]]
+                assert got == want, (name, i, key, got, want)
+    case.time_limit = 1.0e6
+    cases = make_ensemble_cases(case, 10, 11)
+    with E.Ensemble(cases, tables, arithmetic=abi.ARITH_STRICT) as ens:
+        ens.initialize_physical_values()
+        ens.iterate(1000)
+        g = gpu_state_of(ens)
+    oc, _, _ = run_ensemble(cases, 10, tables, 1000, True, 4)
+    o = oracle_state_of(oc)
+    for k in ("position", "velocity", "angular_momentum", "spin", "velocity_errors", "angular_momentum_errors"):
+        assert np.array_equal(g[k], o[k]), (name, k, rel_err(g[k], o[k]))
 
 
 def test_energy_and_angular_momentum_drift_match_oracle(E):
