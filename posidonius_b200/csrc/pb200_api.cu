@@ -228,6 +228,41 @@ __global__ void perturb_kernel(const __grid_constant__ KParams P, const __grid_c
         }
 }
 
+// One system's image gathered into a contiguous staging buffer (pb200_ensemble_get_case: one copy instead of ~100):
+// per body 27 doubles [pos3 vel3 acc3 L3 spin3 verr3 lerr3 | radius rg2 moi | lag pair_h pair_p], then the Roche table
+// (n x n), then t, last_hist, and iteration / n_hist / tswarn as bit patterns.
+#define PB_GATHER_PER_BODY 27
+__global__ void gather_case_kernel(const __grid_constant__ KParams P, size_t s, const double* roche, double* out) {
+    const size_t ns = (size_t)P.n_sys;
+    const int n = P.n_bodies;
+    const size_t cs = (size_t)n * ns;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int item = threadIdx.x; item < n * PB_GATHER_PER_BODY; item += blockDim.x) {
+        const int b = item / PB_GATHER_PER_BODY, f = item % PB_GATHER_PER_BODY;
+        const size_t i = (size_t)b * ns + s;
+        double v;
+        if (f < 21) {
+            const double* arr[7] = {P.pos, P.vel, P.acc, P.L, P.spin, P.verr, P.lerr};
+            v = arr[f / 3][(size_t)(f % 3) * cs + i];
+        } else if (f == 21) v = P.radius[i];
+        else if (f == 22) v = P.rg2[i];
+        else if (f == 23) v = P.moi[i];
+        else if (f == 24) v = (P.flags & FLAG_DYN) ? P.lag[i] : 0.;
+        else if (f == 25) v = (P.flags & FLAG_DYN) ? P.pair_h[i] : nan;
+        else v = (P.flags & FLAG_DYN) ? P.pair_p[i] : nan;
+        out[item] = v;
+    }
+    double* tail = out + n * PB_GATHER_PER_BODY;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) tail[i] = roche[(size_t)i * ns + s];
+    if (threadIdx.x == 0) {
+        double* sys = tail + n * n;
+        sys[0] = P.t[s]; sys[1] = P.last_hist[s];
+        sys[2] = __longlong_as_double((long long)P.iteration[s]);
+        sys[3] = __longlong_as_double((long long)P.n_hist[s]);
+        sys[4] = __longlong_as_double((long long)P.tswarn[s]);
+    }
+}
+
 // DFMA chain microbenchmark: 8 independent chains per thread.
 __global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
     double x0 = threadIdx.x * 1e-9, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
@@ -263,6 +298,7 @@ struct pb200_ensemble {
     double *d_mass = nullptr, *d_mass_g = nullptr, *d_sigma = nullptr, *d_k2t = nullptr, *d_k2f = nullptr, *d_roche = nullptr;
     double *d_energy = nullptr, *d_angmom = nullptr;
     double *d_wind_k = nullptr, *d_wind_sat = nullptr, *d_diss = nullptr, *d_diss_scale = nullptr;
+    double* d_gather = nullptr;   // staging of pb200_ensemble_get_case
     unsigned int* d_records = nullptr;
     size_t records_capacity = 0;
     double recovery_snapshot_period = 0.;
@@ -861,29 +897,30 @@ int pb200_ensemble_get_case(pb200_ensemble_t* e, size_t s, pb200_case_t* out) {
     out->time_limit = e->P.time_limit;
     out->historic_snapshot_period = e->P.hist_period;
     out->recovery_snapshot_period = e->recovery_snapshot_period;
-    const size_t ns = e->n_sys, nb = (size_t)e->n_bodies;
-    auto get = [&](const void* dev, size_t index, void* dst, size_t bytes) -> cudaError_t {
-        return cudaMemcpy(dst, (const char*)dev + index * bytes, bytes, cudaMemcpyDeviceToHost);
-    };
+    const size_t nb = (size_t)e->n_bodies;
+    const size_t count = nb * PB_GATHER_PER_BODY + nb * nb + 5;
+    if (!e->d_gather) { int rc = dev_alloc(e, &e->d_gather, (size_t)PB200_MAX_PARTICLES * PB_GATHER_PER_BODY + PB200_MAX_PARTICLES * PB200_MAX_PARTICLES + 5); if (rc != PB200_OK) return rc; }
+    gather_case_kernel<<<1, 128, 0, e->stream>>>(e->P, s, e->d_roche, e->d_gather);
+    e->launches++;
+    CUDA_TRY(cudaGetLastError());
+    std::vector<double> g(count);
+    CUDA_TRY(cudaMemcpyAsync(g.data(), e->d_gather, count * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
     for (size_t b = 0; b < nb; b++) {
         pb200_body_t& B = out->bodies[b];
+        const double* v = g.data() + b * PB_GATHER_PER_BODY;
         for (int c = 0; c < 3; c++) {
-            size_t i = ((size_t)c * nb + b) * ns + s;
-            CUDA_TRY(get(e->P.pos, i, &B.inertial_position[c], 8)); CUDA_TRY(get(e->P.vel, i, &B.inertial_velocity[c], 8));
-            CUDA_TRY(get(e->P.acc, i, &B.inertial_acceleration[c], 8)); CUDA_TRY(get(e->P.L, i, &B.angular_momentum[c], 8));
-            CUDA_TRY(get(e->P.spin, i, &B.spin[c], 8));
-            CUDA_TRY(get(e->P.verr, i, &out->inertial_velocity_errors[b][c], 8));
-            CUDA_TRY(get(e->P.lerr, i, &out->particle_angular_momentum_errors[b][c], 8));
+            B.inertial_position[c] = v[c]; B.inertial_velocity[c] = v[3 + c]; B.inertial_acceleration[c] = v[6 + c];
+            B.angular_momentum[c] = v[9 + c]; B.spin[c] = v[12 + c];
+            out->inertial_velocity_errors[b][c] = v[15 + c]; out->particle_angular_momentum_errors[b][c] = v[18 + c];
         }
-        size_t i = b * ns + s;
-        CUDA_TRY(get(e->P.radius, i, &B.radius, 8)); CUDA_TRY(get(e->P.rg2, i, &B.radius_of_gyration_2, 8));
-        CUDA_TRY(get(e->P.moi, i, &B.moment_of_inertia, 8));
+        B.radius = v[21]; B.radius_of_gyration_2 = v[22]; B.moment_of_inertia = v[23];
         if (e->P.flags & FLAG_DYN) {
-            CUDA_TRY(get(e->P.lag, i, &B.tides_lag_angle, 8));
+            B.tides_lag_angle = v[24];
             const int hid = out->bodies[e->P.host].id;
             if ((int)b != e->P.host && B.id >= 0 && B.id < PB200_MAX_PARTICLES && hid >= 0 && hid < PB200_MAX_PARTICLES) {
-                CUDA_TRY(get(e->P.pair_h, i, &out->pair_dependent_scaled_dissipation_factor[hid * PB200_MAX_PARTICLES + B.id], 8));
-                CUDA_TRY(get(e->P.pair_p, i, &out->pair_dependent_scaled_dissipation_factor[B.id * PB200_MAX_PARTICLES + hid], 8));
+                out->pair_dependent_scaled_dissipation_factor[hid * PB200_MAX_PARTICLES + B.id] = v[25];
+                out->pair_dependent_scaled_dissipation_factor[B.id * PB200_MAX_PARTICLES + hid] = v[26];
             }
         }
     }
@@ -897,13 +934,15 @@ int pb200_ensemble_get_case(pb200_ensemble_t* e, size_t s, pb200_case_t* out) {
                 out->bodies[b].heliocentric_velocity[c] = (int)b == e->P.host ? 0. : out->bodies[b].inertial_velocity[c] - H.inertial_velocity[c];
             }
     }
-    for (size_t i = 0; i < nb * nb; i++) CUDA_TRY(get(e->d_roche, i * ns + s, &out->roche_radiuses[i], 8));
-    unsigned long long u;
-    CUDA_TRY(get(e->P.t, s, &out->current_time, 8));
-    CUDA_TRY(get(e->P.last_hist, s, &out->last_historic_snapshot_time, 8));
-    CUDA_TRY(get(e->P.iteration, s, &u, 8)); out->current_iteration = u;
-    CUDA_TRY(get(e->P.n_hist, s, &u, 8)); out->n_historic_snapshots = u;
-    CUDA_TRY(get(e->P.tswarn, s, &u, 8)); out->timestep_warning = u;
+    const double* tail = g.data() + nb * PB_GATHER_PER_BODY;
+    for (size_t i = 0; i < nb * nb; i++) out->roche_radiuses[i] = tail[i];
+    const double* sysv = tail + nb * nb;
+    out->current_time = sysv[0];
+    out->last_historic_snapshot_time = sysv[1];
+    uint64_t u;
+    std::memcpy(&u, &sysv[2], 8); out->current_iteration = u;
+    std::memcpy(&u, &sysv[3], 8); out->n_historic_snapshots = u;
+    std::memcpy(&u, &sysv[4], 8); out->timestep_warning = u;
     return PB200_OK;
 }
 
