@@ -348,11 +348,14 @@ static unsigned plan_pieces(unsigned grid, unsigned slots, unsigned long long n_
 
 template <class K>
 static cudaError_t launch_sliced(pb200_ensemble* e, K kernel, int& configured_device, int& blocks_per_sm, unsigned grid, unsigned long long n) {
+    // PB200_SMEM_PAD_KB (experiments only): extra dynamic shared memory per CTA, to lower the residency of the same binary
+    static const size_t pad = []() { const char* v = getenv("PB200_SMEM_PAD_KB"); return v ? (size_t)atoi(v) * 1024 : (size_t)0; }();
+    const size_t smem = PB_SMEM_BYTES + pad;
     if (configured_device != e->device) {
         // the cold slots need more than the default 48 KB of dynamic shared memory
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM_BYTES);
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, PB_BLOCK, PB_SMEM_BYTES);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, PB_BLOCK, smem);
         if (err != cudaSuccess) return err;
         configured_device = e->device;
     }
@@ -362,7 +365,7 @@ static cudaError_t launch_sliced(pb200_ensemble* e, K kernel, int& configured_de
         cudaError_t err = cudaMemsetAsync(e->P.sched, 0, (size_t)(grid + 1) * sizeof(unsigned int), e->stream);
         if (err != cudaSuccess) return err;
     }
-    kernel<<<grid * e->P.n_pieces, PB_BLOCK, PB_SMEM_BYTES, e->stream>>>(e->P, n);
+    kernel<<<grid * e->P.n_pieces, PB_BLOCK, smem, e->stream>>>(e->P, n);
     return cudaGetLastError();
 }
 
