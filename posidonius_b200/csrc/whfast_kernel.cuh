@@ -356,6 +356,7 @@ enum ColdSlot : int {
     M_0, M_1, M_2, M_3, M_4, M_5, M_6, M_7,
     N_COLD_SLOTS,
     E_S = X_11,   // fast mode: X_11, D_2, D_3 as a triple (host spin exchange)
+    K_ROCHE2 = M_7,   // max over j > b of the squared Roche radius of the pair (b, j): the cheap pre-test of gravity()
     // fast mode: 13 GR polynomial coefficients overlay the strict-mode slots (never live together)
     G_0 = Z_0
 };

@@ -216,7 +216,11 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
 template <int COORD>
 __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const Cold& cold, int gb, int b, size_t sys, const Lane& q, int& fail) {
     S3 acc = s3(sd(0.), sd(0.), sd(0.));
-    const double q_m = cold.get(K_M), q_R = cold.get(K_R);
+    const double q_R = cold.get(K_R);
+    // upper bound of this body's squared Roche radii (K_ROCHE2, set when the CTA starts): the table itself stays in global
+    // memory and is read only when a pair comes that close — no global load in the step loop, so the L1 that the
+    // shared-memory carve-out leaves (28 KB at 12 warps/SM) does not matter
+    const double roche_max2 = cold.get(K_ROCHE2);
     const int n = PB_N(P);
     const int first_other = PB_HOST(P) == 0 ? 1 : 0;
     fail = 0;
@@ -233,9 +237,11 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const C
         S3 d = q.r - rj;
         sd d2 = d.x * d.x + d.y * d.y + d.z * d.z;
         if (b < j) {
-            double rr = __ldg(P.roche + ((size_t)(b * n + j)) * (size_t)P.n_sys + sys);
             double rs = __dadd_rn(q_R, Rj);
-            if (d2.v <= __dmul_rn(rr, rr)) { if (!fail) fail = PB200_STATUS_ROCHE_DESTROYED; }
+            if (d2.v <= roche_max2) {
+                const double rr = __ldg(P.roche + ((size_t)(b * n + j)) * (size_t)P.n_sys + sys);
+                if (d2.v <= __dmul_rn(rr, rr)) { if (!fail) fail = PB200_STATUS_ROCHE_DESTROYED; }
+            }
             if (d2.v <= __dmul_rn(rs, rs)) { if (!fail) fail = PB200_STATUS_COLLISION; }
             if (b == PB_HOST(P) && d2.v > kMaxDistance2) { if (!fail) fail = PB200_STATUS_EJECTED; }
         }
@@ -254,7 +260,7 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const C
 #define PB_STEP_BARRIER 1   // +2 % at block 64 x 5, +5 % at 128 x 3 (profiles/r1_variants.md)
 #endif
 #ifndef PB_MIN_BLOCKS
-#define PB_MIN_BLOCKS 5   // 64 x 5: 167 registers/thread, 10 warps/SM, no spills (measured best: profiles/r1_variants.md)
+#define PB_MIN_BLOCKS 5   // code-generation hint only: <= 168 registers/thread, no spills; six CTAs (12 warps) are resident (profiles/r1_variants.md)
 #endif
 #ifdef PB_MAXNREG
 #define PB_KERNEL_ATTR __launch_bounds__(PB_BLOCK) __maxnreg__(PB_MAXNREG)
@@ -330,6 +336,15 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
             st.t = 0.; st.last_hist = 0.; st.tswarn = true; st.status = PB200_STATUS_COMPLETED; st.warnings = 0; st.hist_count = 0;
         }
         st.steps_done = 0; st.n_hist_new = 0; st.event_step = 0;
+    }
+    {
+        double rmax2 = 0.;
+        if (ro.valid)
+            for (int j = b + 1; j < n; j++) {
+                const double rr = __ldg(P.roche + ((size_t)(b * n + j)) * (size_t)P.n_sys + sys);
+                rmax2 = fmax(rmax2, __dmul_rn(rr, rr));
+            }
+        cold.set(K_ROCHE2, rmax2);
     }
     bool alive = sys_ok && st.status == PB200_STATUS_OK;
     if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
