@@ -38,13 +38,17 @@ __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, c
     cold.set(C_INVM, 1. / m);
     const double mgs = Mg + mg;
     cold.set(C_MGS, gg * mgs);                                     // gated: A = mgs / (r^2 c^2) vanishes for non-GR lanes
-    cold.set(C_FA, gg * (kG * kInvC2));                            // G / c^2 of the 1.5PN terms, gated
-    cold.set(C_GRF, Mg * mg / (mgs * mgs));                       // general_relativity.rs:98
-    cold.set(C_MURED, (M * m) / (M + m));                         // general_relativity.rs:383
-    cold.set(C_MD, M - m);                                        // mass_factor * star_planet_mass (:319-321, 336)
-    cold.set(C_MOM, m / M);
-    cold.set(C_FMS, 2. + 1.5 * m / M);                            // :390
-    cold.set(C_FMP, 2. + 1.5 * M / m);                            // :419
+    // 1.5PN spin-orbit terms (general_relativity.rs:300-456) in terms of the spins (L = I w), G / c^2 and the role gate folded in:
+    //   mass_factor * (Lp / m - Ls / M) = Z - S with S = Ls + Lp and Z = (M / m) Lp + (m / M) Ls, so the three vectors of the
+    //   acceleration are 2S + msf = S + Z, 3S + msf = 2S + Z and 7S + 3 msf = 4S + 3Z
+    const double fa = gg * (kG * kInvC2);
+    const double mured = (M * m) / (M + m);                       // general_relativity.rs:383
+    cold.set(C_MFA, fa * m);                                      // force = m * acceleration: the host gets -F / M, the planet F / m
+    cold.set(C_ZP, I * (M / m));
+    cold.set(C_ZH, Ih * (m / M));
+    cold.set(C_DP1, fa * I * ((2. + 1.5 * M / m) * mured));       // :419  dLp/dt: (2 + 3 M / 2m) Lorb x Lp
+    cold.set(C_DS1, fa * Ih * ((2. + 1.5 * m / M) * mured));      // :390  dLs/dt: (2 + 3 m / 2M) Lorb x Ls
+    cold.set(C_SXS, fa * I * Ih);                                 // Lp x Ls and the 3 (n.L)(n x L) terms
     // polynomials in the GR factor f of the 1PN / 2PN terms (general_relativity.rs:197-205, 256-268): per-system constants
     const double f = Mg * mg / (mgs * mgs), f2 = f * f;
     cold.set(G_0, 1.0 + 3.0 * f);
@@ -88,81 +92,76 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     // lag angle of the dynamical-tide models, once per step like the other evolving quantities (evolution.rs:548-567)
     if (evolve_now && (PB_FLAGS(P) & FLAG_DYN) && (PB_FLAGS(P) & FLAG_EVO)) { update_lag_angle(P, ro, b, sys, t, sd(w2), true); __syncwarp(); }
 #endif
-    double inv_d2 = inv_d * inv_d;
-    double d = dot(hr, hr) * inv_d;
-    double radvel = dot(hr, hv) * inv_d;
-    V3 rxv = cross(hr, hv);
-    V3 a_p = v3(0., 0., 0.), dl_p = v3(0., 0., 0.);       // this body's own acceleration / torque
-    V3 a_h = v3(0., 0., 0.), dl_h = v3(0., 0., 0.);       // contribution to the host
+    // Everything below is assembled as ONE force on the planet, F = Kr r + Kv v + (vector terms): the planet's acceleration is
+    // F / m, the host's -F / M (Q5: no indirect term), and the torques as coefficient sums over a small vector basis
+    // (r, r x v, r x w, (r x v) x w, w_p x w_s) - the effects share the cross products instead of rebuilding them.
+    const double inv_d2 = inv_d * inv_d, inv_d4 = inv_d2 * inv_d2;
+    const double radvel = dot(hr, hv) * inv_d;
+    const V3 rxv = cross(hr, hv);
+    const V3 cs = cross(hr, sh), cp = cross(hr, q.s);     // r x w_host, r x w_planet (fresh spins)
     const double inv_m = cold.get(C_INVM), inv_M = cold.getk(PB_HOST(P), C_INVM);
+    double Kr = 0., Kv = 0.;          // coefficients of r and v in F
+    double Pcp = 0., Hcs = 0.;        // coefficient of r x w_planet in dLp/dt, of r x w_host in the host's dL/dt
+    V3 F = v3(0., 0., 0.), dl_p = v3(0., 0., 0.), dl_h = v3(0., 0., 0.);
     if (PB_FLAGS(P) & FLAG_TIDES) {
         // constant_time_lag.rs:206-332, tides/common.rs:223-345
-        double inv_d4 = inv_d2 * inv_d2;
-        double inv_d7 = inv_d4 * inv_d2 * inv_d;
-        double Fos = cold.get(C_AS) * inv_d7;
-        double Fop = cold.get(C_AP) * inv_d7;
+        const double inv_d6 = inv_d4 * inv_d2, inv_d7 = inv_d6 * inv_d;
+        double FodS = cold.get(C_AS) * inv_d6;      // F_orth * r
+        double FodP = cold.get(C_AP) * inv_d6;
 #if !PB_FIXED_N
         if (PB_FLAGS(P) & FLAG_DYN) {
             sd sig_h, sig_p;
             pair_dependent_sigmas(P, ro, cold, hl, b, sys, strict(hr), strict(hv), sd(w2), sd(wh2), sig_h, sig_p);
-            Fos = cold.get(D_0) * sig_h.v * inv_d7;
-            Fop = cold.get(D_1) * sig_p.v * inv_d7;
+            FodS = cold.get(D_0) * sig_h.v * inv_d6;
+            FodP = cold.get(D_1) * sig_p.v * inv_d6;
         }
 #endif
-        double Fsum = Fos + Fop;
-        // radial: conservative + dissipative (-13.5 vr/r^8 (...) = -3 vr/r (Fos + Fop))
-        double f3 = -cold.get(C_BK) * inv_d7 - 2.0 * Fsum * radvel * inv_d;
-        V3 wxr_s = cross(sh, hr), wxr_p = cross(q.s, hr);
-        double k3 = f3 * inv_d, ks = Fos * inv_d, kp = Fop * inv_d;
-        V3 F = v3(k3 * hr.x + ks * (wxr_s.x - hv.x) + kp * (wxr_p.x - hv.x),
-                  k3 * hr.y + ks * (wxr_s.y - hv.y) + kp * (wxr_p.y - hv.y),
-                  k3 * hr.z + ks * (wxr_s.z - hv.z) + kp * (wxr_p.z - hv.z));
+        const double Fos = FodS * inv_d, Fop = FodP * inv_d;
+        const double ks = Fos * inv_d, kp = Fop * inv_d;
+        // radial: conservative + dissipative (-13.5 vr/r^8 (...) = -3 vr/r (Fos + Fop)), plus the radial part of the orthogonal one
+        Kr = -inv_d * (cold.get(C_BK) * inv_d7 + (2.0 * inv_d) * ((Fos + Fop) * radvel));
+        Kv = -(ks + kp);
+        // F_orth (w x r - v) = -F_orth (r x w) - F_orth v
+        F = v3(-(ks * cs.x + kp * cp.x), -(ks * cs.y + kp * cp.y), -(ks * cs.z + kp * cp.z));
         // torques (eqs 8-9 Bolmont+2015): N = Forth (d w - (r.w) r/d - (r x v)/d); dL/dt = -N
-        V3 Np = v3(Fop * (d * q.s.x - (rs_p * hr.x + rxv.x) * inv_d), Fop * (d * q.s.y - (rs_p * hr.y + rxv.y) * inv_d),
-                   Fop * (d * q.s.z - (rs_p * hr.z + rxv.z) * inv_d));
-        V3 Ns = v3(Fos * (d * sh.x - (rs_s * hr.x + rxv.x) * inv_d), Fos * (d * sh.y - (rs_s * hr.y + rxv.y) * inv_d),
-                   Fos * (d * sh.z - (rs_s * hr.z + rxv.z) * inv_d));
-        a_p = inv_m * F;
-        a_h = (-inv_M) * F;
-        dl_p = v3(-Np.x, -Np.y, -Np.z);
-        dl_h = v3(-Ns.x, -Ns.y, -Ns.z);
+        const double krp = kp * rs_p, krs = ks * rs_s;
+        dl_p = v3(krp * hr.x + kp * rxv.x - FodP * q.s.x, krp * hr.y + kp * rxv.y - FodP * q.s.y, krp * hr.z + kp * rxv.z - FodP * q.s.z);
+        dl_h = v3(krs * hr.x + ks * rxv.x - FodS * sh.x, krs * hr.y + ks * rxv.y - FodS * sh.y, krs * hr.z + ks * rxv.z - FodS * sh.z);
         if (tide_save && ro.valid) {
             // internals that calculate_denergy_dt (tides/common.rs:263-279) will read at the next snapshot; warp-uniform
             // branch, taken on the last step before a snapshot or the end of a launch only
             const size_t ns = (size_t)P.n_sys;
             double* ts = P.tide_scratch + (size_t)b * ns + sys;
-            const size_t cs = (size_t)PB_N(P) * ns;
-            ts[0 * cs] = hr.x; ts[1 * cs] = hr.y; ts[2 * cs] = hr.z;
-            ts[3 * cs] = hv.x; ts[4 * cs] = hv.y; ts[5 * cs] = hv.z;
-            ts[6 * cs] = d; ts[7 * cs] = radvel; ts[8 * cs] = Fop;
-            ts[9 * cs] = -3.0 * Fop * radvel * inv_d;  // dissipative radial part with the star as a point mass
-            ts[10 * cs] = -Np.x; ts[11 * cs] = -Np.y; ts[12 * cs] = -Np.z;
+            const size_t cs_ = (size_t)PB_N(P) * ns;
+            const double d = dot(hr, hr) * inv_d;
+            ts[0 * cs_] = hr.x; ts[1 * cs_] = hr.y; ts[2 * cs_] = hr.z;
+            ts[3 * cs_] = hv.x; ts[4 * cs_] = hv.y; ts[5 * cs_] = hv.z;
+            ts[6 * cs_] = d; ts[7 * cs_] = radvel; ts[8 * cs_] = Fop;
+            ts[9 * cs_] = -3.0 * Fop * radvel * inv_d;  // dissipative radial part with the star as a point mass
+            ts[10 * cs_] = dl_p.x; ts[11 * cs_] = dl_p.y; ts[12 * cs_] = dl_p.z;
         }
     }
     if (PB_FLAGS(P) & FLAG_FLAT) {
         // oblate_spheroid.rs:12-97, rotational_flattening/common.rs:165-237
-        double inv_d5 = inv_d2 * inv_d2 * inv_d;
-        double inv_d7 = inv_d5 * inv_d2;
-        double Ks = cold.get(C_KS);
-        double Kp = cold.get(C_KP);
-        double Fos = -Ks * rs_s * inv_d5;
-        double Fop = -Kp * rs_p * inv_d5;
-        double Frad = -0.5 * inv_d5 * (Ks * wh2 + Kp * w2) + 2.5 * inv_d7 * (Ks * rs_s * rs_s + Kp * rs_p * rs_p);
-        V3 F = v3(Frad * hr.x + Fop * q.s.x + Fos * sh.x, Frad * hr.y + Fop * q.s.y + Fos * sh.y, Frad * hr.z + Fop * q.s.z + Fos * sh.z);
-        V3 Np = Fop * cross(hr, q.s);
-        V3 Ns = Fos * cross(hr, sh);
-        a_p = a_p + inv_m * F;
-        a_h = a_h - inv_M * F;
-        dl_p = dl_p - Np;
-        dl_h = dl_h - Ns;
+        const double inv_d5 = inv_d4 * inv_d;
+        const double KsRs = cold.get(C_KS) * rs_s, KpRp = cold.get(C_KP) * rs_p;
+        const double Fos = -KsRs * inv_d5;
+        const double Fop = -KpRp * inv_d5;
+        const double q1 = cold.get(C_KS) * wh2 + cold.get(C_KP) * w2;
+        const double q2 = KsRs * rs_s + KpRp * rs_p;
+        Kr += inv_d5 * ((2.5 * inv_d2) * q2 - 0.5 * q1);
+        F = v3(F.x + Fop * q.s.x + Fos * sh.x, F.y + Fop * q.s.y + Fos * sh.y, F.z + Fop * q.s.z + Fos * sh.z);
+        // torques F_orth (r x w); dL/dt = -N
+        Pcp = -Fop;
+        Hcs = -Fos;
     }
-    if (GR == PB200_GR_KIDDER1995) {
+    if (GR == PB200_GR_KIDDER1995 && (PB_FLAGS(P) & FLAG_GR)) {
         // general_relativity.rs:177-456
-        double v2 = dot(hv, hv);
-        double mgs = cold.get(C_MGS);
-        double A = mgs * inv_d2 * kInvC2;
-        double u = mgs * inv_d;
-        double rv2 = radvel * radvel;
+        const double v2 = dot(hv, hv);
+        const double mgs = cold.get(C_MGS);
+        const double A = mgs * inv_d2 * kInvC2;
+        const double u = mgs * inv_d;
+        const double rv2 = radvel * radvel;
         // 1PN; the orthoradial term divides by |v| and multiplies by |v|: cancelled. Coefficients G_k: make_consts.
         double rad = -A * (cold.get(G_0) * v2 - cold.get(G_0 + 1) * u - cold.get(G_0 + 2) * rv2);
         double orth = A * cold.get(G_0 + 3) * radvel;
@@ -170,32 +169,37 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         rad += -A * (cold.get(G_0 + 4) * (u * u) + cold.get(G_0 + 5) * (v2 * v2) + cold.get(G_0 + 6) * (rv2 * rv2)
                      - cold.get(G_0 + 7) * rv2 * v2 - cold.get(G_0 + 8) * u * v2 - cold.get(G_0 + 9) * u * rv2);
         orth += 0.5 * A * radvel * (cold.get(G_0 + 10) * v2 - cold.get(G_0 + 11) * u - cold.get(G_0 + 12) * rv2);
-        double kr = rad * inv_d;
-        V3 a = v3(kr * hr.x + orth * hv.x, kr * hr.y + orth * hv.y, kr * hr.z + orth * hv.z);
-        // 1.5PN spin-orbit (:300-456); component-wise products exactly as the reference writes them
-        V3 Ls = cold.getk(PB_HOST(P), K_I) * sh, Lp = cold.get(K_I) * q.s;
-        V3 nn = inv_d * hr;
-        double md = cold.get(C_MD);
-        V3 msf = v3(md * (Lp.x * inv_m - Ls.x * inv_M), md * (Lp.y * inv_m - Ls.y * inv_M), md * (Lp.z * inv_m - Ls.z * inv_M));
-        V3 S = Ls + Lp;
-        V3 nxv = cross(nn, hv);
-        V3 e1 = v3(6. * nn.x * (nxv.x * (2. * S.x + msf.x)), 6. * nn.y * (nxv.y * (2. * S.y + msf.y)), 6. * nn.z * (nxv.z * (2. * S.z + msf.z)));
-        V3 e7 = v3(7. * S.x + 3. * msf.x, 7. * S.y + 3. * msf.y, 7. * S.z + 3. * msf.z);
-        V3 e2 = cross(hv, e7);
-        V3 e3s = v3(3. * S.x + msf.x, 3. * S.y + msf.y, 3. * S.z + msf.z);
-        V3 e3 = (3. * radvel) * cross(nn, e3s);
-        const double fa = cold.get(C_FA);
-        a = a + fa * (e1 - e2 + e3);
-        // Kidder 1995 eqs 2.4a, 2.4b
-        V3 Lo = cold.get(C_MURED) * rxv;
-        V3 LpxLs = cross(Lp, Ls);
-        V3 ds = cold.get(C_FMS) * cross(Lo, Ls) - LpxLs + (3. * dot(nn, Lp)) * cross(nn, Ls);
-        V3 dp = cold.get(C_FMP) * cross(Lo, Lp) + LpxLs + (3. * dot(nn, Ls)) * cross(nn, Lp);
-        a_p = a_p + a;
-        a_h = a_h - cold.get(C_MOM) * a;
-        dl_p = dl_p + fa * dp;
-        dl_h = dl_h + fa * ds;
+        const double m = cold.get(K_M);
+        Kr += m * (rad * inv_d);
+        Kv += m * orth;
+        // 1.5PN spin-orbit (:300-456) with n = r / d, n x v = (r x v) / d and the spin combinations of make_consts
+        const double Ip = cold.get(K_I), Ih = cold.getk(PB_HOST(P), K_I), zp = cold.get(C_ZP), zh = cold.get(C_ZH);
+        const V3 S = v3(Ip * q.s.x + Ih * sh.x, Ip * q.s.y + Ih * sh.y, Ip * q.s.z + Ih * sh.z);
+        const V3 Z = v3(zp * q.s.x + zh * sh.x, zp * q.s.y + zh * sh.y, zp * q.s.z + zh * sh.z);
+        const V3 A1 = S + Z;                                                   // 2S + msf
+        const V3 A3 = A1 + S;                                                  // 3S + msf
+        const V3 A7 = v3(3. * A1.x + S.x, 3. * A1.y + S.y, 3. * A1.z + S.z);   // 7S + 3 msf
+        const double mfa = cold.get(C_MFA);
+        const double s1 = 6. * mfa * inv_d2, s3 = 3. * mfa * (radvel * inv_d);
+        const V3 e2 = cross(hv, A7), e3 = cross(hr, A3);
+        F = v3(F.x + s1 * (hr.x * rxv.x * A1.x) - mfa * e2.x + s3 * e3.x,
+               F.y + s1 * (hr.y * rxv.y * A1.y) - mfa * e2.y + s3 * e3.y,
+               F.z + s1 * (hr.z * rxv.z * A1.z) - mfa * e2.z + s3 * e3.z);
+        // Kidder 1995 eqs 2.4a, 2.4b: dLs/dt = fms Lo x Ls - Lp x Ls + 3 (n.Lp) n x Ls, dLp/dt = fmp Lo x Lp + Lp x Ls + 3 (n.Ls) n x Lp
+        const double sxs_k = cold.get(C_SXS);
+        const double c3 = 3. * sxs_k * inv_d2;
+        Pcp += c3 * dot(hr, sh);
+        Hcs += c3 * dot(hr, q.s);
+        const V3 wxw = cross(q.s, sh), jp = cross(rxv, q.s), js = cross(rxv, sh);
+        const double dp1 = cold.get(C_DP1), ds1 = cold.get(C_DS1);
+        dl_p = v3(dl_p.x + dp1 * jp.x + sxs_k * wxw.x, dl_p.y + dp1 * jp.y + sxs_k * wxw.y, dl_p.z + dp1 * jp.z + sxs_k * wxw.z);
+        dl_h = v3(dl_h.x + ds1 * js.x - sxs_k * wxw.x, dl_h.y + ds1 * js.y - sxs_k * wxw.y, dl_h.z + ds1 * js.z - sxs_k * wxw.z);
     }
+    F = v3(F.x + Kr * hr.x + Kv * hv.x, F.y + Kr * hr.y + Kv * hv.y, F.z + Kr * hr.z + Kv * hv.z);
+    dl_p = v3(dl_p.x + Pcp * cp.x, dl_p.y + Pcp * cp.y, dl_p.z + Pcp * cp.z);
+    dl_h = v3(dl_h.x + Hcs * cs.x, dl_h.y + Hcs * cs.y, dl_h.z + Hcs * cs.z);
+    const V3 a_p = inv_m * F;
+    const V3 a_h = (-inv_M) * F;
     // lanes that are not orbiting bodies carry zero constants (make_consts): their terms vanish; reduce onto the host
     // Transposed reduction through the exchange columns: every lane leaves its six contributions, lane c adds component
     // c over the group (columns visited in rotated order: conflict-free banks), the host lane collects the six totals.

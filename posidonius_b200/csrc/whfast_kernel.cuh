@@ -341,7 +341,7 @@ enum ColdSlot : int {
     K_M, K_MG, K_R, K_I,
     // constants of the perturbation forces (every division with step-invariant operands is done once)
     // (host-body quantities — its mass, inertia, 1/M — are read from the host's own column with getk, they have no slot)
-    C_INVI, C_AS, C_AP, C_BK, C_KS, C_KP, C_INVM, C_MGS, C_GRF, C_MURED, C_MD, C_MOM, C_FMS, C_FMP, C_FA,
+    C_INVI, C_AS, C_AP, C_BK, C_KS, C_KP, C_INVM, C_MGS, C_MFA, C_ZP, C_ZH, C_DP1, C_DS1, C_SXS, C_SPARE,
     // constants of the coordinate transforms (strict)
     // The host's columns of the last three are meaningless for the host body itself and carry the per-system values:
     // K_ETAK <- total mass, K_BACKW <- refined reciprocal of the total mass, K_WHDSF <- refined reciprocal of the host
