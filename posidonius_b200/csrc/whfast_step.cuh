@@ -169,15 +169,15 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
             const V3 dl_old = cold.get3(S_DLX);
             const V3 Lf_old = v3(__dadd_rn(Lo.x, dl_old.x), __dadd_rn(Lo.y, dl_old.y), __dadd_rn(Lo.z, dl_old.z));
             V3 ddv = plain(vf - vf_old), ddl = Lf - Lf_old, vfp = plain(vf);
-            double s_dv = ro.valid ? dot(ddv, ddv) : 0., s_fv = ro.valid ? dot(vfp, vfp) : 0.;
-            s_dv = group_sum(s_dv, W); s_fv = group_sum(s_fv, W);
-            // delta/total < eps^2 decided as delta < eps^2 * total (no division; NaN compares false either way)
-            bool okv = s_dv < kEps2 * s_fv;
+            // delta/total < eps^2 decided as sum(delta_i - eps^2 total_i) < 0: one group sum per test, no division; NaN
+            // compares false either way. The two sides differ by factors of order one whenever an iterate moved by an ulp
+            // (delta_i = ulp^2 <= eps^2 v_i^2), so the rounding of the merged sum cannot flip the decision.
+            double c_v = ro.valid ? dot(ddv, ddv) - kEps2 * dot(vfp, vfp) : 0.;
+            bool okv = group_sum(c_v, W) < 0.;
             bool okl = true;
             if (PB_SPIN(P)) {
-                double s_dl = ro.valid ? dot(ddl, ddl) : 0., s_fl = ro.valid ? dot(Lf, Lf) : 0.;
-                s_dl = group_sum(s_dl, W); s_fl = group_sum(s_fl, W);
-                okl = s_dl < kEps2 * s_fl;
+                double c_l = ro.valid ? dot(ddl, ddl) - kEps2 * dot(Lf, Lf) : 0.;
+                okl = group_sum(c_l, W) < 0.;
             }
             conv_now = okv && okl;
         }
@@ -255,6 +255,65 @@ __device__ __forceinline__ S3 gravity(const KParams& P, const Roles& ro, const C
     }
     return acc;
 }
+
+#if PB_FIXED_N == 8
+// The same for exactly 8 bodies, host 0, democratic heliocentric coordinates: every unordered pair is evaluated ONCE.
+// -G / |d|^3 is symmetric in the pair bit for bit (the components of d change sign exactly, their squares and the order of
+// the sum do not), so planet b computes it for its next three neighbours on the ring of the seven planets, leaves it where
+// both members of the pair will look for it (own column and the partner's, slot = rank of the other body among the
+// partners in index order), and then accumulates its six terms in index order like the reference's inner loop — with the
+// same roundings as gravity() above. The pair's Roche / collision checks are done by the lane that computes the pair; the
+// host pairs (ignored by the acceleration, universe.rs:251-255) are checked by the planet. `code` packs (lower index,
+// higher index, status): the group-wide minimum is the first failing pair of the reference's loop order.
+__device__ __forceinline__ S3 gravity_n8_dh(const KParams& P, const Roles& ro, const Cold& cold, int b, size_t sys, const Lane& q, int& code) {
+    const double q_R = cold.get(K_R);
+    const double roche_max2 = cold.get(K_ROCHE2);
+    const bool pl = ro.planet;
+    const int bb = pl ? b : 1;   // host / padding lanes walk planet 1's pattern on their own (never published) values
+    code = 0x7fffffff;
+    auto check = [&](int lo, int hi, double d2, double Rj, bool host_pair) {
+        int fail = 0;
+        if (d2 <= roche_max2) {
+            const double rr = __ldg(P.roche + ((size_t)(lo * 8 + hi)) * (size_t)P.n_sys + sys);
+            if (d2 <= __dmul_rn(rr, rr)) fail = PB200_STATUS_ROCHE_DESTROYED;
+        }
+        const double rs = __dadd_rn(q_R, Rj);
+        if (!fail && d2 <= __dmul_rn(rs, rs)) fail = PB200_STATUS_COLLISION;
+        if (!fail && host_pair && d2 > kMaxDistance2) fail = PB200_STATUS_EJECTED;
+        if (fail && pl) { const int c = (lo << 8) | (hi << 4) | fail; code = c < code ? c : code; }
+    };
+    {
+        const S3 d = q.r - strict(cold.getk3(0, E_R));
+        const sd d2 = d.x * d.x + d.y * d.y + d.z * d.z;
+        check(0, bb, d2.v, cold.getk(0, K_R), true);
+    }
+#pragma unroll
+    for (int k = 1; k <= 3; k++) {
+        int j = bb + k; j = j > 7 ? j - 7 : j;
+        const S3 d = q.r - strict(cold.getk3(j, E_R));
+        const sd d2 = d.x * d.x + d.y * d.y + d.z * d.z;
+        check(bb < j ? bb : j, bb < j ? j : bb, d2.v, cold.getk(j, K_R), false);
+        const sd dist = ssqrt(d2);
+        const sd g = sd(-kG) / (dist * dist * dist);
+        if (pl) {
+            // rank of the partner among this body's partners (index order, 0-based), and of this body among the partner's
+            cold.set(E_A + (j > bb ? j - 2 : j - 1), g.v);
+            cold.grp[j + (E_A + (bb > j ? bb - 2 : bb - 1)) * PB_BLOCK] = g.v;
+        }
+    }
+    __syncwarp();
+    S3 acc = s3(sd(0.), sd(0.), sd(0.));
+#pragma unroll
+    for (int k = 1; k <= 6; k++) {
+        const int j = k + (k >= bb ? 1 : 0);
+        const sd pre = sd(cold.get(E_A + k - 1)) * sd(cold.getk(j, K_M));
+        const S3 d = q.r - strict(cold.getk3(j, E_R));
+        acc.x = acc.x + pre * d.x; acc.y = acc.y + pre * d.y; acc.z = acc.z + pre * d.z;
+    }
+    if (!pl) acc = s3(sd(0.), sd(0.), sd(0.));
+    return acc;
+}
+#endif
 
 #ifndef PB_STEP_BARRIER
 #define PB_STEP_BARRIER 1   // +2 % at block 64 x 5, +5 % at 128 x 3 (profiles/r1_variants.md)
@@ -340,8 +399,10 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
     {
         double rmax2 = 0.;
         if (ro.valid)
-            for (int j = b + 1; j < n; j++) {
-                const double rr = __ldg(P.roche + ((size_t)(b * n + j)) * (size_t)P.n_sys + sys);
+            for (int j = 0; j < n; j++) {
+                if (j == b) continue;
+                const int lo = b < j ? b : j, hi = b < j ? j : b;   // the table is filled for lo < hi (universe.rs:177-196)
+                const double rr = __ldg(P.roche + ((size_t)(lo * n + hi)) * (size_t)P.n_sys + sys);
                 rmax2 = fmax(rmax2, __dmul_rn(rr, rr));
             }
         cold.set(K_ROCHE2, rmax2);
@@ -596,9 +657,18 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         int fail;
                         cold.set3(E_R, plain(q.r));
                         __syncwarp();
-                        anew_s = gravity<COORD>(P, ro, cold, gb, b, sys, q, fail);
-                        // group-wide failure: lowest body index wins, like the reference's loop order
-                        int code = (ro.valid && fail) ? ((b << 4) | fail) : 0x7fffffff;
+                        int code;
+#if PB_FIXED_N == 8
+                        if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
+                            anew_s = gravity_n8_dh(P, ro, cold, b, sys, q, code);
+                            (void)fail;
+                        } else
+#endif
+                        {
+                            anew_s = gravity<COORD>(P, ro, cold, gb, b, sys, q, fail);
+                            // group-wide failure: lowest body index wins, like the reference's loop order
+                            code = (ro.valid && fail) ? ((b << 4) | fail) : 0x7fffffff;
+                        }
                         for (int off = W >> 1; off > 0; off >>= 1) { int o = __shfl_xor_sync(FULL, code, off); code = o < code ? o : code; }
                         const bool died = alive && code != 0x7fffffff;
                         if (alive) cold.set3(S_AX, plain(anew_s));
