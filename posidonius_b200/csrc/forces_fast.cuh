@@ -77,9 +77,9 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
                                                    V3& dl_out, bool tide_save) {
     const int W = PB_W(P);
     // Q3: r.omega uses the spins of the previous evaluation (universe.rs:429-430)
-    // (the host's spin travels through the exchange triple E_S: still the previous evaluation's here)
-    V3 s_host_prev = cold.getk3(PB_HOST(P), E_S);
-    double rs_s = dot(hr, s_host_prev), rs_p = dot(hr, q.s);
+    // The two dot products are carried from the previous evaluation (by-products of its spin-orbit terms: no reload of the
+    // host's previous spin); the midpoint sets them when the position has changed.
+    const double rs_s = q.rs_s, rs_p = q.rs_p;
     // calculate_spin (particles/common.rs:3-15)
     q.s = cold.get(C_INVI) * q.L;
     double w2 = dot(q.s, q.s);
@@ -88,6 +88,7 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     __syncwarp();
     V3 sh = cold.getk3(PB_HOST(P), E_S);
     double wh2 = cold.getk(PB_HOST(P), M_6);
+    q.rs_s = dot(hr, sh); q.rs_p = dot(hr, q.s);   // for the next evaluation (Q3) and the 3 (n.L)(n x L) terms below
 #if !PB_FIXED_N
     // lag angle of the dynamical-tide models, once per step like the other evolving quantities (evolution.rs:548-567)
     if (evolve_now && (PB_FLAGS(P) & FLAG_DYN) && (PB_FLAGS(P) & FLAG_EVO)) { update_lag_angle(P, ro, b, sys, t, sd(w2), true); __syncwarp(); }
@@ -188,8 +189,8 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         // Kidder 1995 eqs 2.4a, 2.4b: dLs/dt = fms Lo x Ls - Lp x Ls + 3 (n.Lp) n x Ls, dLp/dt = fmp Lo x Lp + Lp x Ls + 3 (n.Ls) n x Lp
         const double sxs_k = cold.get(C_SXS);
         const double c3 = 3. * sxs_k * inv_d2;
-        Pcp += c3 * dot(hr, sh);
-        Hcs += c3 * dot(hr, q.s);
+        Pcp += c3 * q.rs_s;
+        Hcs += c3 * q.rs_p;
         const V3 wxw = cross(q.s, sh), jp = cross(rxv, q.s), js = cross(rxv, sh);
         const double dp1 = cold.get(C_DP1), ds1 = cold.get(C_DS1);
         dl_p = v3(dl_p.x + dp1 * jp.x + sxs_k * wxw.x, dl_p.y + dp1 * jp.y + sxs_k * wxw.y, dl_p.z + dp1 * jp.z + sxs_k * wxw.z);

@@ -384,6 +384,7 @@ enum : int { E_A = S_VOX, E_B = S_LOX, E_C = S_DVX, E_D = S_DLX, E_R = S_RX };
 struct Lane {
     S3 r, v;            // inertial position / velocity (strict arithmetic only)
     V3 L, s;            // angular momentum, spin (of the previous evaluation)
+    double rs_s, rs_p;  // fast mode: r . w_host, r . w_planet with the spins of the previous evaluation (Q3)
 };
 __device__ __forceinline__ V3 plain(S3 a) { return v3(a.x.v, a.y.v, a.z.v); }
 __device__ __forceinline__ S3 strict(V3 a) { return s3(sd(a.x), sd(a.y), sd(a.z)); }

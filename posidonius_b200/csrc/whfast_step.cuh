@@ -114,6 +114,7 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
     const V3 hr = plain(hr_s);
     const double inv_d = ARITH ? 0. : rsqrt(dot(hr, hr));
     const sd dist_s = ARITH ? ssqrt(hr_s.x * hr_s.x + hr_s.y * hr_s.y + hr_s.z * hr_s.z) : sd(1.);   // universe.rs:328-330
+    if (!ARITH) { q.rs_s = dot(hr, cold.getk3(PB_HOST(P), E_S)); q.rs_p = dot(hr, q.s); }   // Q3: previous spins, new position
     bool done = !alive;  // group-uniform
     bool converged = false;
 #pragma unroll 1
@@ -127,7 +128,9 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
             if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
         }
         const S3 vh_s = ARITH ? shfl3(q.v, hl) : strict(cold.getk3(PB_HOST(P), M_0));
-        const S3 hv_s = ro.planet ? q.v - vh_s : s3(sd(0.), sd(1.), sd(0.));
+        // fast mode: the forces hold no division, and every term of a non-orbiting lane is multiplied by a zero constant
+        // (make_consts), so the host / padding lanes need no dummy velocity (six selects less per evaluation)
+        const S3 hv_s = (ARITH && !ro.planet) ? s3(sd(0.), sd(1.), sd(0.)) : q.v - vh_s;
         V3 hv = plain(hv_s);
         V3 a, dldt;
         // the tidal internals of a step's last evaluation are kept for the next snapshot's denergy_dt (`!done`: a converged
@@ -182,7 +185,9 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
             conv_now = okv && okl;
         }
         if (!done) {
-            cold.set3(S_DVX, plain(ndv)); if (PB_SPIN(P)) cold.set3(S_DLX, ndl);
+            // the increments of iteration 0 are never read (the convergence test starts at it = 2 with those of it = 1, the
+            // final update uses the last ones, and a live system always runs at least 3 iterations)
+            if (it > 0) { cold.set3(S_DVX, plain(ndv)); if (PB_SPIN(P)) cold.set3(S_DLX, ndl); }
             if (conv_now) { done = true; converged = true; }
             else {
                 // average (whfast.rs:453-466)
@@ -316,7 +321,7 @@ __device__ __forceinline__ S3 gravity_n8_dh(const KParams& P, const Roles& ro, c
 #endif
 
 #ifndef PB_STEP_BARRIER
-#define PB_STEP_BARRIER 1   // +2 % at block 64 x 5, +5 % at 128 x 3 (profiles/r1_variants.md)
+#define PB_STEP_BARRIER 0   // a block-wide barrier per step paid +2 % at 3 250 FP64 instructions per warp-step, costs 3 % at 2 700 (profiles/r1_variants.md)
 #endif
 #ifndef PB_MIN_BLOCKS
 #define PB_MIN_BLOCKS 5   // code-generation hint only: <= 168 registers/thread, no spills; six CTAs (12 warps) are resident (profiles/r1_variants.md)

@@ -46,8 +46,8 @@ def main():
     hdr = rows[1]
     ia, ie, isrc = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Source")
     base = None
-    outer = collections.defaultdict(lambda: [0, 0])
-    inner = collections.defaultdict(lambda: [0, 0])
+    outer = collections.defaultdict(lambda: [0, 0, 0, 0])
+    inner = collections.defaultdict(lambda: [0, 0, 0, 0])
     tot = [0, 0]
     for r in rows[2:]:
         try:
@@ -67,12 +67,16 @@ def main():
         o2 = step_frames[0] if step_frames else ch[0]
         outer["%s:%d" % o][f64] += ex
         inner["%s:%d" % o2][f64] += ex
+        smem = {"LDS": 2, "STS": 3}.get(op.split(".")[0])
+        if smem:
+            outer["%s:%d" % o][smem] += ex
+            inner["%s:%d" % o2][smem] += ex
         tot[f64] += ex
     print("per warp-step: %.0f instructions, %.0f FP64" % ((tot[0] + tot[1]) / warp_steps, tot[1] / warp_steps))
     for name, table in (("kernel-body call site (outermost whfast_step.cuh frame)", outer), ("innermost whfast_step.cuh frame", inner)):
-        print("\n%s: FP64 / other per warp-step" % name)
+        print("\n%s: FP64 / other (of which LDS, STS) per warp-step" % name)
         for k, v in sorted(table.items(), key=lambda kv: -(kv[1][0] + kv[1][1]))[:40]:
-            print("  %-28s %8.1f %8.1f" % (k, v[1] / warp_steps, v[0] / warp_steps))
+            print("  %-28s %8.1f %8.1f %8.1f %8.1f" % (k, v[1] / warp_steps, v[0] / warp_steps, v[2] / warp_steps, v[3] / warp_steps))
 
 
 if __name__ == "__main__":
