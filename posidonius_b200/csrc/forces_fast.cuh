@@ -83,7 +83,8 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     // calculate_spin (particles/common.rs:3-15)
     q.s = cold.get(C_INVI) * q.L;
     double w2 = dot(q.s, q.s);
-    __syncwarp();
+    // (no barrier before these stores: the group's last reads of E_S / M_6 lie before the previous evaluation's exchange
+    // barriers)
     cold.set3(E_S, q.s); cold.set(M_6, w2);
     __syncwarp();
     V3 sh = cold.getk3(PB_HOST(P), E_S);
@@ -204,7 +205,7 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     // lanes that are not orbiting bodies carry zero constants (make_consts): their terms vanish; reduce onto the host
     // Transposed reduction through the exchange columns: every lane leaves its six contributions, lane c adds component
     // c over the group (columns visited in rotated order: conflict-free banks), the host lane collects the six totals.
-    __syncwarp();   // the totals of the previous evaluation have been read
+    // (the totals of the previous evaluation and the host velocity in M_0 were read before the spin-exchange barrier above)
     cold.set3(M_0, a_h); cold.set3(M_3, dl_h);
     __syncwarp();
     for (int c = b; c < 6; c += W) {

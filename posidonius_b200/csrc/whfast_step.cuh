@@ -93,6 +93,32 @@ __device__ __forceinline__ S3 ordered_diff_others(const Cold& cold, S3 init, int
     return acc;
 }
 
+extern __shared__ double pb_smem[];
+
+// ---- Distributed ordered sums (8 bodies, host 0). The reference accumulates its sums over the bodies serially, so the
+// association order is fixed and every lane of the group used to walk all seven terms of all three components of every
+// sum itself (bit-identical copies, 21 LDS + 21 DADD per vector sum and lane). The SCALAR sums are independent of each
+// other, though: lane c of the group accumulates scalar c over the bodies in index order — same additions, same order,
+// same bits — applies the scalar's division, and leaves the result in one slot that the group reads back. Body k's term
+// of scalar c sits in column (k ^ c) of slot base + c, so that at every step of the walk the reducing lanes touch
+// different banks (a plain [scalar][body] layout would be a six-way bank conflict).
+#define PB_DIST (PB_FIXED_N == 8)
+__device__ __forceinline__ volatile double* dist_cell(int row, int k) { return (volatile double*)pb_smem + (row ^ k); }
+// The column indices are loop-invariant; left alone, the compiler hoists all of them out of the step loop into ~30
+// registers (and spills). An empty volatile asm makes the thread index opaque where it is used: one LOP3 per access instead.
+__device__ __forceinline__ int dist_tid() { int t = (int)threadIdx.x; asm volatile("" : "+r"(t)); return t; }
+__device__ __forceinline__ void dist_put(int base, int c, double v) { *dist_cell(dist_tid() + (base + c) * PB_BLOCK, c) = v; }
+__device__ __forceinline__ void dist_put3(int base, int c0, V3 v) { dist_put(base, c0, v.x); dist_put(base, c0 + 1, v.y); dist_put(base, c0 + 2, v.z); }
+// the row of the scalar this lane reduces (lanes beyond the last scalar repeat it; their results are never read)
+__device__ __forceinline__ int dist_row(int base, int b, int n_scalars) { return dist_tid() + (base + (b < n_scalars ? b : n_scalars - 1)) * PB_BLOCK; }
+// acc (+/-)= term of body 1, 2, ... 7 in index order
+template <bool SUB>
+__device__ __forceinline__ sd dist_walk(int row, sd acc) {
+#pragma unroll
+    for (int k = 1; k < 8; k++) { const sd t = sd(*dist_cell(row, k)); acc = SUB ? acc - t : acc + t; }
+    return acc;
+}
+
 // Implicit midpoint on v and L (whfast.rs:322-466) around Universe::calculate_additional_effects.
 // Registers across the evaluation: v, L, spin, heliocentric position and 1/r. Originals, increments and Kahan
 // residuals sit in the cold slots and are touched once per iteration.
@@ -333,8 +359,6 @@ __device__ __forceinline__ S3 gravity_n8_dh(const KParams& P, const Roles& ro, c
 #endif
 #define PB_SMEM_BYTES (N_COLD_SLOTS * PB_BLOCK * sizeof(double))
 
-extern __shared__ double pb_smem[];
-
 template <int COORD, int GR, int ARITH>
 __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
     const int W = PB_W(P);
@@ -446,6 +470,11 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
     }
     const int first_other = PB_HOST(P) == 0 ? 1 : 0;
     const sd zero = sd(0.), one = sd(1.);
+#ifdef PB_NO_DIST
+    constexpr bool DIST = false;
+#else
+    constexpr bool DIST = PB_DIST && COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC;   // distributed ordered sums (8-body build)
+#endif
     const S3 zero3 = s3(zero, zero, zero);
     const S3 one3 = s3(one, one, one);
 
@@ -525,6 +554,9 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                 rM.b = M_s.v; rM.y = cold.getk(PB_HOST(P), K_WHDSF); rT.b = mtot.v; rT.y = cold.getk(PB_HOST(P), K_BACKW);
                 S3 apos, avel;       // this body's alternative coordinates
                 S3 spos, svel;       // the host slot of the alternative coordinates (centre of mass), replicated in the group
+                // 8-body build: the scalar of (spos, svel) this lane owns (lane 0-2: spos, 3-5: svel) and, for lanes 0-2, the
+                // matching component of svel; spos itself is not kept
+                sd my_com = zero, my_sv = zero;
                 S3 anew_s = zero3;
                 const bool kwork = ro.planet && alive;
                 // ---- inertial -> alternative coordinates (whfast.rs:881-1023)
@@ -551,11 +583,23 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                 } else {
                     // host first, then the others (whfast.rs:986-995)
                     S3 mr = q.r * m_s, mv = q.v * m_s;
+                    if (DIST) {
+                        // scalars 0-2: sum m r / M_tot (centre of mass), 3-5: sum m v / M_tot; lane c owns scalar c for the step
+                        dist_put3(E_A, 0, plain(mr)); dist_put3(E_A, 3, plain(mv)); cold.set3(E_R, plain(q.r));
+                        __syncwarp();
+                        const int row = dist_row(E_A, b, 6);
+                        my_com = dist_walk<false>(row, zero + sd(*dist_cell(row, 0))) / rT;
+                        cold.set(M_0, my_com.v);
+                        __syncwarp();
+                        svel = strict(v3(cold.getk(3, M_0), cold.getk(4, M_0), cold.getk(5, M_0)));
+                        my_sv = sd(cold.getk(b < 3 ? b + 3 : 3, M_0));
+                    } else {
                     cold.set3(E_A, plain(mr)); cold.set3(E_B, plain(mv)); cold.set3(E_R, plain(q.r));
                     __syncwarp();
                     S3 sr = ordered_sum_others(cold, zero3 + strict(cold.getk3(PB_HOST(P), E_A)), E_A, n, PB_HOST(P));
                     S3 sv = ordered_sum_others(cold, zero3 + strict(cold.getk3(PB_HOST(P), E_B)), E_B, n, PB_HOST(P));
                     spos = sr / rT; svel = sv / rT;
+                    }
                     apos = q.r - strict(cold.getk3(PB_HOST(P), E_R));
                     avel = q.v - svel;
                     if (COORD == PB200_COORD_WHDS) avel = avel * sd(cold.get(K_WHDSF));
@@ -601,10 +645,18 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     for (int jump_slot = 0; jump_slot < 2; jump_slot++) {
                         if (jump_slot == 1) {
                             kepler_step(kwork, apos, avel, sd(cold.get(K_KMU)), hdt_s, st.tswarn, st.warnings);
-                            spos = spos + hdt_s * svel;
+                            if (DIST) { if (b < 3) my_com = my_com + hdt_s * my_sv; }
+                            else spos = spos + hdt_s * svel;
                         }
                         if (COORD != PB200_COORD_JACOBI && jump_slot != phase) {
-                            if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
+                            if (DIST) {
+                                dist_put3(E_C, 0, plain(m_s * avel));
+                                __syncwarp();
+                                const sd p = dist_walk<false>(dist_row(E_C, b, 3), zero);
+                                cold.set(M_0, (hdt_s * p / rM).v);
+                                __syncwarp();
+                                apos = s3(apos.x + sd(cold.getk(0, M_0)), apos.y + sd(cold.getk(1, M_0)), apos.z + sd(cold.getk(2, M_0)));
+                            } else if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
                                 cold.set3(E_C, plain(m_s * avel));
                                 __syncwarp();
                                 S3 p = ordered_sum_others(cold, zero3, E_C, n, PB_HOST(P));
@@ -643,6 +695,22 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         S3 num = ro.planet ? apos * m_s : one3;
                         S3 term = num / rT;
                         const S3 vterm = avel * sd(cold.get(K_BACKW));
+                        if (DIST) {
+                            // scalars 0-2: star position, 3-5: star velocity (read in the second pass only)
+                            dist_put3(E_C, 0, plain(term));
+                            if (phase == 1) dist_put3(E_C, 3, plain(vterm));
+                            __syncwarp();
+                            cold.set(M_0, dist_walk<true>(dist_row(E_C, b, 6), my_com).v);
+                            __syncwarp();
+                            const S3 star_r = strict(v3(cold.getk(0, M_0), cold.getk(1, M_0), cold.getk(2, M_0)));
+                            const S3 nr = ro.host ? star_r : apos + star_r;
+                            if (alive) q.r = nr;
+                            if (phase == 1) {
+                                S3 nv = avel + svel;
+                                if (ro.host) nv = strict(v3(cold.getk(3, M_0), cold.getk(4, M_0), cold.getk(5, M_0)));
+                                if (alive) q.v = nv;
+                            }
+                        } else {
                         cold.set3(E_D, plain(term));
                         if (phase == 1) cold.set3(E_A, plain(vterm));
                         __syncwarp();
@@ -655,6 +723,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                             S3 star_v = ordered_diff_others(cold, svel, E_A, n, PB_HOST(P));
                             if (ro.host) nv = star_v;
                             if (alive) q.v = nv;
+                        }
                         }
                     }
                     if (phase == 0) {

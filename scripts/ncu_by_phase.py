@@ -2,7 +2,7 @@
 """Executed warp-instructions of the step kernel by CALL SITE in the kernel body (outermost frame of nvdisasm's inline
 chains) and by the innermost function, split into FP64 and other instructions.
 
-usage: ncu_by_phase.py report.ncu-rep libposidonius_b200.so 'kernel-substring' warp_steps
+usage: ncu_by_phase.py report.ncu-rep libposidonius_b200.so 'kernel-substring' warp_steps [outer-frame file:line -> opcode histogram of that phase]
 """
 import collections
 import csv
@@ -17,6 +17,8 @@ import tempfile
 def main():
     rep, so, kern = sys.argv[1:4]
     warp_steps = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
+    focus = sys.argv[5] if len(sys.argv) > 5 else None
+    ophist = collections.Counter()
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
     cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin") and "case_io" not in f][0]
@@ -72,6 +74,10 @@ def main():
             outer["%s:%d" % o][smem] += ex
             inner["%s:%d" % o2][smem] += ex
         tot[f64] += ex
+        if focus and "%s:%d" % o == focus:
+            ophist[op.split(".")[0]] += ex
+    if focus:
+        print("opcodes inside %s per warp-step: " % focus + ", ".join("%s %.1f" % (k, v / warp_steps) for k, v in ophist.most_common(25)))
     print("per warp-step: %.0f instructions, %.0f FP64" % ((tot[0] + tot[1]) / warp_steps, tot[1] / warp_steps))
     for name, table in (("kernel-body call site (outermost whfast_step.cuh frame)", outer), ("innermost whfast_step.cuh frame", inner)):
         print("\n%s: FP64 / other (of which LDS, STS) per warp-step" % name)
