@@ -6,6 +6,22 @@
 namespace PB_NS {
 using namespace pb200;
 
+extern __shared__ double pb_smem[];
+
+// ---- Distributed ordered sums (8 bodies, host 0). The reference accumulates its sums over the bodies serially, so the
+// association order is fixed and every lane of the group used to walk all seven terms of all three components of every
+// sum itself (bit-identical copies, 21 LDS + 21 DADD per vector sum and lane). The SCALAR sums are independent of each
+// other, though: lane c of the group accumulates scalar c over the bodies in index order — same additions, same order,
+// same bits — applies the scalar's division, and leaves the result in one slot that the group reads back. Body k's term
+// of scalar c sits in column (k ^ c) of slot base + c, so that at every step of the walk the reducing lanes touch
+// different banks (a plain [scalar][body] layout would be a six-way bank conflict).
+#define PB_DIST (PB_FIXED_N == 8)
+__device__ __forceinline__ volatile double* dist_cell(int row, int k) { return (volatile double*)pb_smem + (row ^ k); }
+// The column indices are loop-invariant; left alone, the compiler hoists all of them out of the step loop into ~30
+// registers (and spills). An empty volatile asm makes the thread index opaque where it is used: one LOP3 per access instead.
+__device__ __forceinline__ int dist_tid() { int t = (int)threadIdx.x; asm volatile("" : "+r"(t)); return t; }
+__device__ __forceinline__ void dist_put(int base, int c, double v) { *dist_cell(dist_tid() + (base + c) * PB_BLOCK, c) = v; }
+__device__ __forceinline__ void dist_put3(int base, int c0, V3 v) { dist_put(base, c0, v.x); dist_put(base, c0 + 1, v.y); dist_put(base, c0 + 2, v.z); }
 // Derives the force constants from masses, radii and dissipation parameters (cold path: launch start and whenever a
 // radius evolves). sigma / k2 are fetched from global memory here, they are not kept on chip.
 __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys) {
@@ -208,19 +224,21 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     // (the totals of the previous evaluation and the host velocity in M_0 were read before the spin-exchange barrier above)
     cold.set3(M_0, a_h); cold.set3(M_3, dl_h);
     __syncwarp();
+#if PB_FIXED_N == 8
+    if (b < 6) {
+        // lane c adds component c: columns visited in XOR order (body b ^ j at step j: conflict-free banks, one LOP3 per address)
+        const int row = dist_tid() + (M_0 + b) * PB_BLOCK;
+        const double x0 = *dist_cell(row, 0), x1 = *dist_cell(row, 1), x2 = *dist_cell(row, 2), x3 = *dist_cell(row, 3),
+                     x4 = *dist_cell(row, 4), x5 = *dist_cell(row, 5), x6 = *dist_cell(row, 6), x7 = *dist_cell(row, 7);
+        *dist_cell(row, 0) = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));   // only this lane reads column b of slot M_0 + b: no hazard
+    }
+#else
     for (int c = b; c < 6; c += W) {
-        double t;
-        if (PB_FIXED_N == 8) {
-            const double x0 = cold.getk(b, M_0 + c), x1 = cold.getk((b + 1) & 7, M_0 + c), x2 = cold.getk((b + 2) & 7, M_0 + c),
-                         x3 = cold.getk((b + 3) & 7, M_0 + c), x4 = cold.getk((b + 4) & 7, M_0 + c), x5 = cold.getk((b + 5) & 7, M_0 + c),
-                         x6 = cold.getk((b + 6) & 7, M_0 + c), x7 = cold.getk((b + 7) & 7, M_0 + c);
-            t = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
-        } else {
-            t = 0.;
-            for (int j = 0; j < W; j++) t += cold.getk((j + b) & (W - 1), M_0 + c);
-        }
+        double t = 0.;
+        for (int j = 0; j < W; j++) t += cold.getk((j + b) & (W - 1), M_0 + c);
         cold.set(M_0 + c, t);   // only this lane reads column b of slot M_0 + c: no hazard
     }
+#endif
     __syncwarp();
     a_out = a_p; dl_out = dl_p;
     if (ro.host) {

@@ -251,7 +251,6 @@ __device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu_i
 #pragma unroll 1
         for (int k = 1; k < 32; k++) {
             if (!__any_sync(FULL, active)) break;
-#ifdef PB_KEPLER_INPLACE
             // The G-functions and 1/r are evaluated in place: a lane that has finished (or never worked) re-evaluates them at
             // the x they were computed from (old_x) and gets the same bits back, instead of every lane copying eight doubles
             // under a predicate on every pass.
@@ -265,18 +264,6 @@ __device__ __forceinline__ void kepler_step(bool work, S3& pos, S3& vel, sd mu_i
                 old_x = x; x = xn;
                 if (x.v == old_x.v || x.v == old_x2.v) { converged = true; active = false; }
             }
-#else
-            sd h0, h1, h2, h3;
-            stiefel_gs3(beta, x, h0, h1, h2, h3);
-            sd e = eta0 * h1 + zeta0 * h2;
-            sd rin = sd(1.) / (r0 + e);
-            sd xn = rin * (x * e - eta0 * h2 - zeta0 * h3 + dt);
-            if (active) {
-                sd old_x2 = old_x;
-                old_x = x; x = xn; ri = rin; g0 = h0; g1 = h1; g2 = h2; g3 = h3;
-                if (x.v == old_x.v || x.v == old_x2.v) { converged = true; active = false; }
-            }
-#endif
         }
     }
     const bool bisect = work && !converged;

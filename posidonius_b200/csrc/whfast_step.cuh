@@ -93,22 +93,7 @@ __device__ __forceinline__ S3 ordered_diff_others(const Cold& cold, S3 init, int
     return acc;
 }
 
-extern __shared__ double pb_smem[];
-
-// ---- Distributed ordered sums (8 bodies, host 0). The reference accumulates its sums over the bodies serially, so the
-// association order is fixed and every lane of the group used to walk all seven terms of all three components of every
-// sum itself (bit-identical copies, 21 LDS + 21 DADD per vector sum and lane). The SCALAR sums are independent of each
-// other, though: lane c of the group accumulates scalar c over the bodies in index order — same additions, same order,
-// same bits — applies the scalar's division, and leaves the result in one slot that the group reads back. Body k's term
-// of scalar c sits in column (k ^ c) of slot base + c, so that at every step of the walk the reducing lanes touch
-// different banks (a plain [scalar][body] layout would be a six-way bank conflict).
-#define PB_DIST (PB_FIXED_N == 8)
-__device__ __forceinline__ volatile double* dist_cell(int row, int k) { return (volatile double*)pb_smem + (row ^ k); }
-// The column indices are loop-invariant; left alone, the compiler hoists all of them out of the step loop into ~30
-// registers (and spills). An empty volatile asm makes the thread index opaque where it is used: one LOP3 per access instead.
-__device__ __forceinline__ int dist_tid() { int t = (int)threadIdx.x; asm volatile("" : "+r"(t)); return t; }
-__device__ __forceinline__ void dist_put(int base, int c, double v) { *dist_cell(dist_tid() + (base + c) * PB_BLOCK, c) = v; }
-__device__ __forceinline__ void dist_put3(int base, int c0, V3 v) { dist_put(base, c0, v.x); dist_put(base, c0 + 1, v.y); dist_put(base, c0 + 2, v.z); }
+// ---- Distributed ordered sums: see the layout notes next to dist_cell (forces_fast.cuh).
 // the row of the scalar this lane reduces (lanes beyond the last scalar repeat it; their results are never read)
 __device__ __forceinline__ int dist_row(int base, int b, int n_scalars) { return dist_tid() + (base + (b < n_scalars ? b : n_scalars - 1)) * PB_BLOCK; }
 // acc (+/-)= term of body 1, 2, ... 7 in index order
