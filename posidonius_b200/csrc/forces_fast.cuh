@@ -6,7 +6,7 @@
 namespace PB_NS {
 using namespace pb200;
 
-extern __shared__ double pb_smem[];
+extern __shared__ __align__(16) double pb_smem[];
 
 // ---- Distributed ordered sums (8 bodies, host 0). The reference accumulates its sums over the bodies serially, so the
 // association order is fixed and every lane of the group used to walk all seven terms of all three components of every
@@ -22,6 +22,19 @@ __device__ __forceinline__ volatile double* dist_cell(int row, int k) { return (
 __device__ __forceinline__ int dist_tid() { int t = (int)threadIdx.x; asm volatile("" : "+r"(t)); return t; }
 __device__ __forceinline__ void dist_put(int base, int c, double v) { *dist_cell(dist_tid() + (base + c) * PB_BLOCK, c) = v; }
 __device__ __forceinline__ void dist_put3(int base, int c0, V3 v) { dist_put(base, c0, v.x); dist_put(base, c0 + 1, v.y); dist_put(base, c0 + 2, v.z); }
+#ifdef PB_GPAIR
+// The 13 GR polynomial coefficients as 16-byte cells [pair][thread][2] inside their 13-slot region: one LDS.128 fetches two
+// of them (same shared-memory wavefronts, half the instructions).
+__device__ __forceinline__ volatile double2* gpair_cell(int p) {
+    return reinterpret_cast<volatile double2*>(pb_smem + G_0 * PB_BLOCK) + (p * PB_BLOCK + (int)threadIdx.x);
+}
+__device__ __forceinline__ void gpair_set(int p, double a, double b) { volatile double2* c = gpair_cell(p); c->x = a; c->y = b; }
+__device__ __forceinline__ double2 gpair_get(int p) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared((const void*)gpair_cell(p))));
+    return v;
+}
+#endif
 // Derives the force constants from masses, radii and dissipation parameters (cold path: launch start and whenever a
 // radius evolves). sigma / k2 are fetched from global memory here, they are not kept on chip.
 __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys) {
@@ -67,6 +80,15 @@ __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, c
     cold.set(C_SXS, fa * I * Ih);                                 // Lp x Ls and the 3 (n.L)(n x L) terms
     // polynomials in the GR factor f of the 1PN / 2PN terms (general_relativity.rs:197-205, 256-268): per-system constants
     const double f = Mg * mg / (mgs * mgs), f2 = f * f;
+#ifdef PB_GPAIR
+    gpair_set(0, 1.0 + 3.0 * f, 2.0 * (2.0 + f));
+    gpair_set(1, 1.5 * f, 2.0 * (2.0 - f));
+    gpair_set(2, 0.75 * (12.0 + 29.0 * f), f * (3.0 - 4.0 * f));
+    gpair_set(3, 1.875 * f * (1.0 - 3.0 * f), 1.5 * f * (3.0 - 4.0 * f));
+    gpair_set(4, 0.5 * f * (13.0 - 4.0 * f), 2.0 + 25.0 * f + 2.0 * f2);
+    gpair_set(5, f * (15.0 + 4.0 * f), 4.0 + 41.0 * f + 8.0 * f2);
+    cold.set(G_0 + 12, 3.0 * f * (3.0 + 2.0 * f));
+#else
     cold.set(G_0, 1.0 + 3.0 * f);
     cold.set(G_0 + 1, 2.0 * (2.0 + f));
     cold.set(G_0 + 2, 1.5 * f);
@@ -80,6 +102,7 @@ __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, c
     cold.set(G_0 + 10, f * (15.0 + 4.0 * f));
     cold.set(G_0 + 11, 4.0 + 41.0 * f + 8.0 * f2);
     cold.set(G_0 + 12, 3.0 * f * (3.0 + 2.0 * f));
+#endif
     __syncwarp();   // the host's column (1/M, inertia) is read by the other lanes
 }
 
@@ -181,12 +204,20 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         const double u = mgs * inv_d;
         const double rv2 = radvel * radvel;
         // 1PN; the orthoradial term divides by |v| and multiplies by |v|: cancelled. Coefficients G_k: make_consts.
+#ifdef PB_GPAIR
+        const double2 g01 = gpair_get(0), g23 = gpair_get(1), g45 = gpair_get(2), g67 = gpair_get(3), g89 = gpair_get(4), gab = gpair_get(5);
+        double rad = -A * (g01.x * v2 - g01.y * u - g23.x * rv2);
+        double orth = A * g23.y * radvel;
+        rad += -A * (g45.x * (u * u) + g45.y * (v2 * v2) + g67.x * (rv2 * rv2) - g67.y * rv2 * v2 - g89.x * u * v2 - g89.y * u * rv2);
+        orth += 0.5 * A * radvel * (gab.x * v2 - gab.y * u - cold.get(G_0 + 12) * rv2);
+#else
         double rad = -A * (cold.get(G_0) * v2 - cold.get(G_0 + 1) * u - cold.get(G_0 + 2) * rv2);
         double orth = A * cold.get(G_0 + 3) * radvel;
         // 2PN (Kidder 1995 eq. 2.2d)
         rad += -A * (cold.get(G_0 + 4) * (u * u) + cold.get(G_0 + 5) * (v2 * v2) + cold.get(G_0 + 6) * (rv2 * rv2)
                      - cold.get(G_0 + 7) * rv2 * v2 - cold.get(G_0 + 8) * u * v2 - cold.get(G_0 + 9) * u * rv2);
         orth += 0.5 * A * radvel * (cold.get(G_0 + 10) * v2 - cold.get(G_0 + 11) * u - cold.get(G_0 + 12) * rv2);
+#endif
         const double m = cold.get(K_M);
         Kr += m * (rad * inv_d);
         Kv += m * orth;
