@@ -6,7 +6,7 @@
 namespace PB_NS {
 using namespace pb200;
 
-extern __shared__ __align__(16) double pb_smem[];
+extern __shared__ __align__(128) double pb_smem[];   // 64-byte aligned groups of 8 columns: dist_ld / dist_st flip address bits 3-5
 
 // ---- Distributed ordered sums (8 bodies, host 0). The reference accumulates its sums over the bodies serially, so the
 // association order is fixed and every lane of the group used to walk all seven terms of all three components of every
@@ -16,25 +16,25 @@ extern __shared__ __align__(16) double pb_smem[];
 // of scalar c sits in column (k ^ c) of slot base + c, so that at every step of the walk the reducing lanes touch
 // different banks (a plain [scalar][body] layout would be a six-way bank conflict).
 #define PB_DIST (PB_FIXED_N == 8)
-__device__ __forceinline__ volatile double* dist_cell(int row, int k) { return (volatile double*)pb_smem + (row ^ k); }
-// The column indices are loop-invariant; left alone, the compiler hoists all of them out of the step loop into ~30
-// registers (and spills). An empty volatile asm makes the thread index opaque where it is used: one LOP3 per access instead.
-__device__ __forceinline__ int dist_tid() { int t = (int)threadIdx.x; asm volatile("" : "+r"(t)); return t; }
-__device__ __forceinline__ void dist_put(int base, int c, double v) { *dist_cell(dist_tid() + (base + c) * PB_BLOCK, c) = v; }
-__device__ __forceinline__ void dist_put3(int base, int c0, V3 v) { dist_put(base, c0, v.x); dist_put(base, c0 + 1, v.y); dist_put(base, c0 + 2, v.z); }
-#ifdef PB_GPAIR
-// The 13 GR polynomial coefficients as 16-byte cells [pair][thread][2] inside their 13-slot region: one LDS.128 fetches two
-// of them (same shared-memory wavefronts, half the instructions).
-__device__ __forceinline__ volatile double2* gpair_cell(int p) {
-    return reinterpret_cast<volatile double2*>(pb_smem + G_0 * PB_BLOCK) + (p * PB_BLOCK + (int)threadIdx.x);
+// A "row" is the shared-memory BYTE address of this thread's column in a slot; body (b ^ k)'s column is row ^ (k << 3): one
+// LOP3 per access (the dynamic shared memory is 128-byte aligned, a group's eight columns are one aligned 64-byte line).
+// The addresses are loop-invariant; left alone, the compiler hoists all of them out of the step loop into ~30 registers
+// (and spills). An empty volatile asm makes the thread's own address opaque where it is used.
+__device__ __forceinline__ unsigned dist_self(const Cold& cold) {
+    unsigned a = (unsigned)__cvta_generic_to_shared((const void*)cold.base);
+    asm volatile("" : "+r"(a));
+    return a;
 }
-__device__ __forceinline__ void gpair_set(int p, double a, double b) { volatile double2* c = gpair_cell(p); c->x = a; c->y = b; }
-__device__ __forceinline__ double2 gpair_get(int p) {
-    double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"((unsigned)__cvta_generic_to_shared((const void*)gpair_cell(p))));
+__device__ __forceinline__ double dist_ld(unsigned row, int k) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(row ^ (unsigned)(k << 3)) : "memory");
     return v;
 }
-#endif
+__device__ __forceinline__ void dist_st(unsigned row, int k, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" : : "r"(row ^ (unsigned)(k << 3)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void dist_put(const Cold& cold, int base, int c, double v) { dist_st(dist_self(cold) + (unsigned)((base + c) * PB_BLOCK * 8), c, v); }
+__device__ __forceinline__ void dist_put3(const Cold& cold, int base, int c0, V3 v) { dist_put(cold, base, c0, v.x); dist_put(cold, base, c0 + 1, v.y); dist_put(cold, base, c0 + 2, v.z); }
 // Derives the force constants from masses, radii and dissipation parameters (cold path: launch start and whenever a
 // radius evolves). sigma / k2 are fetched from global memory here, they are not kept on chip.
 __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys) {
@@ -54,55 +54,39 @@ __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, c
     // Disabled role) carries zeros, so the force code needs no per-lane branches or selects.
     const double gt = ro.t_on ? 1. : 0., gf = ro.f_on ? 1. : 0., gg = ro.g_on ? 1. : 0.;
     const double gts = P.tides_host_central ? gt : 0., gfs = P.flat_host_central ? gf : 0.;
-    cold.set(C_AS, gts * (4.5 * m2 * (Rh5 * Rh5) * sig_h));         // 4.5 m^2 R*^10 sigma*   (constant_time_lag.rs:232-234)
-    cold.set(C_AP, gt * (4.5 * M2 * (R5 * R5) * sigma));            // 4.5 M^2 R^10 sigma     (constant_time_lag.rs:243-245)
-    cold.set(C_BK, gt * (3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * k2t))); // 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2) (:283-285)
+    cold.set2(C_AS, 0, gts * (4.5 * m2 * (Rh5 * Rh5) * sig_h),      // 4.5 m^2 R*^10 sigma*   (constant_time_lag.rs:232-234)
+                       gt * (4.5 * M2 * (R5 * R5) * sigma));         // 4.5 M^2 R^10 sigma     (constant_time_lag.rs:243-245)
+    const double c_bk = gt * (3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * k2t));   // 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2) (:283-285)
 #if !PB_FIXED_N
     // dynamical tides: the same constants without sigma (the pair-dependent sigma multiplies them per evaluation)
     cold.set(D_0, gts * (4.5 * m2 * (Rh5 * Rh5)));
     cold.set(D_1, gt * (4.5 * M2 * (R5 * R5)));
 #endif
-    cold.set(C_KS, gfs * (m * k2f_h * Rh5));                        // flattening: m k2f* R*^5 (oblate_spheroid.rs:37)
-    cold.set(C_KP, gf * (M * k2f * R5));                            //             M k2f R^5   (oblate_spheroid.rs:42)
+    cold.set2(C_AS, 1, gfs * (m * k2f_h * Rh5),                     // flattening: m k2f* R*^5 (oblate_spheroid.rs:37)
+                       gf * (M * k2f * R5));                        //             M k2f R^5   (oblate_spheroid.rs:42)
     cold.set(C_INVM, 1. / m);
     const double mgs = Mg + mg;
-    cold.set(C_MGS, gg * mgs);                                     // gated: A = mgs / (r^2 c^2) vanishes for non-GR lanes
+    cold.set2(C_AS, 5, c_bk, gg * mgs);                            // gated: A = mgs / (r^2 c^2) vanishes for non-GR lanes
     // 1.5PN spin-orbit terms (general_relativity.rs:300-456) in terms of the spins (L = I w), G / c^2 and the role gate folded in:
     //   mass_factor * (Lp / m - Ls / M) = Z - S with S = Ls + Lp and Z = (M / m) Lp + (m / M) Ls, so the three vectors of the
     //   acceleration are 2S + msf = S + Z, 3S + msf = 2S + Z and 7S + 3 msf = 4S + 3Z
     const double fa = gg * (kG * kInvC2);
     const double mured = (M * m) / (M + m);                       // general_relativity.rs:383
-    cold.set(C_MFA, fa * m);                                      // force = m * acceleration: the host gets -F / M, the planet F / m
-    cold.set(C_ZP, I * (M / m));
-    cold.set(C_ZH, Ih * (m / M));
-    cold.set(C_DP1, fa * I * ((2. + 1.5 * M / m) * mured));       // :419  dLp/dt: (2 + 3 M / 2m) Lorb x Lp
-    cold.set(C_DS1, fa * Ih * ((2. + 1.5 * m / M) * mured));      // :390  dLs/dt: (2 + 3 m / 2M) Lorb x Ls
-    cold.set(C_SXS, fa * I * Ih);                                 // Lp x Ls and the 3 (n.L)(n x L) terms
+    cold.set2(C_AS, 2, I * (M / m), Ih * (m / M));                // Z = zp w_p + zh w_s
+    cold.set2(C_AS, 3, fa * I * ((2. + 1.5 * M / m) * mured),     // :419  dLp/dt: (2 + 3 M / 2m) Lorb x Lp
+                       fa * Ih * ((2. + 1.5 * m / M) * mured));   // :390  dLs/dt: (2 + 3 m / 2M) Lorb x Ls
+    cold.set2(C_AS, 4, fa * m,                                    // force = m * acceleration: the host gets -F / M, the planet F / m
+                       fa * I * Ih);                              // Lp x Ls and the 3 (n.L)(n x L) terms
     // polynomials in the GR factor f of the 1PN / 2PN terms (general_relativity.rs:197-205, 256-268): per-system constants
     const double f = Mg * mg / (mgs * mgs), f2 = f * f;
-#ifdef PB_GPAIR
-    gpair_set(0, 1.0 + 3.0 * f, 2.0 * (2.0 + f));
-    gpair_set(1, 1.5 * f, 2.0 * (2.0 - f));
-    gpair_set(2, 0.75 * (12.0 + 29.0 * f), f * (3.0 - 4.0 * f));
-    gpair_set(3, 1.875 * f * (1.0 - 3.0 * f), 1.5 * f * (3.0 - 4.0 * f));
-    gpair_set(4, 0.5 * f * (13.0 - 4.0 * f), 2.0 + 25.0 * f + 2.0 * f2);
-    gpair_set(5, f * (15.0 + 4.0 * f), 4.0 + 41.0 * f + 8.0 * f2);
+    // 13 polynomial coefficients: six pair cells and a single
+    cold.set2(G_0, 0, 1.0 + 3.0 * f, 2.0 * (2.0 + f));
+    cold.set2(G_0, 1, 1.5 * f, 2.0 * (2.0 - f));
+    cold.set2(G_0, 2, 0.75 * (12.0 + 29.0 * f), f * (3.0 - 4.0 * f));
+    cold.set2(G_0, 3, 1.875 * f * (1.0 - 3.0 * f), 1.5 * f * (3.0 - 4.0 * f));
+    cold.set2(G_0, 4, 0.5 * f * (13.0 - 4.0 * f), 2.0 + 25.0 * f + 2.0 * f2);
+    cold.set2(G_0, 5, f * (15.0 + 4.0 * f), 4.0 + 41.0 * f + 8.0 * f2);
     cold.set(G_0 + 12, 3.0 * f * (3.0 + 2.0 * f));
-#else
-    cold.set(G_0, 1.0 + 3.0 * f);
-    cold.set(G_0 + 1, 2.0 * (2.0 + f));
-    cold.set(G_0 + 2, 1.5 * f);
-    cold.set(G_0 + 3, 2.0 * (2.0 - f));
-    cold.set(G_0 + 4, 0.75 * (12.0 + 29.0 * f));
-    cold.set(G_0 + 5, f * (3.0 - 4.0 * f));
-    cold.set(G_0 + 6, 1.875 * f * (1.0 - 3.0 * f));
-    cold.set(G_0 + 7, 1.5 * f * (3.0 - 4.0 * f));
-    cold.set(G_0 + 8, 0.5 * f * (13.0 - 4.0 * f));
-    cold.set(G_0 + 9, 2.0 + 25.0 * f + 2.0 * f2);
-    cold.set(G_0 + 10, f * (15.0 + 4.0 * f));
-    cold.set(G_0 + 11, 4.0 + 41.0 * f + 8.0 * f2);
-    cold.set(G_0 + 12, 3.0 * f * (3.0 + 2.0 * f));
-#endif
     __syncwarp();   // the host's column (1/M, inertia) is read by the other lanes
 }
 
@@ -141,14 +125,16 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     const V3 rxv = cross(hr, hv);
     const V3 cs = cross(hr, sh), cp = cross(hr, q.s);     // r x w_host, r x w_planet (fresh spins)
     const double inv_m = cold.get(C_INVM), inv_M = cold.getk(PB_HOST(P), C_INVM);
+    const double2 bk_mgs = cold.get2(C_AS, 5);   // (3 K2 (...), gated mu_s + mu_p): tides / GR
     double Kr = 0., Kv = 0.;          // coefficients of r and v in F
     double Pcp = 0., Hcs = 0.;        // coefficient of r x w_planet in dLp/dt, of r x w_host in the host's dL/dt
     V3 F = v3(0., 0., 0.), dl_p = v3(0., 0., 0.), dl_h = v3(0., 0., 0.);
     if (PB_FLAGS(P) & FLAG_TIDES) {
         // constant_time_lag.rs:206-332, tides/common.rs:223-345
         const double inv_d6 = inv_d4 * inv_d2, inv_d7 = inv_d6 * inv_d;
-        double FodS = cold.get(C_AS) * inv_d6;      // F_orth * r
-        double FodP = cold.get(C_AP) * inv_d6;
+        const double2 as_ap = cold.get2(C_AS, 0);
+        double FodS = as_ap.x * inv_d6;      // F_orth * r
+        double FodP = as_ap.y * inv_d6;
 #if !PB_FIXED_N
         if (PB_FLAGS(P) & FLAG_DYN) {
             sd sig_h, sig_p;
@@ -160,7 +146,7 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         const double Fos = FodS * inv_d, Fop = FodP * inv_d;
         const double ks = Fos * inv_d, kp = Fop * inv_d;
         // radial: conservative + dissipative (-13.5 vr/r^8 (...) = -3 vr/r (Fos + Fop)), plus the radial part of the orthogonal one
-        Kr = -inv_d * (cold.get(C_BK) * inv_d7 + (2.0 * inv_d) * ((Fos + Fop) * radvel));
+        Kr = -inv_d * (bk_mgs.x * inv_d7 + (2.0 * inv_d) * ((Fos + Fop) * radvel));
         Kv = -(ks + kp);
         // F_orth (w x r - v) = -F_orth (r x w) - F_orth v
         F = v3(-(ks * cs.x + kp * cp.x), -(ks * cs.y + kp * cp.y), -(ks * cs.z + kp * cp.z));
@@ -185,10 +171,11 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     if (PB_FLAGS(P) & FLAG_FLAT) {
         // oblate_spheroid.rs:12-97, rotational_flattening/common.rs:165-237
         const double inv_d5 = inv_d4 * inv_d;
-        const double KsRs = cold.get(C_KS) * rs_s, KpRp = cold.get(C_KP) * rs_p;
+        const double2 ks_kp = cold.get2(C_AS, 1);
+        const double KsRs = ks_kp.x * rs_s, KpRp = ks_kp.y * rs_p;
         const double Fos = -KsRs * inv_d5;
         const double Fop = -KpRp * inv_d5;
-        const double q1 = cold.get(C_KS) * wh2 + cold.get(C_KP) * w2;
+        const double q1 = ks_kp.x * wh2 + ks_kp.y * w2;
         const double q2 = KsRs * rs_s + KpRp * rs_p;
         Kr += inv_d5 * ((2.5 * inv_d2) * q2 - 0.5 * q1);
         F = v3(F.x + Fop * q.s.x + Fos * sh.x, F.y + Fop * q.s.y + Fos * sh.y, F.z + Fop * q.s.z + Fos * sh.z);
@@ -199,48 +186,40 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     if (GR == PB200_GR_KIDDER1995 && (PB_FLAGS(P) & FLAG_GR)) {
         // general_relativity.rs:177-456
         const double v2 = dot(hv, hv);
-        const double mgs = cold.get(C_MGS);
+        const double mgs = bk_mgs.y;
         const double A = mgs * inv_d2 * kInvC2;
         const double u = mgs * inv_d;
         const double rv2 = radvel * radvel;
         // 1PN; the orthoradial term divides by |v| and multiplies by |v|: cancelled. Coefficients G_k: make_consts.
-#ifdef PB_GPAIR
-        const double2 g01 = gpair_get(0), g23 = gpair_get(1), g45 = gpair_get(2), g67 = gpair_get(3), g89 = gpair_get(4), gab = gpair_get(5);
+        const double2 g01 = cold.get2(G_0, 0), g23 = cold.get2(G_0, 1), g45 = cold.get2(G_0, 2), g67 = cold.get2(G_0, 3), g89 = cold.get2(G_0, 4), gab = cold.get2(G_0, 5);
         double rad = -A * (g01.x * v2 - g01.y * u - g23.x * rv2);
         double orth = A * g23.y * radvel;
         rad += -A * (g45.x * (u * u) + g45.y * (v2 * v2) + g67.x * (rv2 * rv2) - g67.y * rv2 * v2 - g89.x * u * v2 - g89.y * u * rv2);
         orth += 0.5 * A * radvel * (gab.x * v2 - gab.y * u - cold.get(G_0 + 12) * rv2);
-#else
-        double rad = -A * (cold.get(G_0) * v2 - cold.get(G_0 + 1) * u - cold.get(G_0 + 2) * rv2);
-        double orth = A * cold.get(G_0 + 3) * radvel;
-        // 2PN (Kidder 1995 eq. 2.2d)
-        rad += -A * (cold.get(G_0 + 4) * (u * u) + cold.get(G_0 + 5) * (v2 * v2) + cold.get(G_0 + 6) * (rv2 * rv2)
-                     - cold.get(G_0 + 7) * rv2 * v2 - cold.get(G_0 + 8) * u * v2 - cold.get(G_0 + 9) * u * rv2);
-        orth += 0.5 * A * radvel * (cold.get(G_0 + 10) * v2 - cold.get(G_0 + 11) * u - cold.get(G_0 + 12) * rv2);
-#endif
         const double m = cold.get(K_M);
         Kr += m * (rad * inv_d);
         Kv += m * orth;
         // 1.5PN spin-orbit (:300-456) with n = r / d, n x v = (r x v) / d and the spin combinations of make_consts
-        const double Ip = cold.get(K_I), Ih = cold.getk(PB_HOST(P), K_I), zp = cold.get(C_ZP), zh = cold.get(C_ZH);
+        const double2 z_ph = cold.get2(C_AS, 2), d_ps = cold.get2(C_AS, 3), mfa_sxs = cold.get2(C_AS, 4);
+        const double Ip = cold.get(K_I), Ih = cold.getk(PB_HOST(P), K_I), zp = z_ph.x, zh = z_ph.y;
         const V3 S = v3(Ip * q.s.x + Ih * sh.x, Ip * q.s.y + Ih * sh.y, Ip * q.s.z + Ih * sh.z);
         const V3 Z = v3(zp * q.s.x + zh * sh.x, zp * q.s.y + zh * sh.y, zp * q.s.z + zh * sh.z);
         const V3 A1 = S + Z;                                                   // 2S + msf
         const V3 A3 = A1 + S;                                                  // 3S + msf
         const V3 A7 = v3(3. * A1.x + S.x, 3. * A1.y + S.y, 3. * A1.z + S.z);   // 7S + 3 msf
-        const double mfa = cold.get(C_MFA);
+        const double mfa = mfa_sxs.x;
         const double s1 = 6. * mfa * inv_d2, s3 = 3. * mfa * (radvel * inv_d);
         const V3 e2 = cross(hv, A7), e3 = cross(hr, A3);
         F = v3(F.x + s1 * (hr.x * rxv.x * A1.x) - mfa * e2.x + s3 * e3.x,
                F.y + s1 * (hr.y * rxv.y * A1.y) - mfa * e2.y + s3 * e3.y,
                F.z + s1 * (hr.z * rxv.z * A1.z) - mfa * e2.z + s3 * e3.z);
         // Kidder 1995 eqs 2.4a, 2.4b: dLs/dt = fms Lo x Ls - Lp x Ls + 3 (n.Lp) n x Ls, dLp/dt = fmp Lo x Lp + Lp x Ls + 3 (n.Ls) n x Lp
-        const double sxs_k = cold.get(C_SXS);
+        const double sxs_k = mfa_sxs.y;
         const double c3 = 3. * sxs_k * inv_d2;
         Pcp += c3 * q.rs_s;
         Hcs += c3 * q.rs_p;
         const V3 wxw = cross(q.s, sh), jp = cross(rxv, q.s), js = cross(rxv, sh);
-        const double dp1 = cold.get(C_DP1), ds1 = cold.get(C_DS1);
+        const double dp1 = d_ps.x, ds1 = d_ps.y;
         dl_p = v3(dl_p.x + dp1 * jp.x + sxs_k * wxw.x, dl_p.y + dp1 * jp.y + sxs_k * wxw.y, dl_p.z + dp1 * jp.z + sxs_k * wxw.z);
         dl_h = v3(dl_h.x + ds1 * js.x - sxs_k * wxw.x, dl_h.y + ds1 * js.y - sxs_k * wxw.y, dl_h.z + ds1 * js.z - sxs_k * wxw.z);
     }
@@ -258,10 +237,10 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
 #if PB_FIXED_N == 8
     if (b < 6) {
         // lane c adds component c: columns visited in XOR order (body b ^ j at step j: conflict-free banks, one LOP3 per address)
-        const int row = dist_tid() + (M_0 + b) * PB_BLOCK;
-        const double x0 = *dist_cell(row, 0), x1 = *dist_cell(row, 1), x2 = *dist_cell(row, 2), x3 = *dist_cell(row, 3),
-                     x4 = *dist_cell(row, 4), x5 = *dist_cell(row, 5), x6 = *dist_cell(row, 6), x7 = *dist_cell(row, 7);
-        *dist_cell(row, 0) = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));   // only this lane reads column b of slot M_0 + b: no hazard
+        const unsigned row = dist_self(cold) + (unsigned)((M_0 + b) * PB_BLOCK * 8);
+        const double x0 = dist_ld(row, 0), x1 = dist_ld(row, 1), x2 = dist_ld(row, 2), x3 = dist_ld(row, 3),
+                     x4 = dist_ld(row, 4), x5 = dist_ld(row, 5), x6 = dist_ld(row, 6), x7 = dist_ld(row, 7);
+        dist_st(row, 0, ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7)));   // only this lane reads column b of slot M_0 + b: no hazard
     }
 #else
     for (int c = b; c < 6; c += W) {

@@ -345,7 +345,8 @@ enum ColdSlot : int {
     K_M, K_MG, K_R, K_I,
     // constants of the perturbation forces (every division with step-invariant operands is done once)
     // (host-body quantities — its mass, inertia, 1/M — are read from the host's own column with getk, they have no slot)
-    C_INVI, C_AS, C_AP, C_BK, C_KS, C_KP, C_INVM, C_MGS, C_MFA, C_ZP, C_ZH, C_DP1, C_DS1, C_SXS, C_SPARE,
+    // (C_AS .. C_MGS are one region of 16-byte pair cells in fast mode: Cold::get2 / set2)
+    C_INVI, C_INVM, C_AS, C_AP, C_KS, C_KP, C_ZP, C_ZH, C_DP1, C_DS1, C_MFA, C_SXS, C_BK, C_MGS, C_SPARE,
     // constants of the coordinate transforms (strict)
     // The host's columns of the last three are meaningless for the host body itself and carry the per-system values:
     // K_ETAK <- total mass, K_BACKW <- refined reciprocal of the total mass, K_WHDSF <- refined reciprocal of the host
@@ -374,13 +375,39 @@ enum ColdSlot : int {
 struct Cold {
     volatile double* base;  // shared memory + threadIdx.x
     volatile double* grp;   // base - b: the column of the group's body 0
+    volatile double* pair;  // this thread's 16-byte cell in the first two slots of a pair region (inside the warp's own columns)
     __device__ __forceinline__ double getk(int k, int slot) const { return grp[k + slot * PB_BLOCK]; }
     __device__ __forceinline__ double get(int slot) const { return base[slot * PB_BLOCK]; }
     __device__ __forceinline__ void set(int slot, double v) const { base[slot * PB_BLOCK] = v; }
     __device__ __forceinline__ V3 get3(int slot) const { return v3(get(slot), get(slot + 1), get(slot + 2)); }
     __device__ __forceinline__ void set3(int slot, V3 v) const { set(slot, v.x); set(slot + 1, v.y); set(slot + 2, v.z); }
     __device__ __forceinline__ V3 getk3(int k, int slot) const { return v3(getk(k, slot), getk(k, slot + 1), getk(k, slot + 2)); }
+    // Pair regions: values that are always read together by their own thread (force constants, the midpoint's originals,
+    // increments and Kahan residuals) sit as 16-byte cells inside a run of 2 n consecutive slots (cell p of a warp = its 32 columns of slots 2p and 2p + 1), so one
+    // LDS.128 / STS.128 moves two of them: the same shared-memory wavefronts, half the instructions. `region` is the first
+    // slot of the run; a region is only ever accessed through these four functions while it holds pairs.
+    __device__ __forceinline__ unsigned pair_addr(int region, int p) const {
+        return (unsigned)__cvta_generic_to_shared((const void*)(pair + (region + 2 * p) * PB_BLOCK));
+    }
+    __device__ __forceinline__ double2 get2(int region, int p) const {
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(pair_addr(region, p)) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void set2(int region, int p, double a, double b) const {
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" : : "r"(pair_addr(region, p)), "d"(a), "d"(b) : "memory");
+    }
+    // two vectors in three cells: (a.x, a.y) (a.z, b.x) (b.y, b.z)
+    __device__ __forceinline__ void get6(int region, V3& a, V3& b) const {
+        const double2 p0 = get2(region, 0), p1 = get2(region, 1), p2 = get2(region, 2);
+        a = v3(p0.x, p0.y, p1.x); b = v3(p1.y, p2.x, p2.y);
+    }
+    __device__ __forceinline__ void set6(int region, V3 a, V3 b) const {
+        set2(region, 0, a.x, a.y); set2(region, 1, a.z, b.x); set2(region, 2, b.y, b.z);
+    }
 };
+// pair regions of the midpoint (six slots each): Kahan residuals (v, L), originals (v, L), increments (v, L)
+enum : int { R_ERR = S_EVX, R_ORIG = S_VOX, R_INCR = S_DVX };
 // exchange triples of the core (dead midpoint slots)
 enum : int { E_A = S_VOX, E_B = S_LOX, E_C = S_DVX, E_D = S_DLX, E_R = S_RX };
 

@@ -38,8 +38,10 @@ __device__ __forceinline__ void store_lane(const KParams& P, const Roles& ro, co
     P.acc[i] = cold.get(S_AX); P.acc[i + cs] = cold.get(S_AY); P.acc[i + 2 * cs] = cold.get(S_AZ);
     P.L[i] = q.L.x; P.L[i + cs] = q.L.y; P.L[i + 2 * cs] = q.L.z;
     P.spin[i] = q.s.x; P.spin[i + cs] = q.s.y; P.spin[i + 2 * cs] = q.s.z;
-    P.verr[i] = cold.get(S_EVX); P.verr[i + cs] = cold.get(S_EVY); P.verr[i + 2 * cs] = cold.get(S_EVZ);
-    P.lerr[i] = cold.get(S_ELX); P.lerr[i + cs] = cold.get(S_ELY); P.lerr[i + 2 * cs] = cold.get(S_ELZ);
+    V3 ev, el;
+    cold.get6(R_ERR, ev, el);
+    P.verr[i] = ev.x; P.verr[i + cs] = ev.y; P.verr[i + 2 * cs] = ev.z;
+    P.lerr[i] = el.x; P.lerr[i + cs] = el.y; P.lerr[i + 2 * cs] = el.z;
     // radius / radius of gyration / moment of inertia are written when they evolve (evolve_lane)
     if (b == 0) {
         P.t[sys] = st.t; P.last_hist[sys] = st.last_hist;
@@ -93,14 +95,14 @@ __device__ __forceinline__ S3 ordered_diff_others(const Cold& cold, S3 init, int
     return acc;
 }
 
-// ---- Distributed ordered sums: see the layout notes next to dist_cell (forces_fast.cuh).
+// ---- Distributed ordered sums: see the layout notes next to dist_ld (forces_fast.cuh).
 // the row of the scalar this lane reduces (lanes beyond the last scalar repeat it; their results are never read)
-__device__ __forceinline__ int dist_row(int base, int b, int n_scalars) { return dist_tid() + (base + (b < n_scalars ? b : n_scalars - 1)) * PB_BLOCK; }
+__device__ __forceinline__ unsigned dist_row(const Cold& cold, int base, int b, int n_scalars) { return dist_self(cold) + (unsigned)((base + (b < n_scalars ? b : n_scalars - 1)) * PB_BLOCK * 8); }
 // acc (+/-)= term of body 1, 2, ... 7 in index order
 template <bool SUB>
-__device__ __forceinline__ sd dist_walk(int row, sd acc) {
+__device__ __forceinline__ sd dist_walk(unsigned row, sd acc) {
 #pragma unroll
-    for (int k = 1; k < 8; k++) { const sd t = sd(*dist_cell(row, k)); acc = SUB ? acc - t : acc + t; }
+    for (int k = 1; k < 8; k++) { const sd t = sd(dist_ld(row, k)); acc = SUB ? acc - t : acc + t; }
     return acc;
 }
 
@@ -115,8 +117,8 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
     // positions do not change inside the midpoint: heliocentric position and 1/r once (universe.rs:318-351)
     __syncwarp();   // the core's last exchange reads are done before these slots are rewritten
     cold.set3(S_RX, plain(q.r));
-    cold.set3(S_VOX, plain(q.v)); cold.set3(S_LOX, q.L);
-    cold.set3(S_DVX, v3(0., 0., 0.)); cold.set3(S_DLX, v3(0., 0., 0.));
+    cold.set6(R_ORIG, plain(q.v), q.L);
+    cold.set6(R_INCR, v3(0., 0., 0.), v3(0., 0., 0.));
     if (!ARITH) { cold.set3(M_0, plain(q.v)); cold.set3(E_S, q.s); }   // fast mode: the host's current v and last spin for the group
     __syncwarp();
     const S3 rh_s = strict(cold.getk3(PB_HOST(P), S_RX));
@@ -168,9 +170,9 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
             }
         }
         // final = orig + (dt * a - err)   (whfast.rs:353-378), with the previous final for the convergence test
-        const S3 vo = strict(cold.get3(S_VOX));
-        const V3 Lo = cold.get3(S_LOX);
-        const V3 ev = cold.get3(S_EVX), el = cold.get3(S_ELX);
+        V3 vo_p, Lo, ev, el;
+        cold.get6(R_ORIG, vo_p, Lo); cold.get6(R_ERR, ev, el);
+        const S3 vo = strict(vo_p);
         S3 ndv = s3(dt * sd(a.x) - sd(ev.x), dt * sd(a.y) - sd(ev.y), dt * sd(a.z) - sd(ev.z));
         V3 ndl = v3((dt * sd(dldt.x) - sd(el.x)).v, (dt * sd(dldt.y) - sd(el.y)).v, (dt * sd(dldt.z) - sd(el.z)).v);
         S3 vf = vo + ndv;
@@ -179,8 +181,9 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
         if (it >= 2) {
             // whfast.rs:424-451 (sums over bodies by butterfly: only the branch decision depends on them); the previous
             // iterate's final values are rebuilt from the stored increments
-            const S3 vf_old = vo + strict(cold.get3(S_DVX));
-            const V3 dl_old = cold.get3(S_DLX);
+            V3 dv_old, dl_old;
+            cold.get6(R_INCR, dv_old, dl_old);
+            const S3 vf_old = vo + strict(dv_old);
             const V3 Lf_old = v3(__dadd_rn(Lo.x, dl_old.x), __dadd_rn(Lo.y, dl_old.y), __dadd_rn(Lo.z, dl_old.z));
             V3 ddv = plain(vf - vf_old), ddl = Lf - Lf_old, vfp = plain(vf);
             // delta/total < eps^2 decided as sum(delta_i - eps^2 total_i) < 0: one group sum per test, no division; NaN
@@ -198,7 +201,7 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
         if (!done) {
             // the increments of iteration 0 are never read (the convergence test starts at it = 2 with those of it = 1, the
             // final update uses the last ones, and a live system always runs at least 3 iterations)
-            if (it > 0) { cold.set3(S_DVX, plain(ndv)); if (PB_SPIN(P)) cold.set3(S_DLX, ndl); }
+            if (it > 0) cold.set6(R_INCR, plain(ndv), ndl);
             if (conv_now) { done = true; converged = true; }
             else {
                 // average (whfast.rs:453-466)
@@ -216,14 +219,19 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
     q.r = strict(cold.get3(S_RX));
     if (alive) {
         if (!converged) warnings |= PB200_WARN_MIDPOINT_NOT_CONVERGED;
-        const S3 vo = strict(cold.get3(S_VOX)), dv = strict(cold.get3(S_DVX));
+        V3 vo_p, Lo, dv_p, dl, ev_new, el_new;
+        cold.get6(R_ORIG, vo_p, Lo); cold.get6(R_INCR, dv_p, dl);
+        const S3 vo = strict(vo_p), dv = strict(dv_p);
         q.v = vo + dv;
-        cold.set3(S_EVX, plain((q.v - vo) - dv));
+        ev_new = plain((q.v - vo) - dv);
         if (PB_SPIN(P)) {
-            const V3 Lo = cold.get3(S_LOX), dl = cold.get3(S_DLX);
             q.L = v3(__dadd_rn(Lo.x, dl.x), __dadd_rn(Lo.y, dl.y), __dadd_rn(Lo.z, dl.z));
-            cold.set3(S_ELX, v3(__dsub_rn(__dsub_rn(q.L.x, Lo.x), dl.x), __dsub_rn(__dsub_rn(q.L.y, Lo.y), dl.y), __dsub_rn(__dsub_rn(q.L.z, Lo.z), dl.z)));
+            el_new = v3(__dsub_rn(__dsub_rn(q.L.x, Lo.x), dl.x), __dsub_rn(__dsub_rn(q.L.y, Lo.y), dl.y), __dsub_rn(__dsub_rn(q.L.z, Lo.z), dl.z));
+        } else {
+            V3 unused;
+            cold.get6(R_ERR, unused, el_new);   // the L residuals stay as they are (they share a cell with the v residuals)
         }
+        cold.set6(R_ERR, ev_new, el_new);
     }
 }
 
@@ -383,6 +391,9 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
     Cold cold;
     cold.base = pb_smem + threadIdx.x;
     cold.grp = cold.base - b;
+    // a warp's pair cells stay inside the warp's own 32 columns (the warps of a CTA run unsynchronised): lanes 0-15 use the
+    // first slot of a cell pair, lanes 16-31 the second, 16 bytes per lane
+    cold.pair = pb_smem + (((threadIdx.x & 31u) >> 4) * PB_BLOCK + (threadIdx.x & ~31u) + 2u * (threadIdx.x & 15u));
 
     Lane q;
     SysState st;
@@ -393,13 +404,13 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
             auto ld3 = [&](const double* a) { return v3(ldm(a + i), ldm(a + i + cs), ldm(a + i + 2 * cs)); };
             q.r = strict(ld3(P.pos)); q.v = strict(ld3(P.vel));
             q.L = ld3(P.L); q.s = ld3(P.spin);
-            cold.set3(S_EVX, ld3(P.verr)); cold.set3(S_ELX, ld3(P.lerr)); cold.set3(S_AX, ld3(P.acc));
+            cold.set6(R_ERR, ld3(P.verr), ld3(P.lerr)); cold.set3(S_AX, ld3(P.acc));
             cold.set(K_M, P.mass[i]); cold.set(K_MG, P.mass_g[i]); cold.set(K_R, ldm(P.radius + i)); cold.set(K_I, ldm(P.moi + i));
         } else {
             // padding lanes: finite, non-zero dummies (never read by live lanes, never stored)
             q.r = s3(sd(1. + b), sd(0.), sd(0.)); q.v = s3(sd(0.), sd(0.), sd(0.));
             q.L = v3(0., 0., 1.); q.s = v3(0., 0., 1.);
-            cold.set3(S_EVX, v3(0., 0., 0.)); cold.set3(S_ELX, v3(0., 0., 0.)); cold.set3(S_AX, v3(0., 0., 0.));
+            cold.set6(R_ERR, v3(0., 0., 0.), v3(0., 0., 0.)); cold.set3(S_AX, v3(0., 0., 0.));
             cold.set(K_M, 1.); cold.set(K_MG, 1.); cold.set(K_R, 1.); cold.set(K_I, 1.);
         }
         if (sys_ok) {
@@ -570,10 +581,10 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     S3 mr = q.r * m_s, mv = q.v * m_s;
                     if (DIST) {
                         // scalars 0-2: sum m r / M_tot (centre of mass), 3-5: sum m v / M_tot; lane c owns scalar c for the step
-                        dist_put3(E_A, 0, plain(mr)); dist_put3(E_A, 3, plain(mv)); cold.set3(E_R, plain(q.r));
+                        dist_put3(cold, E_A, 0, plain(mr)); dist_put3(cold, E_A, 3, plain(mv)); cold.set3(E_R, plain(q.r));
                         __syncwarp();
-                        const int row = dist_row(E_A, b, 6);
-                        my_com = dist_walk<false>(row, zero + sd(*dist_cell(row, 0))) / rT;
+                        const unsigned row = dist_row(cold, E_A, b, 6);
+                        my_com = dist_walk<false>(row, zero + sd(dist_ld(row, 0))) / rT;
                         cold.set(M_0, my_com.v);
                         __syncwarp();
                         svel = strict(v3(cold.getk(3, M_0), cold.getk(4, M_0), cold.getk(5, M_0)));
@@ -635,9 +646,9 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         }
                         if (COORD != PB200_COORD_JACOBI && jump_slot != phase) {
                             if (DIST) {
-                                dist_put3(E_C, 0, plain(m_s * avel));
+                                dist_put3(cold, E_C, 0, plain(m_s * avel));
                                 __syncwarp();
-                                const sd p = dist_walk<false>(dist_row(E_C, b, 3), zero);
+                                const sd p = dist_walk<false>(dist_row(cold, E_C, b, 3), zero);
                                 cold.set(M_0, (hdt_s * p / rM).v);
                                 __syncwarp();
                                 apos = s3(apos.x + sd(cold.getk(0, M_0)), apos.y + sd(cold.getk(1, M_0)), apos.z + sd(cold.getk(2, M_0)));
@@ -682,10 +693,10 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         const S3 vterm = avel * sd(cold.get(K_BACKW));
                         if (DIST) {
                             // scalars 0-2: star position, 3-5: star velocity (read in the second pass only)
-                            dist_put3(E_C, 0, plain(term));
-                            if (phase == 1) dist_put3(E_C, 3, plain(vterm));
+                            dist_put3(cold, E_C, 0, plain(term));
+                            if (phase == 1) dist_put3(cold, E_C, 3, plain(vterm));
                             __syncwarp();
-                            cold.set(M_0, dist_walk<true>(dist_row(E_C, b, 6), my_com).v);
+                            cold.set(M_0, dist_walk<true>(dist_row(cold, E_C, b, 6), my_com).v);
                             __syncwarp();
                             const S3 star_r = strict(v3(cold.getk(0, M_0), cold.getk(1, M_0), cold.getk(2, M_0)));
                             const S3 nr = ro.host ? star_r : apos + star_r;
