@@ -266,7 +266,7 @@ def main():
                          "frac": achieved / (fp64_peak / 1e12) if fp64_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one bench launch (65536 systems, its steps cut into
                          # 4 time slices: the state crosses HBM once per slice), ncu, profiles/r1_traffic_bench_launch.csv
-                         "traffic": 1109.2e6 * n_sys / 65536.0,
+                         "traffic": 1230.1e6 * n_sys / 65536.0,
                          "peak_source": "measured here: DFMA-chain microbenchmark (pb200_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                          "frac_of_theoretical_37.2": achieved / FP64_THEORETICAL_TFLOPS,
                          "flops_per_system_step": FLOPS_PER_SYSTEM_STEP},
