@@ -430,6 +430,9 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                 const double rr = __ldg(P.roche + ((size_t)(lo * n + hi)) * (size_t)P.n_sys + sys);
                 rmax2 = fmax(rmax2, __dmul_rn(rr, rr));
             }
+        // 8-body gravity: the host pairs are checked by the planets; the host lane's own (dummy) walk must not pass the
+        // pre-test, or it fetches a Roche radius from global memory on every step (its distance to itself is zero)
+        if (PB_FIXED_N == 8 && COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC && !ro.planet) rmax2 = -1.;
         cold.set(K_ROCHE2, rmax2);
     }
     bool alive = sys_ok && st.status == PB200_STATUS_OK;
