@@ -1,7 +1,8 @@
 // fp64_nan.cu — does the FP64 pipe of a B200 SM slow down when some lanes of a warp carry NaN (or Inf) operands?
 // Why it matters here: the idle lanes of the step kernel (host slot, padding) run the planet code on dummies; without the
 // dummies the Kepler drift of the host slot is NaN throughout, and the whole kernel ran 21 % slower (profiles/r1_variants.md).
-// Answer (profiles/r1_fp64_nan.txt): no — 33.5 TFLOP/s in every case; the slowdown is not in the FP64 pipe.
+// Answer (profiles/r1_fp64_nan.txt): no — 33.5 TFLOP/s in every case; the slowdown was the Stumpff range-reduction loop
+// running hundreds of trips on the host slot's garbage (ncu: 1 313 instead of 492 FP64 instructions per warp-step in the drifts).
 // Dependent-DFMA chains, 4 per thread, 4 warps per scheduler; the lanes selected by `mask` start from the special value.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp64_nan fp64_nan.cu
 #include <cmath>
