@@ -34,6 +34,30 @@
 #undef PB_FIXED_W
 #undef PB_FIXED_SHIFT
 #undef PB_FIXED_FLAGS
+// Small systems with the same compile-time effect set and the host at index 0 (configs 1 and 3 of BASELINE.json: one and
+// two planets, 2 / 4 lanes per system): compile-time body count, lane geometry and role gates; the sums stay the serial ones.
+#define PB_NS pbn2
+#define PB_FIXED_N 2
+#define PB_FIXED_W 2
+#define PB_FIXED_SHIFT 1
+#define PB_FIXED_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
+#include "whfast_step.cuh"
+#undef PB_NS
+#undef PB_FIXED_N
+#undef PB_FIXED_W
+#undef PB_FIXED_SHIFT
+#undef PB_FIXED_FLAGS
+#define PB_NS pbn3
+#define PB_FIXED_N 3
+#define PB_FIXED_W 4
+#define PB_FIXED_SHIFT 2
+#define PB_FIXED_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
+#include "whfast_step.cuh"
+#undef PB_NS
+#undef PB_FIXED_N
+#undef PB_FIXED_W
+#undef PB_FIXED_SHIFT
+#undef PB_FIXED_FLAGS
 #define PB_FIXED_N 0
 #define PB_FIXED_W 0
 #define PB_FIXED_SHIFT 0
@@ -379,6 +403,16 @@ static cudaError_t launch_one(pb200_ensemble* e, unsigned grid, unsigned long lo
 static cudaError_t launch_n8(pb200_ensemble* e, unsigned grid, unsigned long long n) {
     static thread_local int configured_device = -1, blocks_per_sm = 0;
     return launch_sliced(e, pbn8::whfast_steps_kernel<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995, 0>, configured_device,
+                         blocks_per_sm, grid, n);
+}
+
+template <int N>
+static cudaError_t launch_small(pb200_ensemble* e, unsigned grid, unsigned long long n) {
+    static thread_local int configured_device = -1, blocks_per_sm = 0;
+    if (N == 2)
+        return launch_sliced(e, pbn2::whfast_steps_kernel<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995, 0>, configured_device,
+                             blocks_per_sm, grid, n);
+    return launch_sliced(e, pbn3::whfast_steps_kernel<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995, 0>, configured_device,
                          blocks_per_sm, grid, n);
 }
 
@@ -795,10 +829,12 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
     {
         cudaError_t err;
-        const bool n8 = e->n_bodies == 8 && e->P.host == 0 && e->coord == PB200_COORD_DEMOCRATIC_HELIOCENTRIC &&
+        const bool n8 = (e->n_bodies == 8 || e->n_bodies == 2 || e->n_bodies == 3) && e->P.host == 0 && e->coord == PB200_COORD_DEMOCRATIC_HELIOCENTRIC &&
                         e->gr == PB200_GR_KIDDER1995 && e->P.flags == (FLAG_TIDES | FLAG_FLAT | FLAG_GR) &&
                         e->arithmetic == PB200_ARITH_FAST && !e->force_generic;
-        if (n8) err = launch_n8(e, grid, n_steps);
+        if (n8 && e->n_bodies == 8) err = launch_n8(e, grid, n_steps);
+        else if (n8 && e->n_bodies == 2) err = launch_small<2>(e, grid, n_steps);
+        else if (n8) err = launch_small<3>(e, grid, n_steps);
         else switch (e->coord) {
             case PB200_COORD_JACOBI: err = launch_gr<PB200_COORD_JACOBI>(e, grid, n_steps); break;
             case PB200_COORD_DEMOCRATIC_HELIOCENTRIC: err = launch_gr<PB200_COORD_DEMOCRATIC_HELIOCENTRIC>(e, grid, n_steps); break;

@@ -468,6 +468,29 @@ def test_eight_body_specialisation_matches_generic_kernel(E, monkeypatch):
     assert same.mean() > 0.5, same.mean()
 
 
+@pytest.mark.parametrize("name", ["c1_example", "c3_case7"])
+def test_small_system_specialisations_match_generic_kernel(E, monkeypatch, name):
+    """The compile-time 2- and 3-body builds (configs 1 and 3: host 0, democratic heliocentric, tides + flattening + Kidder1995,
+    fast arithmetic; 2 / 4 lanes per system) against the run-time-geometry build of the same step (PB200_FORCE_GENERIC=1) on
+    the same perturbed members: same arithmetic in the same order, 1e-13 relative after 300 steps."""
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import make_ensemble_cases
+    case, tables = case_from_dict(config_case(name))
+    cases = make_ensemble_cases(case, 333, 13)   # the last CTA partly filled
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PB200_FORCE_GENERIC", flag)
+        with E.Ensemble(cases, tables) as ens:
+            ens.initialize_physical_values()
+            ens.iterate(300)
+            out.append(gpu_state_of(ens))
+            st, _, _ = ens.status()
+            assert (st == 0).all() and ens.get_case(332).current_iteration == 300
+    a, b = out
+    for key in ("position", "velocity", "spin", "angular_momentum"):
+        assert rel_err(a[key], b[key]) < 1e-13, key
+
+
 def test_device_built_ensemble_equals_host_recipe(E):
     """pb200_ensemble_create_perturbed builds the members on the device: initial state bit-identical to
     the host statement of the same SplitMix64 recipe, and the same trajectories afterwards; get_case gives a member's image."""
