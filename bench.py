@@ -151,8 +151,8 @@ def main():
     ap.add_argument("--steps-per-call", type=int, default=2000,
                     help="WHFast steps per launch (one bench step); the default times 5 x 2000 = 10^4 steps (SURVEY §8d horizon)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--arithmetic", default="fast", choices=["fast", "strict"],
-                    help="fast (default): FMA/reciprocal forces; strict: forces bit-reproducible against the reference arithmetic")
+    ap.add_argument("--arithmetic", default="hybrid", choices=["hybrid", "fast", "strict"],
+                    help="hybrid (default): fast midpoint iterates, exact committed evaluation; strict: every evaluation exact; fast: none")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -180,7 +180,7 @@ def main():
     n_sys, spc = args.systems, args.steps_per_call
     # keep the whole run inside the case's time limit
     cases = make_ensemble_cases(case, n_sys, 20261017 + CONFIG_INDEX + 1000 * rank)
-    ens = Ensemble(cases, tables, device=local, arithmetic=1 if args.arithmetic == "strict" else 0)
+    ens = Ensemble(cases, tables, device=local, arithmetic={"fast": 0, "strict": 1, "hybrid": 2}[args.arithmetic])
     ens.initialize_physical_values()
     ens.synchronize()
     # pinned host buffers of the boundary call

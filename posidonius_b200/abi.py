@@ -5,7 +5,7 @@ MAX_PARTICLES = 10
 HISTORIC_RECORD_BYTES = 156
 
 OK, E_INVALID, E_UNSUPPORTED, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4
-ARITH_FAST, ARITH_STRICT = 0, 1
+ARITH_FAST, ARITH_STRICT, ARITH_HYBRID = 0, 1, 2
 
 COORD_JACOBI, COORD_DEMOCRATIC_HELIOCENTRIC, COORD_WHDS = 0, 1, 2
 COORDINATES = {"Jacobi": COORD_JACOBI, "DemocraticHeliocentric": COORD_DEMOCRATIC_HELIOCENTRIC, "WHDS": COORD_WHDS}

@@ -58,7 +58,8 @@ __device__ __forceinline__ void pair_dependent_sigmas(const KParams& P, const Ro
     // (0, 0) unless the host is TidesEffect::CentralBody (constant_time_lag.rs:33-41)
     const sd diss_h = sd(P.tides_host_central ? shfl(diss, hl) : 0.), scale_h = sd(P.tides_host_central ? shfl(scale, hl) : 0.);
     const sd R = sd(cold.get(K_R)), Rh = sd(shfl(R.v, hl));
-    const sd gm = sd(cold.getk(PB_HOST(P), K_MG)) + sd(cold.get(K_MG));
+    // mu_host + mu (cold path: the gravitational masses stay in global memory)
+    const sd gm = sd(P.mass_g[(size_t)PB_HOST(P) * ns + (ro.valid ? sys : 0)]) + sd(ro.valid ? P.mass_g[i] : 1.);
     sd q, e;
     perihelion_and_eccentricity(gm, hr, hv, q, e);
     const sd mean_motion = ssqrt_ieee(gm) * sd(pow((q / (sd(1.0) - e)).v, -1.5));

@@ -1,6 +1,7 @@
 // forces_fast.cuh — PB200_ARITH_FAST perturbation forces (tides, flattening, GR Kidder1995) and their per-system constants.
 // Included once per geometry specialisation (see pb200_api.cu), inside namespace PB_NS; no include guard on purpose.
 #include "whfast_kernel.cuh"
+#include "cold_slots.cuh"
 #include "dyn_effects.cuh"
 
 namespace PB_NS {
@@ -35,66 +36,88 @@ __device__ __forceinline__ void dist_st(unsigned row, int k, double v) {
 }
 __device__ __forceinline__ void dist_put(const Cold& cold, int base, int c, double v) { dist_st(dist_self(cold) + (unsigned)((base + c) * PB_BLOCK * 8), c, v); }
 __device__ __forceinline__ void dist_put3(const Cold& cold, int base, int c0, V3 v) { dist_put(cold, base, c0, v.x); dist_put(cold, base, c0 + 1, v.y); dist_put(cold, base, c0 + 2, v.z); }
+// the row of the scalar this lane reduces (lanes beyond the last scalar repeat it; their results are never read)
+__device__ __forceinline__ unsigned dist_row(const Cold& cold, int base, int b, int n_scalars) { return dist_self(cold) + (unsigned)((base + (b < n_scalars ? b : n_scalars - 1)) * PB_BLOCK * 8); }
+// acc (+/-)= term of body 1, 2, ... 7 in index order
+template <bool SUB>
+__device__ __forceinline__ sd dist_walk(unsigned row, sd acc) {
+#pragma unroll
+    for (int k = 1; k < 8; k++) { const sd t = sd(dist_ld(row, k)); acc = SUB ? acc - t : acc + t; }
+    return acc;
+}
+
 // Derives the force constants from masses, radii and dissipation parameters (cold path: launch start and whenever a
-// radius evolves). sigma / k2 are fetched from global memory here, they are not kept on chip.
+// radius evolves). One routine serves every arithmetic mode. What the exact forces (exact_effects.cuh) read is computed
+// with `sd` in the reference's association order: the base quantities (sigma, k2, k2f, R^5, R^10 with powi as LLVM expands
+// it — strict_effects' Z_* constants are rebuilt from them per evaluation), the tidal numerators, 1 / m, the GR factor
+// polynomials, mass_factor (M + m) and the reduced mass. The remaining constants are the fast forces' folded products.
 __device__ __forceinline__ void make_consts(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys) {
-    double sigma = 0., k2t = 0., k2f = 0.;
+    double sigma = 0., k2t = 0., k2f = 0., mg = 1.;
     if (ro.valid) {
         const size_t i = (size_t)b * (size_t)P.n_sys + sys;
-        sigma = P.sigma[i]; k2t = P.k2t[i]; k2f = P.k2f[i];
+        sigma = P.sigma[i]; k2t = P.k2t[i]; k2f = P.k2f[i]; mg = P.mass_g[i];
     }
-    const double m = cold.get(K_M), mg = cold.get(K_MG), R = cold.get(K_R), I = cold.get(K_I);
+    const double m = cold.get(K_M), R = cold.get(K_R), I = cold.get(K_I);
+    const sd R_s = sd(R), R2_s = R_s * R_s, R4_s = R2_s * R2_s, R8_s = R4_s * R4_s;
+    const double R5 = (R_s * R4_s).v, R10 = (R2_s * R8_s).v;      // powi(5) = x * x^4, powi(10) = x^2 * x^8 (Q10)
+    cold.set(K_SIG, sigma); cold.set(K_K2T, k2t); cold.set(K_K2F, k2f); cold.set(K_R5, R5); cold.set(K_R10, R10);
     const double M = shfl(m, hl), Mg = shfl(mg, hl), Ih = shfl(I, hl);
-    const double Rh5 = pow5(shfl(R, hl));
-    const double R5 = pow5(R);
+    const double Rh5 = shfl(R5, hl), Rh10 = shfl(R10, hl);
     const double sig_h = shfl(sigma, hl), k2t_h = shfl(k2t, hl), k2f_h = shfl(k2f, hl);
-    const double m2 = m * m, M2 = M * M;
+    const sd m_s = sd(m), M_s = sd(M);
+    const sd m2_s = m_s * m_s, M2_s = M_s * M_s;
+    const double m2 = m2_s.v, M2 = M2_s.v;
     cold.set(C_INVI, 1. / I);
     // Role gates are folded into the constants: a lane that is not an OrbitingBody of an effect (host slot, padding,
     // Disabled role) carries zeros, so the force code needs no per-lane branches or selects.
     const double gt = ro.t_on ? 1. : 0., gf = ro.f_on ? 1. : 0., gg = ro.g_on ? 1. : 0.;
     const double gts = P.tides_host_central ? gt : 0., gfs = P.flat_host_central ? gf : 0.;
-    cold.set2(C_AS, 0, gts * (4.5 * m2 * (Rh5 * Rh5) * sig_h),      // 4.5 m^2 R*^10 sigma*   (constant_time_lag.rs:232-234)
-                       gt * (4.5 * M2 * (R5 * R5) * sigma));         // 4.5 M^2 R^10 sigma     (constant_time_lag.rs:243-245)
+    // the tidal numerators in the reference's order (the gates are exact factors 0 / 1)
+    cold.set2(C_AS, 0, gts * (sd(4.5) * m2_s * sd(Rh10) * sd(sig_h)).v,      // 4.5 m^2 R*^10 sigma*   (constant_time_lag.rs:232-234)
+                       gt * (sd(4.5) * M2_s * sd(R10) * sd(sigma)).v);        // 4.5 M^2 R^10 sigma     (constant_time_lag.rs:243-245)
     const double c_bk = gt * (3.0 * kK2 * (m2 * Rh5 * k2t_h + M2 * R5 * k2t));   // 3 K2 (m^2 R*^5 k2* + M^2 R^5 k2) (:283-285)
-#if !PB_FIXED_N
-    // dynamical tides: the same constants without sigma (the pair-dependent sigma multiplies them per evaluation)
-    cold.set(D_0, gts * (4.5 * m2 * (Rh5 * Rh5)));
-    cold.set(D_1, gt * (4.5 * M2 * (R5 * R5)));
-#endif
     cold.set2(C_AS, 1, gfs * (m * k2f_h * Rh5),                     // flattening: m k2f* R*^5 (oblate_spheroid.rs:37)
                        gf * (M * k2f * R5));                        //             M k2f R^5   (oblate_spheroid.rs:42)
     cold.set(C_INVM, 1. / m);
-    const double mgs = Mg + mg;
+    const sd mgs_s = sd(Mg) + sd(mg);
+    const double mgs = mgs_s.v;
     cold.set2(C_AS, 5, c_bk, gg * mgs);                            // gated: A = mgs / (r^2 c^2) vanishes for non-GR lanes
     // 1.5PN spin-orbit terms (general_relativity.rs:300-456) in terms of the spins (L = I w), G / c^2 and the role gate folded in:
     //   mass_factor * (Lp / m - Ls / M) = Z - S with S = Ls + Lp and Z = (M / m) Lp + (m / M) Ls, so the three vectors of the
     //   acceleration are 2S + msf = S + Z, 3S + msf = 2S + Z and 7S + 3 msf = 4S + 3Z
     const double fa = gg * (kG * kInvC2);
-    const double mured = (M * m) / (M + m);                       // general_relativity.rs:383
+    const sd msum_s = M_s + m_s, mdiff_s = M_s - m_s;
+    const sd mured_s = (M_s * m_s) / msum_s;                      // general_relativity.rs:383
+    const double mured = mured_s.v;
+    cold.set(Z_MURED, mured);
+    cold.set(Z_MFM, (mdiff_s / msum_s * msum_s).v);               // mass_factor * star_planet_mass (:321, 336)
     cold.set2(C_AS, 2, I * (M / m), Ih * (m / M));                // Z = zp w_p + zh w_s
     cold.set2(C_AS, 3, fa * I * ((2. + 1.5 * M / m) * mured),     // :419  dLp/dt: (2 + 3 M / 2m) Lorb x Lp
                        fa * Ih * ((2. + 1.5 * m / M) * mured));   // :390  dLs/dt: (2 + 3 m / 2M) Lorb x Ls
     cold.set2(C_AS, 4, fa * m,                                    // force = m * acceleration: the host gets -F / M, the planet F / m
                        fa * I * Ih);                              // Lp x Ls and the 3 (n.L)(n x L) terms
-    // polynomials in the GR factor f of the 1PN / 2PN terms (general_relativity.rs:197-205, 256-268): per-system constants
-    const double f = Mg * mg / (mgs * mgs), f2 = f * f;
+    // polynomials in the GR factor f of the 1PN / 2PN terms (general_relativity.rs:98, 197-205, 256-268): per-system
+    // constants, every one a leading sub-expression of the reference's products, so the exact forces read them too
+    const sd f = sd(Mg) * sd(mg) / (mgs_s * mgs_s), f2 = f * f;
     // 13 polynomial coefficients: six pair cells and a single
-    cold.set2(G_0, 0, 1.0 + 3.0 * f, 2.0 * (2.0 + f));
-    cold.set2(G_0, 1, 1.5 * f, 2.0 * (2.0 - f));
-    cold.set2(G_0, 2, 0.75 * (12.0 + 29.0 * f), f * (3.0 - 4.0 * f));
-    cold.set2(G_0, 3, 1.875 * f * (1.0 - 3.0 * f), 1.5 * f * (3.0 - 4.0 * f));
-    cold.set2(G_0, 4, 0.5 * f * (13.0 - 4.0 * f), 2.0 + 25.0 * f + 2.0 * f2);
-    cold.set2(G_0, 5, f * (15.0 + 4.0 * f), 4.0 + 41.0 * f + 8.0 * f2);
-    cold.set(G_0 + 12, 3.0 * f * (3.0 + 2.0 * f));
-    __syncwarp();   // the host's column (1/M, inertia) is read by the other lanes
+    cold.set2(G_0, 0, (sd(1.0) + sd(3.0) * f).v, (sd(2.0) * (sd(2.0) + f)).v);
+    cold.set2(G_0, 1, (sd(1.5) * f).v, (sd(2.0) * (sd(2.0) - f)).v);
+    cold.set2(G_0, 2, (sd(0.75) * (sd(12.0) + sd(29.0) * f)).v, (f * (sd(3.0) - sd(4.0) * f)).v);
+    cold.set2(G_0, 3, (sd(1.875) * f * (sd(1.0) - sd(3.0) * f)).v, (sd(1.5) * f * (sd(3.0) - sd(4.0) * f)).v);
+    cold.set2(G_0, 4, (sd(0.5) * f * (sd(13.0) - sd(4.0) * f)).v, (sd(2.0) + sd(25.0) * f + sd(2.0) * f2).v);
+    cold.set2(G_0, 5, (f * (sd(15.0) + sd(4.0) * f)).v, (sd(4.0) + sd(41.0) * f + sd(8.0) * f2).v);
+    cold.set(G_0 + 12, (sd(3.0) * f * (sd(3.0) + sd(2.0) * f)).v);
+    __syncwarp();   // the host's column (1/M, inertia, base quantities) is read by the other lanes
 }
 
 // ---------------------------------------------------------------------------------------------
 // Universe::calculate_additional_effects for the lane's body at (hr, hv) with the current L
 // (universe.rs:428-614). Returns the inertial additional acceleration and dL/dt of THIS body;
 // host-lane values are the group reductions.
-template <int GR>
+// HYB (hybrid arithmetic, see midpoint()): this evaluation is one of the two uncommitted iterates that precede an exact
+// evaluation. The spin is then the correctly rounded L / I and the carried r . w products are rounded like the
+// reference's, because the exact evaluation that follows reads both (Q3: spins of the previous evaluation).
+template <int GR, bool HYB>
 __device__ __forceinline__ void additional_effects(const KParams& P, const Roles& ro, const Cold& cold, int hl, int b, size_t sys,
                                                    double t, bool evolve_now, Lane& q, V3 hr, double inv_d, V3 hv, V3& a_out,
                                                    V3& dl_out, bool tide_save) {
@@ -104,15 +127,18 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
     // host's previous spin); the midpoint sets them when the position has changed.
     const double rs_s = q.rs_s, rs_p = q.rs_p;
     // calculate_spin (particles/common.rs:3-15)
-    q.s = cold.get(C_INVI) * q.L;
-    double w2 = dot(q.s, q.s);
+    if (HYB) q.s = plain(strict(q.L) / make_rcp(sd(cold.get(K_I))));
+    else q.s = cold.get(C_INVI) * q.L;
+    const double w2 = HYB ? sdot(strict(q.s), strict(q.s)).v : dot(q.s, q.s);
     // (no barrier before these stores: the group's last reads of E_S / M_6 lie before the previous evaluation's exchange
     // barriers)
     cold.set3(E_S, q.s); cold.set(M_6, w2);
     __syncwarp();
     V3 sh = cold.getk3(PB_HOST(P), E_S);
     double wh2 = cold.getk(PB_HOST(P), M_6);
-    q.rs_s = dot(hr, sh); q.rs_p = dot(hr, q.s);   // for the next evaluation (Q3) and the 3 (n.L)(n x L) terms below
+    // for the next evaluation (Q3) and the 3 (n.L)(n x L) terms below
+    if (HYB) { q.rs_s = sdot(strict(hr), strict(sh)).v; q.rs_p = sdot(strict(hr), strict(q.s)).v; }
+    else { q.rs_s = dot(hr, sh); q.rs_p = dot(hr, q.s); }
 #if !PB_FIXED_N
     // lag angle of the dynamical-tide models, once per step like the other evolving quantities (evolution.rs:548-567)
     if (evolve_now && (PB_FLAGS(P) & FLAG_DYN) && (PB_FLAGS(P) & FLAG_EVO)) { update_lag_angle(P, ro, b, sys, t, sd(w2), true); __syncwarp(); }
@@ -139,8 +165,11 @@ __device__ __forceinline__ void additional_effects(const KParams& P, const Roles
         if (PB_FLAGS(P) & FLAG_DYN) {
             sd sig_h, sig_p;
             pair_dependent_sigmas(P, ro, cold, hl, b, sys, strict(hr), strict(hv), sd(w2), sd(wh2), sig_h, sig_p);
-            FodS = cold.get(D_0) * sig_h.v * inv_d6;
-            FodP = cold.get(D_1) * sig_p.v * inv_d6;
+            // the same numerators without the constant sigma (cold path: run-time geometry build only)
+            const double m_ = cold.get(K_M), M_ = cold.getk(PB_HOST(P), K_M);
+            const double gt_ = ro.t_on ? 1. : 0., gts_ = P.tides_host_central ? gt_ : 0.;
+            FodS = gts_ * (4.5 * m_ * m_ * cold.getk(PB_HOST(P), K_R10)) * sig_h.v * inv_d6;
+            FodP = gt_ * (4.5 * M_ * M_ * cold.get(K_R10)) * sig_p.v * inv_d6;
         }
 #endif
         const double Fos = FodS * inv_d, Fop = FodP * inv_d;

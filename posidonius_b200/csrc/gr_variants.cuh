@@ -36,9 +36,9 @@ __device__ __forceinline__ V3 gr_newtonian(const KParams& P, const Roles& ro, co
 }
 
 // general_relativity.rs:461-636
-__device__ __forceinline__ void gr_anderson1975(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, const Lane& q, V3 hr,
+__device__ __forceinline__ void gr_anderson1975(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, size_t sys, const Lane& q, V3 hr,
                                                 V3 acc_newton, bool jacobi_coords, V3& a_out) {
-    const double q_m = cold.get(K_M), q_mg = cold.get(K_MG);
+    const double q_m = cold.get(K_M), q_mg = ro.valid ? P.mass_g[(size_t)b * (size_t)P.n_sys + sys] : 1.;
     V3 an = gr_newtonian(P, ro, cold, gb, hl, b, q, hr, acc_newton, jacobi_coords);
     // inertial -> Jacobi over the OrbitingBody particles (:539-602); every lane carries the running sums
     double eta = shfl(q_m, hl);

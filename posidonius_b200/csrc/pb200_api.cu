@@ -10,58 +10,16 @@
 #include <vector>
 #include "whfast_kernel.cuh"
 
-// The device code of the step is compiled twice: for any geometry at run time (pbgen) and for exactly 8 bodies with the
-// host at index 0 (pbn8: the TRAPPIST-1 layout — body loops unroll, shuffle lanes are immediates).
+// The step kernels themselves are compiled in their own translation units (kernels_tu.cu, one object per geometry build
+// and arithmetic mode, built in parallel by build.py); this file sees the run-time-geometry device headers only for the
+// helpers that the small kernels below share with them (update_lag_angle).
 #define PB_NS pbgen
 #define PB_FIXED_N 0
 #define PB_FIXED_W 0
 #define PB_FIXED_SHIFT 0
 #define PB_FIXED_FLAGS 0
 #include "whfast_step.cuh"
-#undef PB_NS
-#undef PB_FIXED_N
-#undef PB_FIXED_W
-#undef PB_FIXED_SHIFT
-#undef PB_FIXED_FLAGS
-#define PB_NS pbn8
-#define PB_FIXED_N 8
-#define PB_FIXED_W 8
-#define PB_FIXED_SHIFT 3
-#define PB_FIXED_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
-#include "whfast_step.cuh"
-#undef PB_NS
-#undef PB_FIXED_N
-#undef PB_FIXED_W
-#undef PB_FIXED_SHIFT
-#undef PB_FIXED_FLAGS
-// Small systems with the same compile-time effect set and the host at index 0 (configs 1 and 3 of BASELINE.json: one and
-// two planets, 2 / 4 lanes per system): compile-time body count, lane geometry and role gates; the sums stay the serial ones.
-#define PB_NS pbn2
-#define PB_FIXED_N 2
-#define PB_FIXED_W 2
-#define PB_FIXED_SHIFT 1
-#define PB_FIXED_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
-#include "whfast_step.cuh"
-#undef PB_NS
-#undef PB_FIXED_N
-#undef PB_FIXED_W
-#undef PB_FIXED_SHIFT
-#undef PB_FIXED_FLAGS
-#define PB_NS pbn3
-#define PB_FIXED_N 3
-#define PB_FIXED_W 4
-#define PB_FIXED_SHIFT 2
-#define PB_FIXED_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
-#include "whfast_step.cuh"
-#undef PB_NS
-#undef PB_FIXED_N
-#undef PB_FIXED_W
-#undef PB_FIXED_SHIFT
-#undef PB_FIXED_FLAGS
-#define PB_FIXED_N 0
-#define PB_FIXED_W 0
-#define PB_FIXED_SHIFT 0
-#define PB_FIXED_FLAGS 0
+#include "ensemble_host.hpp"
 
 using namespace pb200;
 
@@ -304,38 +262,6 @@ __global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
 }  // namespace pb200
 
 // ---------------------------------------------------------------------------------------------
-struct pb200_ensemble {
-    int device = 0;
-    size_t n_sys = 0;
-    int n_bodies = 0;
-    KParams P{};
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_ms = 0.f;
-    bool timing_pending = false;
-    uint64_t launches = 0;
-    std::vector<void*> allocations;
-    pb200_case_t tmpl{};                // structure + uniform scalars (system 0 image at creation)
-    std::vector<pb200_case_t> cases;    // per-system images when n_cases == n_systems (params may differ), else 1
-    int coord = 0, gr = PB200_GR_DISABLED;
-    // device arrays that are not part of KParams constness
-    double *d_mass = nullptr, *d_mass_g = nullptr, *d_sigma = nullptr, *d_k2t = nullptr, *d_k2f = nullptr, *d_roche = nullptr;
-    double *d_energy = nullptr, *d_angmom = nullptr;
-    double *d_wind_k = nullptr, *d_wind_sat = nullptr, *d_diss = nullptr, *d_diss_scale = nullptr;
-    double* d_gather = nullptr;   // staging of pb200_ensemble_get_case
-    unsigned int* d_records = nullptr;
-    size_t records_capacity = 0;
-    double recovery_snapshot_period = 0.;
-    int arithmetic = PB200_ARITH_FAST;
-    int sm_count = 0;
-    bool perturbed = false;       // built by pb200_ensemble_create_perturbed: heliocentric fields of the image are per member
-    bool force_generic = false;   // PB200_FORCE_GENERIC=1 in the environment: bypass the 8-body specialisation (A/B tests)
-    // host mirror of the ensemble clock (exact snapshot counting without a device round trip)
-    bool uniform_clock = true;
-    double clock_t = 0., clock_last_hist = -1.;
-    size_t hist_pending_host = 0;
-};
-
 template <class T>
 static int dev_alloc(pb200_ensemble* e, T** p, size_t count) {
     void* q = nullptr;
@@ -351,87 +277,6 @@ static int dev_alloc(pb200_ensemble* e, T** p, size_t count) {
 static bool is_dynamical_tide_evolution(const pb200_body_t& b) {
     return b.evolution_type == PB200_EVO_GALLETBOLMONT2017 || b.evolution_type == PB200_EVO_BOLMONTMATHIS2016 ||
            (b.evolution_type == PB200_EVO_LECONTECHABRIER2013 && b.evolution_parameter != 0.);
-}
-
-// Wave quantisation: `grid` CTAs of equal length on `slots` resident CTAs leave the last wave partly empty (65536
-// TRAPPIST-1 systems = 4096 CTAs on 444 slots = 9.23 waves: 7.7 % of the GPU-time idle). Cutting every CTA's steps into k
-// consecutive pieces makes the unit of scheduling k times shorter: 36.9 waves of quarter-length CTAs lose 0.3 %.
-// Returns the number of pieces (1 = plain launch). PB200_PIECES in the environment overrides (experiments).
-static unsigned plan_pieces(unsigned grid, unsigned slots, unsigned long long n_steps) {
-    if (const char* f = getenv("PB200_PIECES")) { int k = atoi(f); if (k >= 1 && (unsigned long long)k <= n_steps) return (unsigned)k; }
-    if (slots == 0 || grid <= slots) return 1;   // everything is resident at once: pieces of a group would only serialise
-    auto eff = [&](unsigned k) { double w = (double)grid * k / slots; return w / std::ceil(w); };
-    unsigned best = 1;
-    double best_eff = eff(1);
-    for (unsigned k = 2; k <= 8; k++) {
-        if (n_steps / k < 50) break;              // keep the per-piece state hand-over through HBM negligible
-        if (eff(k) > best_eff + 0.005) { best = k; best_eff = eff(k); }
-    }
-    return best;
-}
-
-template <class K>
-static cudaError_t launch_sliced(pb200_ensemble* e, K kernel, int& configured_device, int& blocks_per_sm, unsigned grid, unsigned long long n) {
-    // PB200_SMEM_PAD_KB (experiments only): extra dynamic shared memory per CTA, to lower the residency of the same binary
-    static const size_t pad = []() { const char* v = getenv("PB200_SMEM_PAD_KB"); return v ? (size_t)atoi(v) * 1024 : (size_t)0; }();
-    const size_t smem = PB_SMEM_BYTES + pad;
-    if (configured_device != e->device) {
-        // the cold slots need more than the default 48 KB of dynamic shared memory
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, PB_BLOCK, smem);
-        if (err != cudaSuccess) return err;
-        configured_device = e->device;
-    }
-    e->P.n_groups = grid;
-    e->P.n_pieces = plan_pieces(grid, (unsigned)(blocks_per_sm * e->sm_count), n);
-    if (e->P.n_pieces > 1) {
-        cudaError_t err = cudaMemsetAsync(e->P.sched, 0, (size_t)(grid + 1) * sizeof(unsigned int), e->stream);
-        if (err != cudaSuccess) return err;
-    }
-    kernel<<<grid * e->P.n_pieces, PB_BLOCK, smem, e->stream>>>(e->P, n);
-    return cudaGetLastError();
-}
-
-template <int COORD, int GR, int ARITH>
-static cudaError_t launch_one(pb200_ensemble* e, unsigned grid, unsigned long long n) {
-    static thread_local int configured_device = -1, blocks_per_sm = 0;
-    return launch_sliced(e, pbgen::whfast_steps_kernel<COORD, GR, ARITH>, configured_device, blocks_per_sm, grid, n);
-}
-
-// 8 bodies, host at index 0, democratic heliocentric, tides + flattening + Kidder1995, fast arithmetic: the specialised instance
-static cudaError_t launch_n8(pb200_ensemble* e, unsigned grid, unsigned long long n) {
-    static thread_local int configured_device = -1, blocks_per_sm = 0;
-    return launch_sliced(e, pbn8::whfast_steps_kernel<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995, 0>, configured_device,
-                         blocks_per_sm, grid, n);
-}
-
-template <int N>
-static cudaError_t launch_small(pb200_ensemble* e, unsigned grid, unsigned long long n) {
-    static thread_local int configured_device = -1, blocks_per_sm = 0;
-    if (N == 2)
-        return launch_sliced(e, pbn2::whfast_steps_kernel<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995, 0>, configured_device,
-                             blocks_per_sm, grid, n);
-    return launch_sliced(e, pbn3::whfast_steps_kernel<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995, 0>, configured_device,
-                         blocks_per_sm, grid, n);
-}
-
-template <int COORD>
-static cudaError_t launch_gr(pb200_ensemble* e, unsigned grid, unsigned long long n) {
-    if (e->arithmetic == PB200_ARITH_STRICT) {
-        switch (e->gr) {
-            case PB200_GR_KIDDER1995: return launch_one<COORD, PB200_GR_KIDDER1995, 1>(e, grid, n);
-            case PB200_GR_ANDERSON1975: return launch_one<COORD, PB200_GR_ANDERSON1975, 1>(e, grid, n);
-            case PB200_GR_NEWHALL1983: return launch_one<COORD, PB200_GR_NEWHALL1983, 1>(e, grid, n);
-            default: return launch_one<COORD, PB200_GR_DISABLED, 1>(e, grid, n);
-        }
-    }
-    switch (e->gr) {
-        case PB200_GR_KIDDER1995: return launch_one<COORD, PB200_GR_KIDDER1995, 0>(e, grid, n);
-        case PB200_GR_ANDERSON1975: return launch_one<COORD, PB200_GR_ANDERSON1975, 0>(e, grid, n);
-        case PB200_GR_NEWHALL1983: return launch_one<COORD, PB200_GR_NEWHALL1983, 0>(e, grid, n);
-        default: return launch_one<COORD, PB200_GR_DISABLED, 0>(e, grid, n);
-    }
 }
 
 extern "C" {
@@ -772,7 +617,7 @@ int pb200_ensemble_set_snapshot_periods(pb200_ensemble_t* e, double historic, do
 
 int pb200_ensemble_set_arithmetic(pb200_ensemble_t* e, int mode) {
     if (!e) return set_error(PB200_E_INVALID, "null ensemble");
-    if (mode != PB200_ARITH_FAST && mode != PB200_ARITH_STRICT) return set_error(PB200_E_INVALID, "unknown arithmetic mode");
+    if (mode != PB200_ARITH_FAST && mode != PB200_ARITH_STRICT && mode != PB200_ARITH_HYBRID) return set_error(PB200_E_INVALID, "unknown arithmetic mode");
     e->arithmetic = mode;
     return PB200_OK;
 }
@@ -829,17 +674,19 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
     {
         cudaError_t err;
-        const bool n8 = (e->n_bodies == 8 || e->n_bodies == 2 || e->n_bodies == 3) && e->P.host == 0 && e->coord == PB200_COORD_DEMOCRATIC_HELIOCENTRIC &&
-                        e->gr == PB200_GR_KIDDER1995 && e->P.flags == (FLAG_TIDES | FLAG_FLAT | FLAG_GR) &&
-                        e->arithmetic == PB200_ARITH_FAST && !e->force_generic;
-        if (n8 && e->n_bodies == 8) err = launch_n8(e, grid, n_steps);
-        else if (n8 && e->n_bodies == 2) err = launch_small<2>(e, grid, n_steps);
-        else if (n8) err = launch_small<3>(e, grid, n_steps);
-        else switch (e->coord) {
-            case PB200_COORD_JACOBI: err = launch_gr<PB200_COORD_JACOBI>(e, grid, n_steps); break;
-            case PB200_COORD_DEMOCRATIC_HELIOCENTRIC: err = launch_gr<PB200_COORD_DEMOCRATIC_HELIOCENTRIC>(e, grid, n_steps); break;
-            default: err = launch_gr<PB200_COORD_WHDS>(e, grid, n_steps); break;
-        }
+        // compile-time geometry builds (kernels_tu.cu): host at index 0 and one of the effect sets of the BASELINE configurations
+        const bool fixed_ok = e->P.host == 0 && !e->force_generic;
+        const bool dh = e->coord == PB200_COORD_DEMOCRATIC_HELIOCENTRIC, kidder = e->gr == PB200_GR_KIDDER1995;
+        const int tfg = FLAG_TIDES | FLAG_FLAT | FLAG_GR;
+        if (fixed_ok && e->n_bodies == 8 && dh && kidder && e->P.flags == tfg) err = pb200_launch_n8(e, grid, n_steps);
+        else if (fixed_ok && e->n_bodies == 2 && dh && kidder && e->P.flags == tfg) err = pb200_launch_n2(e, grid, n_steps);
+        else if (fixed_ok && e->n_bodies == 3 && dh && kidder && e->P.flags == tfg) err = pb200_launch_n3(e, grid, n_steps);
+        else if (fixed_ok && e->n_bodies == 2 && dh && e->gr == PB200_GR_DISABLED && e->P.flags == FLAG_TIDES) err = pb200_launch_n2t(e, grid, n_steps);
+        else if (fixed_ok && e->n_bodies == 3 && (dh || e->coord == PB200_COORD_JACOBI) && kidder && e->P.flags == (tfg | FLAG_EVO))
+            err = pb200_launch_n3e(e, grid, n_steps);
+        else if (e->arithmetic == PB200_ARITH_FAST) err = pb200_launch_generic_fast(e, grid, n_steps);
+        else if (e->arithmetic == PB200_ARITH_STRICT) err = pb200_launch_generic_strict(e, grid, n_steps);
+        else err = pb200_launch_generic_hybrid(e, grid, n_steps);
         e->launches++;
         if (err != cudaSuccess) return set_error(PB200_E_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(err));
     }

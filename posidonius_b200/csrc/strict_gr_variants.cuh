@@ -1,9 +1,9 @@
 // strict_gr_variants.cuh — PB200_ARITH_STRICT versions of the Anderson1975 and Newhall1983 general relativity variants
 // (effects/general_relativity.rs:461-895): every operation an IEEE round-to-nearest add/mul/div/sqrt in the association
 // order of the reference source, transcribed from the CPU oracle (oracle_core.hpp: gr_newtonian, gr_anderson, gr_newhall),
-// sums over bodies in the reference's loop order. The lanes of a group exchange through the strict mode's exchange columns
-// X_0 .. X_11 (free between the rounds of additional_effects_strict); inertial positions are in S_RX while the midpoint runs.
-// Included inside namespace PB_NS after strict_effects.cuh; no include guard on purpose.
+// sums over bodies in the reference's loop order. The lanes of a group exchange through the columns X_0 .. X_8 (the slots of
+// the Kidder1995 polynomials, which these variants never read; cold_slots.cuh); inertial positions are in S_RX while the
+// midpoint runs. Included inside namespace PB_NS after exact_effects.cuh; no include guard on purpose.
 
 namespace PB_NS {
 using namespace pb200;
@@ -42,7 +42,7 @@ __device__ __forceinline__ S3 gr_newtonian_strict(const KParams& P, const Roles&
 }
 
 // general_relativity.rs:461-636
-__device__ __forceinline__ void gr_anderson1975_strict(const KParams& P, const Roles& ro, const Cold& cold, int b, const Lane& q, S3 hr,
+__device__ __forceinline__ void gr_anderson1975_strict(const KParams& P, const Roles& ro, const Cold& cold, int b, size_t sys, const Lane& q, S3 hr,
                                                        S3 acc_newton, bool jacobi_coords, V3& a_out) {
     const int n = PB_N(P), host = PB_HOST(P);
     const S3 an = gr_newtonian_strict(P, ro, cold, b, hr, acc_newton, jacobi_coords);
@@ -71,7 +71,7 @@ __device__ __forceinline__ void gr_anderson1975_strict(const KParams& P, const R
         sa = s3(sa.x * pme + mk * ck.x, sa.y * pme + mk * ck.y, sa.z * pme + mk * ck.z);
     }
     const sd jacobi_star_mass = eta;
-    const sd mu = sd(cold.getk(host, K_MG));
+    const sd mu = sd(P.mass_g[(size_t)host * (size_t)P.n_sys + (ro.valid ? sys : 0)]);
     // fixed point on the velocity (:478-516), this lane's body
     {
         S3 vi = jv;

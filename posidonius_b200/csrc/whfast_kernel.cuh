@@ -148,7 +148,7 @@ __device__ __forceinline__ V3 shfl3(V3 a, int src) { return v3(shfl(a.x, src), s
 // Stumpff functions c0..c3 (whfast.rs:844-876) and Stiefel G-functions (whfast.rs:835-842), strict arithmetic
 // 1/13!, 1/12!, ..., 1/2! for the series below. Deliberately NOT const: as constant-bank operands the coefficients cost
 // nothing (DADD R, -R, c[3][..]); as literals each one is materialised by two UMOVs before every use.
-__constant__ double kInvFactorial[12] = {1. / 6227020800., 1. / 479001600., 1. / 39916800., 1. / 3628800., 1. / 362880., 1. / 40320.,
+static __constant__ double kInvFactorial[12] = {1. / 6227020800., 1. / 479001600., 1. / 39916800., 1. / 3628800., 1. / 362880., 1. / 40320.,
                                          1. / 5040., 1. / 720., 1. / 120., 1. / 24., 1. / 6., 1. / 2.};
 __device__ __forceinline__ void stumpff_cs3(sd z, sd& c0, sd& c1, sd& c2, sd& c3) {
     int n = 0;
@@ -334,38 +334,7 @@ __device__ __forceinline__ double table_interp(const double* __restrict__ time, 
 #define PB_BLOCK 64
 #endif
 
-enum ColdSlot : int {
-    // Kahan residuals (whfast.rs:117-119) and the midpoint's working set (whfast.rs:333-337)
-    S_EVX, S_EVY, S_EVZ, S_ELX, S_ELY, S_ELZ,
-    S_VOX, S_VOY, S_VOZ, S_LOX, S_LOY, S_LOZ,
-    S_DVX, S_DVY, S_DVZ, S_DLX, S_DLY, S_DLZ,
-    S_RX, S_RY, S_RZ,            // inertial position while the midpoint runs
-    S_AX, S_AY, S_AZ,            // Newtonian acceleration of the last gravity evaluation
-    // body parameters
-    K_M, K_MG, K_R, K_I,
-    // constants of the perturbation forces (every division with step-invariant operands is done once)
-    // (host-body quantities — its mass, inertia, 1/M — are read from the host's own column with getk, they have no slot)
-    // (C_AS .. C_MGS are one region of 16-byte pair cells in fast mode: Cold::get2 / set2)
-    C_INVI, C_INVM, C_AS, C_AP, C_KS, C_KP, C_ZP, C_ZH, C_DP1, C_DS1, C_MFA, C_SXS, C_BK, C_MGS, C_SPARE,
-    // constants of the coordinate transforms (strict)
-    // The host's columns of the last three are meaningless for the host body itself and carry the per-system values:
-    // K_ETAK <- total mass, K_BACKW <- refined reciprocal of the total mass, K_WHDSF <- refined reciprocal of the host
-    // mass (strict.cuh, srcp).
-    K_KMU, K_BACKW, K_WHDSF, K_ETAK,
-    // strict arithmetic mode (strict_effects.cuh): two more constants and the 4-vector exchange buffer for the host sums
-    Z_0, Z_1, X_0, X_1, X_2, X_3, X_4, X_5, X_6, X_7, X_8, X_9, X_10, X_11,
-    // dynamical tides: the sigma-free parts of the tidal constants (the pair-dependent sigma multiplies them per evaluation);
-    // D_2, D_3 are used by the strict mode only
-    D_2, D_3, D_0, D_1,
-    // exchange space of the fast-mode midpoint: six contributions to the host sums / their totals, spare
-    M_0, M_1, M_2, M_3, M_4, M_5, M_6, M_7,
-    N_COLD_SLOTS,
-    E_S = X_11,   // fast mode: X_11, D_2, D_3 as a triple (host spin exchange)
-    K_ROCHE2 = M_7,   // max over j > b of the squared Roche radius of the pair (b, j): the cheap pre-test of gravity()
-    // fast mode: 13 GR polynomial coefficients overlay the strict-mode slots (never live together)
-    G_0 = Z_0
-};
-
+// (the slot map itself — enum ColdSlot — is per geometry build: cold_slots.cuh)
 //
 // The same columns double as the exchange medium inside a group: a lane leaves a value in its own column of a slot,
 // __syncwarp(), and any lane of the group reads it with one LDS.64 (`getk`: column of body k). That replaces the
@@ -406,11 +375,6 @@ struct Cold {
         set2(region, 0, a.x, a.y); set2(region, 1, a.z, b.x); set2(region, 2, b.y, b.z);
     }
 };
-// pair regions of the midpoint (six slots each): Kahan residuals (v, L), originals (v, L), increments (v, L)
-enum : int { R_ERR = S_EVX, R_ORIG = S_VOX, R_INCR = S_DVX };
-// exchange triples of the core (dead midpoint slots)
-enum : int { E_A = S_VOX, E_B = S_LOX, E_C = S_DVX, E_D = S_DLX, E_R = S_RX };
-
 // Per-lane register state.
 struct Lane {
     S3 r, v;            // inertial position / velocity (strict arithmetic only)

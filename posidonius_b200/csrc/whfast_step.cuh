@@ -5,7 +5,7 @@
 // bodies that the reference accumulates serially are accumulated in the same order by walking the group with
 // shuffles (every lane carries the running sum, so all lanes hold bit-identical copies).
 #include "gr_variants.cuh"
-#include "strict_effects.cuh"
+#include "exact_effects.cuh"
 #include "strict_gr_variants.cuh"
 
 namespace PB_NS {
@@ -35,7 +35,7 @@ __device__ __forceinline__ void store_lane(const KParams& P, const Roles& ro, co
     const size_t cs = (size_t)PB_N(P) * ns;
     P.pos[i] = q.r.x.v; P.pos[i + cs] = q.r.y.v; P.pos[i + 2 * cs] = q.r.z.v;
     P.vel[i] = q.v.x.v; P.vel[i + cs] = q.v.y.v; P.vel[i + 2 * cs] = q.v.z.v;
-    P.acc[i] = cold.get(S_AX); P.acc[i + cs] = cold.get(S_AY); P.acc[i + 2 * cs] = cold.get(S_AZ);
+    // (the Newtonian acceleration is written by the step that computed it: store_acc)
     P.L[i] = q.L.x; P.L[i + cs] = q.L.y; P.L[i + 2 * cs] = q.L.z;
     P.spin[i] = q.s.x; P.spin[i + cs] = q.s.y; P.spin[i + 2 * cs] = q.s.z;
     V3 ev, el;
@@ -95,20 +95,20 @@ __device__ __forceinline__ S3 ordered_diff_others(const Cold& cold, S3 init, int
     return acc;
 }
 
-// ---- Distributed ordered sums: see the layout notes next to dist_ld (forces_fast.cuh).
-// the row of the scalar this lane reduces (lanes beyond the last scalar repeat it; their results are never read)
-__device__ __forceinline__ unsigned dist_row(const Cold& cold, int base, int b, int n_scalars) { return dist_self(cold) + (unsigned)((base + (b < n_scalars ? b : n_scalars - 1)) * PB_BLOCK * 8); }
-// acc (+/-)= term of body 1, 2, ... 7 in index order
-template <bool SUB>
-__device__ __forceinline__ sd dist_walk(unsigned row, sd acc) {
-#pragma unroll
-    for (int k = 1; k < 8; k++) { const sd t = sd(dist_ld(row, k)); acc = SUB ? acc - t : acc + t; }
-    return acc;
-}
-
 // Implicit midpoint on v and L (whfast.rs:322-466) around Universe::calculate_additional_effects.
 // Registers across the evaluation: v, L, spin, heliocentric position and 1/r. Originals, increments and Kahan
 // residuals sit in the cold slots and are touched once per iteration.
+//
+// ARITH selects the arithmetic of the perturbation forces:
+//   0 (PB200_ARITH_FAST)    every evaluation with the fast forces (forces_fast.cuh);
+//   1 (PB200_ARITH_STRICT)  every evaluation with the exact forces (exact_effects.cuh): bit-identical to the reference's arithmetic;
+//   2 (PB200_ARITH_HYBRID)  iterations 0 and 1 with the fast forces, every later one — among them the one whose increments
+//     are COMMITTED (the reference needs at least three iterations, whfast.rs:386) — with the exact forces. The committed
+//     increment, hence the new v, L and their Kahan residuals, carry the reference's roundings whenever the two uncommitted
+//     iterates rounded to the same doubles as the reference's, which they do except with probability ~ |dv| / |v| per
+//     component (the iterates enter the exact evaluation only through v_orig + dv / 2, and a relative error of 1e-15 in a
+//     dv of relative size 1e-8 .. 1e-6 rarely moves that sum across a rounding boundary). Nothing accumulates: the
+//     residuals are exact again after every committed evaluation.
 template <int COORD, int GR, int ARITH>
 __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, bool alive, Lane& q,
                                          double t, bool evolution, unsigned int& warnings, bool save_tides, size_t sys) {
@@ -119,15 +119,17 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
     cold.set3(S_RX, plain(q.r));
     cold.set6(R_ORIG, plain(q.v), q.L);
     cold.set6(R_INCR, v3(0., 0., 0.), v3(0., 0., 0.));
-    if (!ARITH) { cold.set3(M_0, plain(q.v)); cold.set3(E_S, q.s); }   // fast mode: the host's current v and last spin for the group
+    cold.set3(M_0, plain(q.v)); cold.set3(E_S, q.s);   // the host's current v and last spin for the group
     __syncwarp();
     const S3 rh_s = strict(cold.getk3(PB_HOST(P), S_RX));
     // idle lanes (host slot, padding) get a unit dummy so that rsqrt/div stay on their fast paths for the whole warp
     const S3 hr_s = ro.planet ? q.r - rh_s : s3(sd(1.), sd(0.), sd(0.));
     const V3 hr = plain(hr_s);
-    const double inv_d = ARITH ? 0. : rsqrt(dot(hr, hr));
+    const double inv_d = ARITH == 1 ? 0. : rsqrt(dot(hr, hr));
     const sd dist_s = ARITH ? ssqrt(hr_s.x * hr_s.x + hr_s.y * hr_s.y + hr_s.z * hr_s.z) : sd(1.);   // universe.rs:328-330
-    if (!ARITH) { q.rs_s = dot(hr, cold.getk3(PB_HOST(P), E_S)); q.rs_p = dot(hr, q.s); }   // Q3: previous spins, new position
+    // Q3: previous spins, new position
+    if (ARITH) { q.rs_s = sdot(hr_s, strict(cold.getk3(PB_HOST(P), E_S))).v; q.rs_p = sdot(hr_s, strict(q.s)).v; }
+    else { q.rs_s = dot(hr, cold.getk3(PB_HOST(P), E_S)); q.rs_p = dot(hr, q.s); }
     bool done = !alive;  // group-uniform
     bool converged = false;
 #pragma unroll 1
@@ -135,40 +137,47 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
         if (!__any_sync(FULL, !done)) break;
         if (evolution && it == 0 && (PB_FLAGS(P) & FLAG_EVO)) {
             // once per step in evolving configurations: re-derive the constants unconditionally (warp-uniform control flow
-            // around the shuffles inside make_consts*)
+            // around the shuffles inside make_consts)
             (void)evolve_lane(P, ro, cold, b, sys, t, alive);
             __syncwarp();
-            if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
+            make_consts(P, ro, cold, hl, b, sys);
         }
-        const S3 vh_s = ARITH ? shfl3(q.v, hl) : strict(cold.getk3(PB_HOST(P), M_0));
-        // fast mode: the forces hold no division, and every term of a non-orbiting lane is multiplied by a zero constant
-        // (make_consts), so the host / padding lanes need no dummy velocity (six selects less per evaluation)
-        const S3 hv_s = (ARITH && !ro.planet) ? s3(sd(0.), sd(1.), sd(0.)) : q.v - vh_s;
-        V3 hv = plain(hv_s);
+        const S3 vh_s = strict(cold.getk3(PB_HOST(P), M_0));
+        const S3 hv_s = q.v - vh_s;
         V3 a, dldt;
         // the tidal internals of a step's last evaluation are kept for the next snapshot's denergy_dt (`!done`: a converged
         // system's later evaluations are discarded)
         const bool save_now = save_tides && !done;
         const bool evolve_now = evolution && it == 0;
-        if (ARITH) additional_effects_strict<GR>(P, ro, cold, hl, b, sys, t, evolve_now, q, hr_s, dist_s, hv_s, a, dldt, save_now);
-        else additional_effects<GR>(P, ro, cold, hl, b, sys, t, evolve_now, q, hr, inv_d, hv, a, dldt, save_now);
+        const bool exact_now = ARITH == 1 || (ARITH == 2 && it >= 2);   // warp-uniform
+        if (exact_now) {
+            // the idle lanes divide by |v|: a unit dummy
+            const S3 hv_x = ro.planet ? hv_s : s3(sd(0.), sd(1.), sd(0.));
+            additional_effects_exact<GR>(P, ro, cold, hl, b, sys, t, evolve_now, q, hr_s, dist_s, hv_x, a, dldt, save_now);
+        } else {
+            // the fast forces hold no division, and every term of a non-orbiting lane is multiplied by a zero constant
+            // (make_consts), so the host / padding lanes need no dummy velocity (six selects less per evaluation)
+            additional_effects<GR, ARITH == 2>(P, ro, cold, hl, b, sys, t, evolve_now, q, hr, inv_d, plain(hv_s), a, dldt, save_now);
+        }
+#if !PB_FIXED_N
         if (GR == PB200_GR_ANDERSON1975 || GR == PB200_GR_NEWHALL1983) {
             if (PB_FLAGS(P) & FLAG_GR) {
                 V3 ag;
                 Lane qq = q;
                 qq.r = strict(cold.get3(S_RX));
                 V3 acc_newton = cold.get3(S_AX);
-                if (ARITH) {
-                    if (GR == PB200_GR_ANDERSON1975) gr_anderson1975_strict(P, ro, cold, b, qq, hr_s, strict(acc_newton), COORD == PB200_COORD_JACOBI, ag);
+                if (exact_now) {
+                    if (GR == PB200_GR_ANDERSON1975) gr_anderson1975_strict(P, ro, cold, b, sys, qq, hr_s, strict(acc_newton), COORD == PB200_COORD_JACOBI, ag);
                     else gr_newhall1983_strict(P, ro, cold, b, qq, hr_s, strict(acc_newton), COORD == PB200_COORD_JACOBI, ag);
                     a = plain(strict(a) + strict(ag));
                 } else {
-                    if (GR == PB200_GR_ANDERSON1975) gr_anderson1975(P, ro, cold, gb, hl, b, qq, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
+                    if (GR == PB200_GR_ANDERSON1975) gr_anderson1975(P, ro, cold, gb, hl, b, sys, qq, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
                     else gr_newhall1983(P, ro, cold, gb, hl, b, qq, hr, acc_newton, COORD == PB200_COORD_JACOBI, ag);
                     a = a + ag;
                 }
             }
         }
+#endif
         // final = orig + (dt * a - err)   (whfast.rs:353-378), with the previous final for the convergence test
         V3 vo_p, Lo, ev, el;
         cold.get6(R_ORIG, vo_p, Lo); cold.get6(R_ERR, ev, el);
@@ -209,12 +218,10 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
                 if (PB_SPIN(P)) q.L = v3(__dmul_rn(0.5, __dadd_rn(Lo.x, Lf.x)), __dmul_rn(0.5, __dadd_rn(Lo.y, Lf.y)), __dmul_rn(0.5, __dadd_rn(Lo.z, Lf.z)));
             }
         }
-        if (!ARITH) {
-            // publish the (possibly averaged) velocity for the next evaluation; the host has collected its totals by now
-            __syncwarp();
-            cold.set3(M_0, plain(q.v));
-            __syncwarp();
-        }
+        // publish the (possibly averaged) velocity for the next evaluation; the host has collected its totals by now
+        __syncwarp();
+        cold.set3(M_0, plain(q.v));
+        __syncwarp();
     }
     q.r = strict(cold.get3(S_RX));
     if (alive) {
@@ -350,7 +357,6 @@ __device__ __forceinline__ S3 gravity_n8_dh(const KParams& P, const Roles& ro, c
 #else
 #define PB_KERNEL_ATTR __launch_bounds__(PB_BLOCK, PB_MIN_BLOCKS)
 #endif
-#define PB_SMEM_BYTES (N_COLD_SLOTS * PB_BLOCK * sizeof(double))
 
 template <int COORD, int GR, int ARITH>
 __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
@@ -404,14 +410,20 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
             auto ld3 = [&](const double* a) { return v3(ldm(a + i), ldm(a + i + cs), ldm(a + i + 2 * cs)); };
             q.r = strict(ld3(P.pos)); q.v = strict(ld3(P.vel));
             q.L = ld3(P.L); q.s = ld3(P.spin);
-            cold.set6(R_ERR, ld3(P.verr), ld3(P.lerr)); cold.set3(S_AX, ld3(P.acc));
-            cold.set(K_M, P.mass[i]); cold.set(K_MG, P.mass_g[i]); cold.set(K_R, ldm(P.radius + i)); cold.set(K_I, ldm(P.moi + i));
+            cold.set6(R_ERR, ld3(P.verr), ld3(P.lerr));
+#if !PB_FIXED_N
+            cold.set3(S_AX, ld3(P.acc));
+#endif
+            cold.set(K_M, P.mass[i]); cold.set(K_R, ldm(P.radius + i)); cold.set(K_I, ldm(P.moi + i));
         } else {
             // padding lanes: finite, non-zero dummies (never read by live lanes, never stored)
             q.r = s3(sd(1. + b), sd(0.), sd(0.)); q.v = s3(sd(0.), sd(0.), sd(0.));
             q.L = v3(0., 0., 1.); q.s = v3(0., 0., 1.);
-            cold.set6(R_ERR, v3(0., 0., 0.), v3(0., 0., 0.)); cold.set3(S_AX, v3(0., 0., 0.));
-            cold.set(K_M, 1.); cold.set(K_MG, 1.); cold.set(K_R, 1.); cold.set(K_I, 1.);
+            cold.set6(R_ERR, v3(0., 0., 0.), v3(0., 0., 0.));
+#if !PB_FIXED_N
+            cold.set3(S_AX, v3(0., 0., 0.));
+#endif
+            cold.set(K_M, 1.); cold.set(K_R, 1.); cold.set(K_I, 1.);
         }
         if (sys_ok) {
             st.t = ldm(P.t + sys); st.last_hist = ldm(P.last_hist + sys);
@@ -436,14 +448,16 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
         cold.set(K_ROCHE2, rmax2);
     }
     bool alive = sys_ok && st.status == PB200_STATUS_OK;
-    if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
+    make_consts(P, ro, cold, hl, b, sys);
 
     // constants of the transforms, all strict and in the reference's order; parked in the cold slots
     {
         __syncwarp();
-        const sd m_s = sd(cold.get(K_M)), mg_s = sd(cold.get(K_MG));
+        // (the gravitational masses are only read here and in make_consts: they stay in global memory)
+        const size_t ns_ = (size_t)P.n_sys, sys_ = sys_ok ? sys : 0;
+        const sd m_s = sd(cold.get(K_M)), mg_s = sd(ro.valid ? P.mass_g[(size_t)b * ns_ + sys_] : 1.);
         const sd M_s = sd(cold.getk(PB_HOST(P), K_M));       // m0
-        const sd Mg_s = sd(cold.getk(PB_HOST(P), K_MG));
+        const sd Mg_s = sd(P.mass_g[(size_t)PB_HOST(P) * ns_ + sys_]);
         // total mass as inertial_to_*_posvel accumulate it: host first, then the others in index order
         sd mtot = M_s;
         sd eta_k = sd(0.), mu_k = sd(0.);        // Jacobi: cumulative mass / mass_g up to and including this body
@@ -452,7 +466,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
         for (int k = 0; k < n; k++) {
             if (k == PB_HOST(P)) continue;
             mtot = mtot + sd(cold.getk(k, K_M));
-            mu = mu + sd(cold.getk(k, K_MG));
+            mu = mu + sd(P.mass_g[(size_t)k * ns_ + sys_]);
             if (k == b) { eta_k = mtot; mu_k = mu; }
         }
         // per-body constants of the heliocentric transforms (whfast.rs:1015, 1101, 1112-1114), divided once
@@ -496,7 +510,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                 if (PB_FLAGS(P) & FLAG_EVO) {
                     (void)evolve_lane(P, ro, cold, b, sys, st.t, snap);
                     __syncwarp();
-                    if (ARITH) make_consts_strict(P, ro, cold, hl, b, sys); else make_consts(P, ro, cold, hl, b, sys);
+                    make_consts(P, ro, cold, hl, b, sys);
                 }
                 if (snap) { sd I = sd(cold.get(K_I)); q.s = v3((sd(q.L.x) / I).v, (sd(q.L.y) / I).v, (sd(q.L.z) / I).v); }   // spin = L / I (common.rs:9-11)
 #if !PB_FIXED_N
@@ -538,6 +552,8 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                 }
             }
         }
+        // last step of this CTA's piece, or the step after which the system completes (whfast.rs:300, the same roundings)
+        const bool leaves_now = (step + 1 == step_end) || (__dadd_rn(__dadd_rn(st.t, P.dt), P.dt) > P.time_limit);
         // internals needed by the NEXT snapshot's denergy_dt are those of this step's last evaluation
         const bool save_tides = (step + 1 == step_end) || (__dadd_rn(st.last_hist, P.hist_period) <= __dadd_rn(st.t, P.dt));
 
@@ -744,7 +760,16 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         }
                         for (int off = W >> 1; off > 0; off >>= 1) { int o = __shfl_xor_sync(FULL, code, off); code = o < code ? o : code; }
                         const bool died = alive && code != 0x7fffffff;
+#if !PB_FIXED_N
                         if (alive) cold.set3(S_AX, plain(anew_s));
+#endif
+                        // The Newtonian acceleration is part of the state image (Particle.inertial_acceleration) but not of the
+                        // on-chip state: the step that may be the system's last of this launch writes it out
+                        if (alive && (leaves_now || died) && ro.valid) {
+                            const size_t ns = (size_t)P.n_sys;
+                            const size_t i = (size_t)b * ns + sys, cs = (size_t)n * ns;
+                            P.acc[i] = anew_s.x.v; P.acc[i + cs] = anew_s.y.v; P.acc[i + 2 * cs] = anew_s.z.v;
+                        }
                         if (died) {
                             st.status = code & 15; st.event_step = st.steps_done; alive = false;
                             store_lane(P, ro, cold, sys, b, q, st);

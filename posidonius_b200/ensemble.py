@@ -34,9 +34,10 @@ def validate_case(case, tables):
 
 
 class Ensemble:
-    def __init__(self, cases, tables, n_systems=None, device=0, arithmetic=abi.ARITH_FAST):
+    def __init__(self, cases, tables, n_systems=None, device=0, arithmetic=None):
         """cases: one abi.Case (replicated n_systems times) or a ctypes array / list of n_systems cases.
-        arithmetic: abi.ARITH_FAST (default) or abi.ARITH_STRICT (bit-reproducible forces, see the header)."""
+        arithmetic: None = the library default (abi.ARITH_HYBRID: fast iterates, exact committed evaluation), abi.ARITH_STRICT
+        (every evaluation exact, bit-reproducible) or abi.ARITH_FAST (see the header)."""
         if isinstance(cases, abi.Case):
             arr = (abi.Case * 1)(cases)
             n_cases = 1
@@ -53,11 +54,11 @@ class Ensemble:
         self.n_systems = n_systems
         self.n_particles = lib().pb200_ensemble_n_particles(self._h)
         self.device = device
-        if arithmetic != abi.ARITH_FAST:
+        if arithmetic is not None:
             self.set_arithmetic(arithmetic)
 
     @classmethod
-    def perturbed(cls, base, tables, n_systems, seed, amplitude=1e-3, device=0, arithmetic=abi.ARITH_FAST):
+    def perturbed(cls, base, tables, n_systems, seed, amplitude=1e-3, device=0, arithmetic=None):
         """pb200_ensemble_create_perturbed: the synthetic ensemble of SURVEY §8d built on the device (member 0 = base,
         member k = SplitMix64-perturbed copy); the host never holds per-member case images."""
         self = cls.__new__(cls)
@@ -68,7 +69,7 @@ class Ensemble:
         self.n_systems = n_systems
         self.n_particles = lib().pb200_ensemble_n_particles(self._h)
         self.device = device
-        if arithmetic != abi.ARITH_FAST:
+        if arithmetic is not None:
             self.set_arithmetic(arithmetic)
         return self
 

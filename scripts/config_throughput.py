@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Throughput of every BASELINE.json configuration on one GPU (system-steps/s and algorithmic TFLOP/s with the exact
-flop counts of the oracle's counting build). usage: config_throughput.py [steps_per_launch]"""
+flop counts of the oracle's counting build). usage: config_throughput.py [steps_per_launch] [modes, e.g. hybrid,fast,strict]"""
 import os
 import sys
 import time
@@ -19,28 +19,32 @@ CONFIGS = [("c1_example", 65536), ("c2_case3", 4096), ("c2_case3", 65536), ("c3_
 
 
 def main():
+    from posidonius_b200 import abi
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+    modes = (sys.argv[2] if len(sys.argv) > 2 else "hybrid").split(",")
+    mode_id = {"fast": abi.ARITH_FAST, "strict": abi.ARITH_STRICT, "hybrid": abi.ARITH_HYBRID}
     peak = measure_fp64_peak(0, 30.0)
     print("FP64 peak (DFMA chains) %.2f TFLOP/s" % (peak / 1e12))
-    print("%-22s %8s %6s %14s %10s %8s" % ("config", "systems", "bodies", "system-steps/s", "TFLOP/s", "of peak"))
+    print("%-22s %-6s %8s %6s %14s %10s %8s" % ("config", "arith", "systems", "bodies", "system-steps/s", "TFLOP/s", "of peak"))
     for name, n_sys in CONFIGS:
-        d = config_case(name)
-        d["universe"]["time_limit"] = 1e12
-        d["historic_snapshot_period"] = 1e11
-        case, tables = case_from_dict(d)
-        flops = count_flops(case, tables, 100)["flops_per_step"]
-        cases = make_ensemble_cases(case, n_sys, 5)
-        with Ensemble(cases, tables) as ens:
-            ens.initialize_physical_values()
-            ens.iterate(steps)
-            best = 1e30
-            for _ in range(3):
-                ens.iterate(steps, synchronize=False)
-                best = min(best, ens.last_step_ms())
-            st, _, _ = ens.status()
-        rate = n_sys * steps / (best * 1e-3)
-        print("%-22s %8d %6d %14.4g %10.2f %7.1f%%   alive %d" % (name, n_sys, case.n_particles, rate, rate * flops / 1e12,
-                                                                100.0 * rate * flops / peak, int((st == 0).sum())))
+      for mode in modes:
+          d = config_case(name)
+          d["universe"]["time_limit"] = 1e12
+          d["historic_snapshot_period"] = 1e11
+          case, tables = case_from_dict(d)
+          flops = count_flops(case, tables, 100)["flops_per_step"]
+          cases = make_ensemble_cases(case, n_sys, 5)
+          with Ensemble(cases, tables, arithmetic=mode_id[mode]) as ens:
+              ens.initialize_physical_values()
+              ens.iterate(steps)
+              best = 1e30
+              for _ in range(3):
+                  ens.iterate(steps, synchronize=False)
+                  best = min(best, ens.last_step_ms())
+              st, _, _ = ens.status()
+          rate = n_sys * steps / (best * 1e-3)
+          print("%-22s %-6s %8d %6d %14.4g %10.2f %7.1f%%   alive %d" % (name, mode, n_sys, case.n_particles, rate, rate * flops / 1e12,
+                                                                  100.0 * rate * flops / peak, int((st == 0).sum())))
 
 
 if __name__ == "__main__":

@@ -2,11 +2,14 @@
 
 Tolerances (all written here, justified in DESIGN.md §Parity):
   * golden fixtures (199 steps): the reference's own bar, |x - golden| < 1e-14 absolute on r, v, a.
-  * configuration ensembles vs the oracle on the same seeded inputs: 1e-10 relative (vector norm per body) on
-    r, v, spin after 10^3 steps, and FAST_TOL_1E4 after 10^4 steps. The WHFast core is bit-reproducing; the
-    perturbation forces use FMA/reciprocal arithmetic, so occasional last-bit differences seed the same
-    t^1.5 phase divergence that the CPU restatement shows against ITSELF when FMA contraction is enabled
-    (2.1e-10 on TRAPPIST-1 after 10^4 steps, measured).
+  * configuration ensembles vs the oracle on the same seeded inputs, DEFAULT arithmetic (PB200_ARITH_HYBRID: fast iterates,
+    exact committed evaluation of the implicit midpoint): the north-star bar, 1e-10 relative (vector norm per body) on
+    r, v, spin after 10^3 AND after 10^4 steps, 1024 members per configuration, maximum over members and bodies; most
+    members are bit-identical.
+  * PB200_ARITH_STRICT: bit-identical (array_equal) after 10^4 steps.
+  * PB200_ARITH_FAST (opt-in): FAST_TOL_1E4 = 1e-9 after 10^4 steps. Every evaluation then uses FMA/reciprocal arithmetic,
+    and last-bit differences of the committed increments seed the same t^1.5 phase divergence that the CPU restatement
+    shows against ITSELF when FMA contraction is enabled (2.1e-10 on TRAPPIST-1 after 10^4 steps, measured).
 """
 import json
 import os
@@ -23,7 +26,8 @@ with open(os.path.join(GOLDEN, "manifest.json")) as _f:
     _MANIFEST = json.load(_f)
 
 TOL_1E3 = 1e-10
-FAST_TOL_1E4 = 1e-9
+TOL_1E4 = 1e-10        # BASELINE.json north_star: 1e-10 relative after 10^4 steps
+FAST_TOL_1E4 = 1e-9    # the opt-in all-fast arithmetic only
 
 
 @pytest.fixture(scope="module")
@@ -54,7 +58,7 @@ def test_golden_fixture_on_gpu(E, name):
                     assert np.all(np.abs(got - want) < fx["tolerance_abs"]), (name, s, i, key, got, want)
 
 
-def _run_config(E, idx, name, n_sys, steps, arithmetic=0):
+def _run_config(E, idx, name, n_sys, steps, arithmetic=None):
     from oracle.binding import run_ensemble
     from posidonius_b200.case import case_from_dict
     from posidonius_b200.perturb import make_ensemble_cases
@@ -82,7 +86,22 @@ def test_config_ensemble_vs_oracle_1e3_steps(E, idx, name):
 
 @pytest.mark.parametrize("idx,name", list(enumerate(CONFIG_NAMES)))
 def test_config_ensemble_vs_oracle_1e4_steps(E, idx, name):
-    g, o, st, ost = _run_config(E, idx, name, 16, 10000)
+    """The north-star criterion in the default (benchmarked) arithmetic: 1024 perturbed members per configuration, 10^4
+    steps, maximum over members and bodies of the relative error of r, v, spin below 1e-10; at least 90 % of the members
+    bit-identical to the oracle in r and v (the committed evaluation of every midpoint is exact)."""
+    g, o, st, ost = _run_config(E, idx, name, 1024, 10000)
+    assert np.array_equal(st, ost)
+    for k in ("position", "velocity", "spin", "angular_momentum"):
+        assert rel_err(g[k], o[k]) < TOL_1E4, (name, k, rel_err(g[k], o[k]))
+    same = np.all(g["position"] == o["position"], axis=(1, 2)) & np.all(g["velocity"] == o["velocity"], axis=(1, 2))
+    assert same.mean() >= 0.9, (name, same.mean())
+
+
+@pytest.mark.parametrize("idx,name", list(enumerate(CONFIG_NAMES)))
+def test_fast_arithmetic_vs_oracle_1e4_steps(E, idx, name):
+    """The opt-in all-fast arithmetic (every midpoint evaluation with FMA / reciprocal forces): 1e-9 after 10^4 steps."""
+    from posidonius_b200 import abi
+    g, o, st, ost = _run_config(E, idx, name, 16, 10000, arithmetic=abi.ARITH_FAST)
     assert np.array_equal(st, ost)
     for k in ("position", "velocity", "spin"):
         assert rel_err(g[k], o[k]) < FAST_TOL_1E4, (name, k, rel_err(g[k], o[k]))
@@ -294,7 +313,7 @@ def _ten_body_case():
     return d
 
 
-@pytest.mark.parametrize("arithmetic", [0, 1])
+@pytest.mark.parametrize("arithmetic", [0, 1, 2])
 def test_maximum_size_system_ten_bodies(E, arithmetic):
     """MAX_PARTICLES bodies (src/constants.rs:3): 16 lanes per system, 6 of them padding. Strict mode: bit-identical."""
     from oracle.binding import run_ensemble
@@ -311,10 +330,10 @@ def test_maximum_size_system_ten_bodies(E, arithmetic):
     o = oracle_state_of(oc)
     assert np.array_equal(st, ost)
     for k in ("position", "velocity", "spin", "angular_momentum"):
-        if arithmetic:
+        if arithmetic == 1:
             assert np.array_equal(g[k], o[k]), k
         else:
-            assert rel_err(g[k], o[k]) < TOL_1E3, (k, rel_err(g[k], o[k]))
+            assert rel_err(g[k], o[k]) < (TOL_1E3 if arithmetic == 0 else 1e-13), (k, rel_err(g[k], o[k]))
 
 
 def test_full_size_ensemble_properties(E):
@@ -361,7 +380,7 @@ def _pair_map(case):
 
 
 @pytest.mark.parametrize("name", _SOLAR_LIKE)
-@pytest.mark.parametrize("arithmetic", [0, 1])
+@pytest.mark.parametrize("arithmetic", [0, 1, 2])
 def test_wind_and_dynamical_tides_vs_oracle(E, name, arithmetic):
     """Perturbed 12-member ensembles of the solar-like fixtures (wind on all, pair-dependent sigma on two) for 2000 steps:
     r, v, L, spin against the oracle at 1e-10 (fast) / 1e-13 (strict: only powf(-1.5) is not IEEE-exact), and the state
@@ -382,7 +401,7 @@ def test_wind_and_dynamical_tides_vs_oracle(E, name, arithmetic):
     oc, ost, _ = run_ensemble(cases, n_sys, tables, steps, True, 4)
     o = oracle_state_of(oc)
     assert np.array_equal(st, ost) and np.all(st == 0)
-    tol = 1e-13 if arithmetic else TOL_1E3
+    tol = 1e-13 if arithmetic else TOL_1E3   # strict and hybrid: only powf(-1.5) is not IEEE-exact
     for k in ("position", "velocity", "spin", "angular_momentum"):
         assert rel_err(g[k], o[k]) < tol, (name, k, rel_err(g[k], o[k]))
     for got, s in zip(got_cases, (0, n_sys - 1)):
@@ -468,11 +487,11 @@ def test_eight_body_specialisation_matches_generic_kernel(E, monkeypatch):
     assert same.mean() > 0.5, same.mean()
 
 
-@pytest.mark.parametrize("name", ["c1_example", "c3_case7"])
+@pytest.mark.parametrize("name", ["c1_example", "c2_case3", "c3_case7", "c3_case7_evolving", "c5_circumbinary"])
 def test_small_system_specialisations_match_generic_kernel(E, monkeypatch, name):
-    """The compile-time 2- and 3-body builds (configs 1 and 3: host 0, democratic heliocentric, tides + flattening + Kidder1995,
-    fast arithmetic; 2 / 4 lanes per system) against the run-time-geometry build of the same step (PB200_FORCE_GENERIC=1) on
-    the same perturbed members: same arithmetic in the same order, 1e-13 relative after 300 steps."""
+    """The compile-time 2- and 3-body builds (configs 1, 2, 3, 3-evolving and 5: host 0, compile-time effect set; 2 / 4 lanes
+    per system) against the run-time-geometry build of the same step (PB200_FORCE_GENERIC=1) on the same perturbed members:
+    same arithmetic in the same order, 1e-13 relative after 300 steps."""
     from posidonius_b200.case import case_from_dict
     from posidonius_b200.perturb import make_ensemble_cases
     case, tables = case_from_dict(config_case(name))
@@ -607,7 +626,7 @@ def test_host_not_at_index_zero(E, fixture, order):
     assert o.initialize_physical_values() == 0
     assert o.iterate(10 ** 6) == 199
     want = o.case()
-    for arithmetic in (abi.ARITH_STRICT, abi.ARITH_FAST):
+    for arithmetic in (abi.ARITH_STRICT, abi.ARITH_FAST, abi.ARITH_HYBRID):
         with E.Ensemble(case, tables, n_systems=6, arithmetic=arithmetic) as ens:
             ens.initialize_physical_values()
             ens.iterate(10 ** 6)
