@@ -78,6 +78,7 @@ extern "C" {
 /* warning bits, OR-ed into pb200 "warnings" word (do not stop the system) */
 #define PB200_WARN_MIDPOINT_NOT_CONVERGED 1u /* whfast.rs:389-391 */
 #define PB200_WARN_TIMESTEP_GT_PERIOD 2u     /* whfast.rs:702-707 */
+#define PB200_WARN_HISTORY_DROPPED 4u        /* a historic snapshot found the device history buffer full (not a reference condition) */
 
 /* One body: the fields of `Particle` (src/particles/particle.rs:16-52) that the
  * hot path reads or carries between steps.  Per-effect scratch that the
@@ -224,6 +225,13 @@ void pb200_ensemble_destroy(pb200_ensemble_t* e);
  * members on the host with the same recipe (posidonius-b200 ensemble, posidonius_b200/perturb.py::splitmix_cases). */
 int pb200_ensemble_create_perturbed(const pb200_case_t* base, size_t n_systems, uint64_t seed, double amplitude,
                                     const pb200_table_t* tables, size_t n_tables, int device, pb200_ensemble_t** out);
+/* The same for one SHARD of that ensemble: members first_member .. first_member + n_systems - 1 of the global ensemble that
+ * pb200_ensemble_create_perturbed(seed) defines (one process per GPU, each building its contiguous range — the reference
+ * runs one Universe per process, src/main.rs:124-176). Member k's stream depends on (seed, k) only, so the union of the
+ * shards is the unsharded ensemble bit for bit. */
+int pb200_ensemble_create_perturbed_range(const pb200_case_t* base, uint64_t first_member, size_t n_systems, uint64_t seed,
+                                          double amplitude, const pb200_table_t* tables, size_t n_tables, int device,
+                                          pb200_ensemble_t** out);
 
 /* Integrator::get_n_particles / get_current_time / get_n_historic_snapshots (mod.rs:18-20). */
 int pb200_ensemble_n_particles(const pb200_ensemble_t* e);
@@ -265,6 +273,8 @@ int pb200_ensemble_synchronize(pb200_ensemble_t* e);
 int pb200_ensemble_last_step_ms(pb200_ensemble_t* e, float* ms);
 /* Kernel launches issued by this ensemble so far. */
 uint64_t pb200_ensemble_launch_count(const pb200_ensemble_t* e);
+/* Time slices of the last step launch (1 = every block of systems ran its steps in one piece). */
+unsigned pb200_ensemble_last_pieces(const pb200_ensemble_t* e);
 
 /* Per-system status (PB200_STATUS_*), warning bits and the iteration index of the event. */
 int pb200_ensemble_status(pb200_ensemble_t* e, int32_t* status, uint32_t* warnings,
@@ -299,6 +309,9 @@ int pb200_ensemble_get_case(pb200_ensemble_t* e, size_t s, pb200_case_t* out);
  * the last drain; `pb200_ensemble_history_drain` copies them system-major:
  * dst[((s * n_snapshots + k) * n_bodies + b) * 156 ...] and empties the buffer. */
 size_t pb200_ensemble_history_pending(pb200_ensemble_t* e);
+/* Snapshots per system that the device-side history buffer holds between drains: pb200_ensemble_step refuses a call that
+ * could overflow it, so callers bound their calls by (capacity - pending) snapshot periods. */
+size_t pb200_ensemble_history_capacity(const pb200_ensemble_t* e);
 int pb200_ensemble_history_drain(pb200_ensemble_t* e, void* dst, size_t dst_bytes);
 
 /* Diagnostics with the formulas of Universe::compute_total_energy /

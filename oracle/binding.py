@@ -42,6 +42,7 @@ def lib():
         L.pb200_oracle_history_drain.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.pb200_oracle_summary.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pb200_oracle_last_midpoint_iterations.argtypes = [C.c_void_p]
+        L.pb200_oracle_kepler_branches.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.pb200_oracle_additional_effects.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pb200_oracle_run_ensemble.argtypes = [C.POINTER(abi.Case), C.c_size_t, C.c_size_t, C.POINTER(abi.Table),
                                                 C.c_size_t, C.c_uint64, C.c_int, C.c_int, C.POINTER(abi.Case),
@@ -101,6 +102,12 @@ class OracleSystem:
 
     def last_midpoint_iterations(self):
         return lib().pb200_oracle_last_midpoint_iterations(self._h)
+
+    def kepler_branches(self):
+        """Calls of kepler_individual_step so far by branch: (newton_converged, quartic, bisection, hyperbolic)."""
+        out = (C.c_uint64 * 4)()
+        lib().pb200_oracle_kepler_branches(self._h, out)
+        return tuple(int(x) for x in out)
 
     def additional_effects(self):
         n = self._case.n_particles

@@ -70,6 +70,8 @@ size_t pb200_oracle_history_drain(void* h, void* dst, size_t cap) {
 }
 void pb200_oracle_summary(void* h, double* e, double* l) { ((Sys*)h)->summary(*e, *l); }
 int pb200_oracle_last_midpoint_iterations(void* h) { return ((Sys*)h)->last_midpoint_iterations; }
+// calls of kepler_individual_step by the branch they took: Newton converged, quartic solver, bisection fallback, hyperbolic
+void pb200_oracle_kepler_branches(void* h, uint64_t* out) { for (int k = 0; k < 4; k++) out[k] = ((Sys*)h)->kepler_branches[k]; }
 // The Universe::calculate_additional_effects evaluation alone (for unit parity of accelerations/torques):
 // out_acc / out_dldt: 3 * n doubles, body-major [b][c].
 void pb200_oracle_additional_effects(void* h, double* out_acc, double* out_dldt) {

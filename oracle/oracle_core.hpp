@@ -1465,6 +1465,9 @@ struct System {
     }
     // whfast.rs:676-833
     uint64_t kepler_stumpff_calls = 0;
+    // which branch of the solver each call took (test instrumentation): [0] Newton converged, [1] quartic solver entered,
+    // [2] bisection fallback entered, [3] hyperbolic orbit (beta <= 0)
+    uint64_t kepler_branches[4] = {0, 0, 0, 0};
     void kepler_individual_step(int i, R mass_g, double dt_) {
         R dt = dt_;
         V3<R> p1 = alt[i].pos, v1 = alt[i].vel;
@@ -1492,6 +1495,7 @@ struct System {
             x = 0.;
             x_per_period = NAN;
             xpp_nan = true;
+            kepler_branches[3]++;
         }
         int converged = 0;
         R old_x = x;
@@ -1500,6 +1504,7 @@ struct System {
         R ri = 1. / (r0 + e1);
         x = ri * (x * e1 - eta0 * gs[2] - zeta0 * gs[3] + dt);
         if (!xpp_nan && o_val(o_abs(x - old_x)) > o_val(0.01 * x_per_period)) {
+            kepler_branches[1]++;
             x = beta * dt / mass_g;
             R prev_x[WHFAST_NMAX_QUART + 1];
             for (int k = 0; k <= WHFAST_NMAX_QUART; k++) prev_x[k] = 0.;
@@ -1526,10 +1531,11 @@ struct System {
                 R e = eta0 * gs[1] + zeta0 * gs[2];
                 ri = 1. / (r0 + e);
                 x = ri * (x * e - eta0 * gs[2] - zeta0 * gs[3] + dt);
-                if (o_val(x) == o_val(old_x) || o_val(x) == o_val(old_x2)) { converged = 1; break; }
+                if (o_val(x) == o_val(old_x) || o_val(x) == o_val(old_x2)) { converged = 1; kepler_branches[0]++; break; }
             }
         }
         if (converged == 0) {
+            kepler_branches[2]++;
             R x_min, x_max;
             if (o_val(beta) > 0.) {
                 x_min = x_per_period * o_floor(dt * invperiod);

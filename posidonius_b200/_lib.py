@@ -26,6 +26,8 @@ _SIGNATURES = {
                                         C.c_int, C.POINTER(C.c_void_p)]),
     "pb200_ensemble_create_perturbed": (C.c_int, [C.POINTER(abi.Case), C.c_size_t, C.c_uint64, C.c_double, C.POINTER(abi.Table),
                                                   C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "pb200_ensemble_create_perturbed_range": (C.c_int, [C.POINTER(abi.Case), C.c_uint64, C.c_size_t, C.c_uint64, C.c_double,
+                                                        C.POINTER(abi.Table), C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "pb200_ensemble_destroy": (None, [C.c_void_p]),
     "pb200_ensemble_n_particles": (C.c_int, [C.c_void_p]),
     "pb200_ensemble_n_systems": (C.c_size_t, [C.c_void_p]),
@@ -37,6 +39,8 @@ _SIGNATURES = {
     "pb200_ensemble_synchronize": (C.c_int, [C.c_void_p]),
     "pb200_ensemble_last_step_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "pb200_ensemble_launch_count": (C.c_uint64, [C.c_void_p]),
+    "pb200_ensemble_last_pieces": (C.c_uint, [C.c_void_p]),
+    "pb200_ensemble_history_capacity": (C.c_size_t, [C.c_void_p]),
     "pb200_ensemble_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "pb200_ensemble_download": (C.c_int, [C.c_void_p, C.POINTER(abi.StateView)]),
     "pb200_ensemble_upload": (C.c_int, [C.c_void_p, C.POINTER(abi.StateView)]),

@@ -37,6 +37,7 @@ struct pb200_ensemble {
     // host mirror of the ensemble clock (exact snapshot counting without a device round trip); invalid after an upload of
     // current_time (uniform_clock = false: the device is asked instead)
     bool uniform_clock = true;
+    bool clock_dirty = false;     // current_time was uploaded: the mirror is re-read from the device before the next step
     double clock_t = 0., clock_last_hist = -1.;
     size_t hist_pending_host = 0;
     unsigned last_pieces = 1;     // time slices of the last step launch (diagnostics)
@@ -86,8 +87,9 @@ inline cudaError_t pb200_launch_sliced(pb200_ensemble* e, K kernel, size_t smem_
     return cudaGetLastError();
 }
 
-// One entry per translation unit of kernels_tu.cu. `arith` = PB200_ARITH_*; the generic entries dispatch on e->coord / e->gr.
-// A fixed-geometry entry returns cudaErrorInvalidDeviceFunction-free: the caller checks pb200_fixed_build_for() first.
+// One entry per translation unit of kernels_tu.cu. The run-time-geometry entries (one per arithmetic mode) dispatch on
+// e->coord / e->gr; the compile-time geometry entries dispatch on e->arithmetic (the caller, pb200_ensemble_step, checks
+// that the ensemble has the build's geometry and effect set).
 cudaError_t pb200_launch_generic_fast(pb200_ensemble* e, unsigned grid, unsigned long long n);
 cudaError_t pb200_launch_generic_strict(pb200_ensemble* e, unsigned grid, unsigned long long n);
 cudaError_t pb200_launch_generic_hybrid(pb200_ensemble* e, unsigned grid, unsigned long long n);

@@ -4,7 +4,7 @@
 //   start  <case.json> <recovery.bin> <history.bin> [-l|--limit seconds] [-s|--silent]
 //   resume <recovery.bin> <history.bin> [-l seconds] [-s] [--historic-snapshot-period days]
 //          [--recovery-snapshot-period days] [--time-limit days]
-//   ensemble <case.json> <out_dir> --systems N [--seed S] [--amplitude A] [--steps K] [--device D] [--strict]
+//   ensemble <case.json> <out_dir> --systems N [--seed S] [--amplitude A] [--steps K] [--device D] [--arithmetic hybrid|strict|fast]
 //
 // Same semantics as the reference: `start` refuses to overwrite existing outputs (main.rs:144-148); the history file is
 // truncated to what the recovery snapshot knows (output.rs:91-117); a recovery snapshot is written when iterate() asks
@@ -47,6 +47,7 @@ struct Args {
     std::vector<std::string> pos;
     double limit_s = 0., hist_period = -1., rec_period = -1., time_limit = -1., amplitude = 1e-3;
     bool silent = false, strict = false;
+    int arithmetic = -1;   // -1: the library default (hybrid)
     long long systems = 0, seed = 20261017, steps = -1;
     int device = 0;
 };
@@ -70,6 +71,11 @@ static Args parse(int argc, char** argv, int first) {
         else if (s == "--steps") a.steps = atoll(val(s.c_str()).c_str());
         else if (s == "--device") a.device = atoi(val(s.c_str()).c_str());
         else if (s == "--strict") a.strict = true;
+        else if (s == "--arithmetic") {
+            std::string v = val(s.c_str());
+            if (v == "fast") a.arithmetic = PB200_ARITH_FAST; else if (v == "strict") a.arithmetic = PB200_ARITH_STRICT;
+            else if (v == "hybrid") a.arithmetic = PB200_ARITH_HYBRID; else panic("--arithmetic takes fast, strict or hybrid");
+        }
         else if (!s.empty() && s[0] == '-') panic("unknown option " + s);
         else a.pos.push_back(s);
     }
@@ -114,6 +120,7 @@ static int run_single(const Args& a, bool resume) {
     pb200_ensemble_t* e = nullptr;
     check(pb200_ensemble_create(&c, 1, 1, pb200_table_store_tables(store), pb200_table_store_count(store), a.device, &e), "cannot create the GPU integrator");
     if (a.strict) check(pb200_ensemble_set_arithmetic(e, PB200_ARITH_STRICT), "strict arithmetic");
+    else if (a.arithmetic >= 0) check(pb200_ensemble_set_arithmetic(e, a.arithmetic), "arithmetic mode");
     if (c.current_time == 0.) check(pb200_ensemble_initialize_physical_values(e), "initialize_physical_values");
     // set_snapshot_periods / set_time_limit (whfast.rs:187-224)
     if (a.hist_period > 0. && a.hist_period != c.historic_snapshot_period) INFO("The historic snapshot period changed from %g to %g days", c.historic_snapshot_period, a.hist_period);
@@ -144,10 +151,15 @@ static int run_single(const Args& a, bool resume) {
     bool completed = false;
     pb200_case_t img;
     check(pb200_ensemble_get_case(e, 0, &img), "get_case");
+    // WHFast.last_recovery_snapshot_time lives on the host only (write_recovery_snapshot sets it, whfast.rs:307-308): the image
+    // that get_case returns carries the value of the loaded file, so it is tracked here and re-applied after every get_case
+    double last_recovery = img.last_recovery_snapshot_time;
+    const bool trace = getenv("PB200_CLI_TRACE") != nullptr;
+    const size_t capacity = pb200_ensemble_history_capacity(e);
     while (!completed) {
-        // never more than ~32 historic snapshots per launch (device history buffer), never past the next recovery trigger
+        // never more historic snapshots per launch than the device history buffer holds, never past the next recovery trigger
         double per = img.historic_snapshot_period / img.time_step;
-        uint64_t cap = (uint64_t)std::max(1.0, std::min(20000.0, 32.0 * per));
+        uint64_t cap = (uint64_t)std::max(1.0, std::min(20000.0, per >= 1. ? (double)(capacity - 1) * per : (double)capacity));
         bool trigger = false;
         uint64_t k = cap;
         if (!limited) k = steps_to_recovery_trigger(img, cap, trigger);
@@ -161,6 +173,7 @@ static int run_single(const Args& a, bool resume) {
         int32_t status = 0;
         check(pb200_ensemble_status(e, &status, nullptr, nullptr), "status");
         check(pb200_ensemble_get_case(e, 0, &img), "get_case");
+        img.last_recovery_snapshot_time = last_recovery;
         if (!a.silent) { printf("Year: %.0f (%.1e) | Time step: %.3f days                    \r", img.current_time / 365.25, img.current_time / 365.25, img.time_step); fflush(stdout); }
         if (status == PB200_STATUS_COMPLETED) { INFO("Simulation completed '%s'.", first.c_str()); completed = true; break; }
         if (status != PB200_STATUS_OK) { fflush(hf); printf("\n\n"); panic(failure_text(status)); }
@@ -172,7 +185,8 @@ static int run_single(const Args& a, bool resume) {
         if (write_recovery) {
             // Integrator::write_recovery_snapshot (whfast.rs:307-316)
             fflush(hf);
-            img.last_recovery_snapshot_time = img.current_time;
+            last_recovery = img.last_recovery_snapshot_time = img.current_time;
+            if (trace) { printf("[TRACE] recovery snapshot at t = %.17g (iteration %llu)\n", img.current_time, (unsigned long long)img.current_iteration); fflush(stdout); }
             check(pb200_case_save(recovery.c_str(), &img, pb200_table_store_tables(store), pb200_table_store_count(store)), "write_recovery_snapshot");
             if (limited) { WARN("Reached execution time limit before simulation completion"); break; }
         }
@@ -189,7 +203,7 @@ static int run_single(const Args& a, bool resume) {
 // ---- ensemble: N perturbed members of one case, built on the device from a deterministic SplitMix64
 // stream (pb200_ensemble_create_perturbed): no per-member images on the host
 static int run_ensemble(const Args& a) {
-    if (a.pos.size() < 2 || a.systems <= 0) panic("usage: posidonius-b200 ensemble <case.json> <out_dir> --systems N [--seed S] [--amplitude A] [--steps K] [--device D] [--strict]");
+    if (a.pos.size() < 2 || a.systems <= 0) panic("usage: posidonius-b200 ensemble <case.json> <out_dir> --systems N [--seed S] [--amplitude A] [--steps K] [--device D] [--arithmetic hybrid|strict|fast]");
     const std::string out_dir = a.pos[1];
     pb200_case_t base;
     pb200_table_store_t* store = nullptr;
@@ -200,6 +214,7 @@ static int run_ensemble(const Args& a) {
     check(pb200_ensemble_create_perturbed(&base, S, (uint64_t)a.seed, a.amplitude, pb200_table_store_tables(store), pb200_table_store_count(store), a.device, &e),
           "cannot create the ensemble");
     if (a.strict) check(pb200_ensemble_set_arithmetic(e, PB200_ARITH_STRICT), "strict arithmetic");
+    else if (a.arithmetic >= 0) check(pb200_ensemble_set_arithmetic(e, a.arithmetic), "arithmetic mode");
     if (base.current_time == 0.) check(pb200_ensemble_initialize_physical_values(e), "initialize_physical_values");
     const int n = base.n_particles;
     std::vector<double> e0(S), l0(S), e1(S), l1(S);
@@ -211,10 +226,11 @@ static int run_ensemble(const Args& a) {
     uint64_t done = 0, snapshots = 0;
     auto t0 = std::chrono::steady_clock::now();
     double kernel_ms = 0.;
+    const size_t capacity = pb200_ensemble_history_capacity(e);
     while (done < total) {
-        // stay inside the device history buffer: at most ~16 snapshot periods per call
+        // stay inside the device history buffer (drained after every call): k steps produce at most ceil(k / per) + 1 snapshots
         double per = base.historic_snapshot_period / base.time_step;
-        uint64_t k = std::min<uint64_t>(total - done, (uint64_t)std::max(1.0, std::min(16.0 * per, 100000.0)));
+        uint64_t k = std::min<uint64_t>(total - done, (uint64_t)std::max(1.0, std::min(per >= 1. ? (double)(capacity - 1) * per : (double)capacity, 100000.0)));
         check(pb200_ensemble_step(e, k), "step");
         float ms = 0.f;
         check(pb200_ensemble_last_step_ms(e, &ms), "timing");
@@ -274,7 +290,7 @@ int main(int argc, char** argv) {
     if (argc < 2) {
         fprintf(stderr, "%s\nusage: posidonius-b200 start <case.json> <recovery.bin> <history.bin> [-l seconds] [-s]\n"
                         "       posidonius-b200 resume <recovery.bin> <history.bin> [-l seconds] [-s] [--historic-snapshot-period d] [--recovery-snapshot-period d] [--time-limit d]\n"
-                        "       posidonius-b200 ensemble <case.json> <out_dir> --systems N [--seed S] [--amplitude A] [--steps K] [--device D] [--strict]\n",
+                        "       posidonius-b200 ensemble <case.json> <out_dir> --systems N [--seed S] [--amplitude A] [--steps K] [--device D] [--arithmetic hybrid|strict|fast]\n",
                 pb200_version());
         return 2;
     }

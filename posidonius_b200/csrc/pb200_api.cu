@@ -46,7 +46,7 @@ __device__ __forceinline__ void evolved_values(const KParams& P, int b, double t
     const DevTable& T = P.tables[ti];
     int i = table_upper(T.time, T.n_rows, t);
     if (T.interp_radius) R = table_interp(T.time, T.radius, T.n_rows, i, t);
-    if (T.interp_rg2) rg2 = table_interp(T.time, T.rg2, T.n_rows, i, t);
+    if ((P.evo_rg2 >> b) & 1u) rg2 = table_interp(T.time, T.rg2, T.n_rows, i, t);
 }
 
 __global__ void init_physical_kernel(const __grid_constant__ KParams P) {
@@ -173,12 +173,14 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long& s) 
     return z ^ (z >> 31);
 }
 struct PerturbBase { double hpos[PB200_MAX_PARTICLES][3], hvel[PB200_MAX_PARTICLES][3], mass[PB200_MAX_PARTICLES]; };
-__global__ void perturb_kernel(const __grid_constant__ KParams P, const __grid_constant__ PerturbBase B, unsigned long long seed, double amp) {
+__global__ void perturb_kernel(const __grid_constant__ KParams P, const __grid_constant__ PerturbBase B, unsigned long long seed, double amp,
+                               unsigned long long first_member) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t ns = (size_t)P.n_sys;
-    if (k == 0 || k >= ns) return;   // member 0 is the base case (already uploaded)
+    const unsigned long long member = first_member + (unsigned long long)k;   // index in the global ensemble
+    if (member == 0 || k >= ns) return;   // member 0 is the base case (already uploaded)
     const int n = P.n_bodies;
-    unsigned long long s = seed * 0x100000001b3ull + (unsigned long long)k;
+    unsigned long long s = seed * 0x100000001b3ull + member;
     sd hp[PB200_MAX_PARTICLES][3], hv[PB200_MAX_PARTICLES][3];
     for (int b = 0; b < n; b++) {
         for (int c = 0; c < 3; c++) { hp[b][c] = sd(B.hpos[b][c]); hv[b][c] = sd(B.hvel[b][c]); }
@@ -338,6 +340,16 @@ int pb200_case_validate(const pb200_case_t* c, const pb200_table_t* tables, size
             if (is_dynamical_tide_evolution(b) && !t.inverse_tidal_q_factor) return set_error(PB200_E_INVALID, "evolution table needs an inverse_tidal_q_factor column");
         }
     }
+    // particle ids index the flattened HashMap of pair-dependent dissipation factors: in range and distinct
+    {
+        bool seen[PB200_MAX_PARTICLES] = {false};
+        for (int i = 0; i < n; i++) {
+            const int id = c->bodies[i].id;
+            if (id < 0 || id >= PB200_MAX_PARTICLES) return set_error(PB200_E_INVALID, "particle id out of range [0, MAX_PARTICLES)");
+            if (seen[id]) return set_error(PB200_E_INVALID, "duplicate particle id");
+            seen[id] = true;
+        }
+    }
     // Q4: universe.rs:335-337 reads the host's stale heliocentric velocity; the kernel takes it as zero.
     const double* hv = c->bodies[h].heliocentric_velocity;
     if (hv[0] != 0. || hv[1] != 0. || hv[2] != 0.)
@@ -445,28 +457,31 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     CUDA_TRY_E(cudaEventCreate(&e->ev1));
     // evolution tables (replicated per GPU, read through the read-only path)
     for (int i = 0; i < PB200_MAX_PARTICLES; i++) P.tables[i] = DevTable{nullptr, nullptr, nullptr, 0, 0, 0, nullptr};
+    // Every column a table provides is uploaded, so that bodies of different EvolutionTypes may share one table; which
+    // columns a body interpolates is decided per body (evo_rg2 / dyn_evo masks; pb200_case_validate checked the columns).
+    P.evo_rg2 = 0;
     for (int i = 0; i < n; i++) {
         int ti = P.evo_table[i];
-        if (ti < 0 || P.tables[ti].time) continue;
-        const pb200_table_t& t = tables[ti];
+        if (ti < 0) continue;
         const pb200_body_t& b = c0.bodies[i];
-        double *dt_ = nullptr, *dr = nullptr, *dg = nullptr;
+        if (b.evolution_type == PB200_EVO_BARAFFE2015 || b.evolution_type == PB200_EVO_LECONTE2011 || b.evolution_type == PB200_EVO_LECONTECHABRIER2013)
+            P.evo_rg2 |= 1u << i;
+        if (P.tables[ti].time) continue;
+        const pb200_table_t& t = tables[ti];
+        double *dt_ = nullptr, *dr = nullptr, *dg = nullptr, *dq = nullptr;
         TRY(dev_alloc(e, &dt_, t.n_rows));
         TRY(dev_alloc(e, &dr, t.n_rows));
         CUDA_TRY_E(cudaMemcpy(dt_, t.time, t.n_rows * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_TRY_E(cudaMemcpy(dr, t.radius, t.n_rows * sizeof(double), cudaMemcpyHostToDevice));
-        int need_rg2 = b.evolution_type == PB200_EVO_BARAFFE2015 || b.evolution_type == PB200_EVO_LECONTE2011 ||
-                       b.evolution_type == PB200_EVO_LECONTECHABRIER2013;
-        if (need_rg2) {
+        if (t.radius_of_gyration_2) {
             TRY(dev_alloc(e, &dg, t.n_rows));
             CUDA_TRY_E(cudaMemcpy(dg, t.radius_of_gyration_2, t.n_rows * sizeof(double), cudaMemcpyHostToDevice));
         }
-        double* dq = nullptr;
-        if (is_dynamical_tide_evolution(b)) {
+        if (t.inverse_tidal_q_factor) {
             TRY(dev_alloc(e, &dq, t.n_rows));
             CUDA_TRY_E(cudaMemcpy(dq, t.inverse_tidal_q_factor, t.n_rows * sizeof(double), cudaMemcpyHostToDevice));
         }
-        P.tables[ti] = DevTable{dt_, dr, dg, (int)t.n_rows, 1, need_rg2, dq};
+        P.tables[ti] = DevTable{dt_, dr, dg, (int)t.n_rows, 1, 0, dq};
     }
     const size_t ns = n_systems, nb = (size_t)n;
     TRY(dev_alloc(e, &P.pos, 3 * nb * ns)); TRY(dev_alloc(e, &P.vel, 3 * nb * ns)); TRY(dev_alloc(e, &P.acc, 3 * nb * ns));
@@ -496,6 +511,7 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
         size_t slots = (256ull << 20) / per_slot;
         if (slots < 2) slots = 2;
         if (slots > 64) slots = 64;
+        if (const char* hs = getenv("PB200_HISTORY_SLOTS")) { int v = atoi(hs); if (v >= 2 && (size_t)v < slots) slots = (size_t)v; }   // tests: a small buffer
         P.hist_capacity = (int)slots;
         TRY(dev_alloc(e, &P.hist, (size_t)PB_HIST_FIELDS * nb * ns * slots));
     }
@@ -579,6 +595,11 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
 
 int pb200_ensemble_create_perturbed(const pb200_case_t* base, size_t n_systems, uint64_t seed, double amplitude,
                                     const pb200_table_t* tables, size_t n_tables, int device, pb200_ensemble_t** out) {
+    return pb200_ensemble_create_perturbed_range(base, 0, n_systems, seed, amplitude, tables, n_tables, device, out);
+}
+
+int pb200_ensemble_create_perturbed_range(const pb200_case_t* base, uint64_t first_member, size_t n_systems, uint64_t seed, double amplitude,
+                                          const pb200_table_t* tables, size_t n_tables, int device, pb200_ensemble_t** out) {
     if (!base || !out) return set_error(PB200_E_INVALID, "null argument");
     pb200_ensemble_t* e = nullptr;
     int rc = pb200_ensemble_create(base, 1, n_systems, tables, n_tables, device, &e);   // every member starts as the base case
@@ -589,7 +610,8 @@ int pb200_ensemble_create_perturbed(const pb200_case_t* base, size_t n_systems, 
         for (int c = 0; c < 3; c++) { B.hpos[b][c] = base->bodies[b].heliocentric_position[c]; B.hvel[b][c] = base->bodies[b].heliocentric_velocity[c]; }
         B.mass[b] = base->bodies[b].mass;
     }
-    perturb_kernel<<<(unsigned)((n_systems + 127) / 128), 128, 0, e->stream>>>(e->P, B, (unsigned long long)seed, amplitude);
+    perturb_kernel<<<(unsigned)((n_systems + 127) / 128), 128, 0, e->stream>>>(e->P, B, (unsigned long long)seed, amplitude,
+                                                                                 (unsigned long long)first_member);
     e->launches++;
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
@@ -634,6 +656,33 @@ int pb200_ensemble_initialize_physical_values(pb200_ensemble_t* e) {
     return PB200_OK;
 }
 
+// Re-reads the per-system clocks after an upload of current_time (pb200_ensemble_upload / run_host): the host mirror that
+// counts upcoming snapshots is valid only while every live system shares one clock.
+static int refresh_clock_mirror(pb200_ensemble* e) {
+    const size_t ns = e->n_sys;
+    std::vector<double> t(ns), lh(ns);
+    std::vector<int> hc(ns), st(ns);
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    CUDA_TRY(cudaMemcpy(t.data(), e->P.t, ns * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(lh.data(), e->P.last_hist, ns * sizeof(double), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(hc.data(), e->P.hist_count, ns * sizeof(int), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(st.data(), e->P.status, ns * sizeof(int), cudaMemcpyDeviceToHost));
+    bool uniform = true, have = false;
+    double t0 = 0., lh0 = -1.;
+    int pending = 0;
+    for (size_t s = 0; s < ns; s++) {
+        if (hc[s] > pending) pending = hc[s];
+        if (st[s] != PB200_STATUS_OK) continue;   // stopped systems take no further snapshots
+        if (!have) { t0 = t[s]; lh0 = lh[s]; have = true; }
+        else if (t[s] != t0 || lh[s] != lh0) uniform = false;
+    }
+    e->uniform_clock = uniform;
+    e->clock_t = t0; e->clock_last_hist = lh0;
+    e->hist_pending_host = (size_t)pending;
+    e->clock_dirty = false;
+    return PB200_OK;
+}
+
 int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
     if (!e) return set_error(PB200_E_INVALID, "null ensemble");
     if (n_steps == 0) return PB200_OK;
@@ -641,7 +690,12 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
     const size_t threads = e->n_sys * (size_t)e->P.W;
     const unsigned grid = (unsigned)((threads + PB_BLOCK - 1) / PB_BLOCK);
     // The history planes hold hist_capacity snapshots; refuse a call that could overflow them (the caller drains and
-    // steps in smaller calls). The count is exact when the ensemble shares one clock, else a device query.
+    // steps in smaller calls: pb200_ensemble_history_capacity). The count is exact when the ensemble shares one clock
+    // (host mirror, advanced with the kernel's own roundings), else a bound from a device query.
+    if (e->clock_dirty) {
+        int rc = refresh_clock_mirror(e);
+        if (rc != PB200_OK) return rc;
+    }
     {
         size_t upcoming;
         if (e->uniform_clock) {
@@ -655,18 +709,11 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
             }
             if (e->hist_pending_host + upcoming > (size_t)e->P.hist_capacity)
                 return set_error(PB200_E_INVALID, "history buffer would overflow: call pb200_ensemble_history_drain and step in smaller calls");
-            // advance the host mirror of the clock
-            t = e->clock_t; lh = e->clock_last_hist;
-            for (uint64_t k = 0; k < n_steps; k++) {
-                bool first = lh < 0.;
-                if (first || lh + e->P.hist_period <= t) { if (!first) lh += e->P.hist_period; else lh = 0.; }
-                t += e->P.dt;
-                if (t + e->P.dt > e->P.time_limit) break;
-            }
             e->clock_t = t; e->clock_last_hist = lh;
             e->hist_pending_host += upcoming;
         } else {
             upcoming = (size_t)std::floor((double)n_steps * e->P.dt / e->P.hist_period) + 2;
+            if (upcoming > n_steps) upcoming = (size_t)n_steps;
             if (pb200_ensemble_history_pending(e) + upcoming > (size_t)e->P.hist_capacity)
                 return set_error(PB200_E_INVALID, "history buffer would overflow: call pb200_ensemble_history_drain and step in smaller calls");
         }
@@ -715,6 +762,8 @@ int pb200_ensemble_last_step_ms(pb200_ensemble_t* e, float* ms) {
 }
 
 uint64_t pb200_ensemble_launch_count(const pb200_ensemble_t* e) { return e ? e->launches : 0; }
+unsigned pb200_ensemble_last_pieces(const pb200_ensemble_t* e) { return e ? e->last_pieces : 0; }
+size_t pb200_ensemble_history_capacity(const pb200_ensemble_t* e) { return e ? (size_t)e->P.hist_capacity : 0; }
 
 int pb200_ensemble_status(pb200_ensemble_t* e, int32_t* status, uint32_t* warnings, uint64_t* iteration_of_event) {
     if (!e) return set_error(PB200_E_INVALID, "null ensemble");
@@ -735,6 +784,7 @@ static int copy_state(pb200_ensemble* e, const pb200_state_view_t* v, bool to_ho
         {v->angular_momentum_errors, e->P.lerr, 3 * nb * ns}, {v->radius, e->P.radius, nb * ns},
         {v->radius_of_gyration_2, e->P.rg2, nb * ns}, {v->moment_of_inertia, e->P.moi, nb * ns}, {v->current_time, e->P.t, ns},
     };
+    if (!to_host && v->current_time) e->clock_dirty = true;
     for (const Item& it : items) {
         if (!it.host) continue;
         cudaError_t err = to_host ? cudaMemcpyAsync(it.host, it.dev, it.count * sizeof(double), cudaMemcpyDeviceToHost, e->stream)

@@ -63,8 +63,10 @@ struct DevTable {
     const double* rg2;
     int n_rows;
     int interp_radius;  // 1 unless NonEvolving
-    int interp_rg2;     // Baraffe2015 / Leconte2011 / LeconteChabrier2013
-    const double* qinv; // inverse tidal Q factor: BolmontMathis2016 / GalletBolmont2017 / LeconteChabrier2013(true), else null
+    int reserved;
+    const double* qinv; // inverse tidal Q factor column, null when the table has none
+    // (which columns a BODY interpolates depends on its own EvolutionType: KParams::evo_rg2 / dyn_evo bit masks; a table
+    // shared by bodies of different types carries every column it was given)
 };
 
 // Kernel parameters: everything uniform across the ensemble + SoA pointers.
@@ -78,6 +80,7 @@ struct KParams {
     uint32_t tides_orbiting, flat_orbiting, gr_orbiting, gr_enabled /* != Disabled */;
     int tides_host_central, flat_host_central;
     int evo_table[PB200_MAX_PARTICLES];  // -1 = NonEvolving
+    uint32_t evo_rg2;                    // bit b: body b's EvolutionType interpolates the radius of gyration (Baraffe2015 / Leconte2011 / LeconteChabrier2013)
     DevTable tables[PB200_MAX_PARTICLES];
     // dynamic state, [c][b][s]
     double *pos, *vel, *acc, *L, *spin, *verr, *lerr;

@@ -65,7 +65,7 @@ __device__ __forceinline__ bool evolve_lane(const KParams& P, const Roles& ro, c
     const double R = cold.get(K_R), rg2 = ldm(P.rg2 + idx);
     int i = table_upper(T.time, T.n_rows, t);
     double nr = T.interp_radius ? table_interp(T.time, T.radius, T.n_rows, i, t) : R;
-    double ng = T.interp_rg2 ? table_interp(T.time, T.rg2, T.n_rows, i, t) : rg2;
+    double ng = ((P.evo_rg2 >> b) & 1u) ? table_interp(T.time, T.rg2, T.n_rows, i, t) : rg2;
     if (nr != R || ng != rg2) {
         double I = (sd(cold.get(K_M)) * sd(ng) * (sd(nr) * sd(nr))).v;
         cold.set(K_R, nr); cold.set(K_I, I);
@@ -549,6 +549,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     if (!first) st.last_hist = __dadd_rn(st.last_hist, P.hist_period); else st.last_hist = 0.;
                     st.n_hist_new += 1;
                     if (st.hist_count < P.hist_capacity) st.hist_count += 1;
+                    else st.warnings |= PB200_WARN_HISTORY_DROPPED;   // cannot happen through pb200_ensemble_step's guard
                 }
             }
         }

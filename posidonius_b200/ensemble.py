@@ -58,14 +58,15 @@ class Ensemble:
             self.set_arithmetic(arithmetic)
 
     @classmethod
-    def perturbed(cls, base, tables, n_systems, seed, amplitude=1e-3, device=0, arithmetic=None):
-        """pb200_ensemble_create_perturbed: the synthetic ensemble of SURVEY §8d built on the device (member 0 = base,
-        member k = SplitMix64-perturbed copy); the host never holds per-member case images."""
+    def perturbed(cls, base, tables, n_systems, seed, amplitude=1e-3, device=0, arithmetic=None, first_member=0):
+        """pb200_ensemble_create_perturbed(_range): the synthetic ensemble of SURVEY §8d built on the device (member 0 = base,
+        member k = SplitMix64-perturbed copy); the host never holds per-member case images. first_member: this ensemble is
+        the shard [first_member, first_member + n_systems) of the global ensemble (one process per GPU)."""
         self = cls.__new__(cls)
         self._tables = tables
         self._h = C.c_void_p()
-        _check(lib().pb200_ensemble_create_perturbed(C.byref(base), n_systems, seed, amplitude, tables.as_ctypes(), len(tables),
-                                                     device, C.byref(self._h)))
+        _check(lib().pb200_ensemble_create_perturbed_range(C.byref(base), first_member, n_systems, seed, amplitude, tables.as_ctypes(),
+                                                           len(tables), device, C.byref(self._h)))
         self.n_systems = n_systems
         self.n_particles = lib().pb200_ensemble_n_particles(self._h)
         self.device = device
@@ -131,6 +132,12 @@ class Ensemble:
     def launch_count(self):
         return lib().pb200_ensemble_launch_count(self._h)
 
+    def last_pieces(self):
+        return lib().pb200_ensemble_last_pieces(self._h)
+
+    def history_capacity(self):
+        return lib().pb200_ensemble_history_capacity(self._h)
+
     def status(self):
         st = np.zeros(self.n_systems, dtype=np.int32)
         w = np.zeros(self.n_systems, dtype=np.uint32)
@@ -187,10 +194,15 @@ class Ensemble:
     def history_pending(self):
         return lib().pb200_ensemble_history_pending(self._h)
 
-    def history_drain(self):
-        """Returns a uint8 array [n_systems, n_snapshots, n_particles, 156] of reference-layout records."""
+    def history_drain(self, out=None):
+        """Returns a uint8 array [n_systems, n_snapshots, n_particles, 156] of reference-layout records.
+        out: a (pinned) uint8 buffer of at least that many bytes to reuse; the result is a view of it."""
         n_snap = self.history_pending()
-        buf = np.zeros((self.n_systems, n_snap, self.n_particles, abi.HISTORIC_RECORD_BYTES), dtype=np.uint8)
+        shape = (self.n_systems, n_snap, self.n_particles, abi.HISTORIC_RECORD_BYTES)
+        if out is None:
+            buf = np.zeros(shape, dtype=np.uint8)
+        else:
+            buf = out.reshape(-1)[:int(np.prod(shape))].reshape(shape)
         if n_snap:
             _check(lib().pb200_ensemble_history_drain(self._h, buf.ctypes.data_as(C.c_void_p), buf.nbytes))
         return buf

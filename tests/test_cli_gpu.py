@@ -17,8 +17,9 @@ HISTORY_DTYPE = np.dtype([("current_time", "<f8"), ("time_step", "<f8"), ("parti
     "radius_of_gyration_2", "love_number", "scaled_dissipation_factor", "lag_angle", "denergy_dt", "migration_timescale")])
 
 
-def run(*args, expect=0):
-    p = subprocess.run([CLI] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+def run(*args, expect=0, env=None):
+    p = subprocess.run([CLI] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
+                       env=dict(os.environ, **(env or {})))
     assert p.returncode == expect, p.stdout
     return p.stdout
 
@@ -88,6 +89,49 @@ def test_resume_continues_bit_for_bit(tmp_path):
         assert fa.bodies[i].inertial_position[:] == fb.bodies[i].inertial_position[:]
         assert fa.bodies[i].inertial_velocity[:] == fb.bodies[i].inertial_velocity[:]
         assert fa.bodies[i].angular_momentum[:] == fb.bodies[i].angular_momentum[:]
+
+
+def test_recovery_snapshots_are_written_once_per_recovery_period(tmp_path):
+    """main.rs:158-176 + whfast.rs:237-239, 303-308: a recovery snapshot after the very first step and then whenever
+    last_recovery_snapshot_time + period <= current_time at the start of a step — counted over four recovery periods."""
+    _, case_path = _case(tmp_path, "c2_case3", 64.0, 8.0, 16.0)
+    out = run("start", case_path, tmp_path / "rec.bin", tmp_path / "hist.bin", "--silent", env={"PB200_CLI_TRACE": "1"})
+    got = [float(line.split("t = ")[1].split()[0]) for line in out.splitlines() if line.startswith("[TRACE] recovery snapshot")]
+    # the reference's loop on the accumulated clock
+    t, dt, last_rec, last_hist, want = 0.0, 0.08, -1.0, -1.0, []
+    while True:
+        first = last_hist < 0.0
+        trigger = last_rec + 16.0 <= t
+        if first or last_hist + 8.0 <= t:
+            last_hist = 0.0 if first else last_hist + 8.0
+        t += dt
+        if t + dt > 64.0:
+            break
+        if first or trigger:
+            last_rec = t
+            want.append(t)
+    assert len(want) == 4 and got == want, (got, want)
+
+
+def test_ensemble_subcommand_stays_inside_a_small_history_buffer(tmp_path):
+    """More snapshot periods than history slots: the subcommand bounds its calls by pb200_ensemble_history_capacity."""
+    d = config_case("c2_case3")
+    d["historic_snapshot_period"] = 0.8   # every 10 steps
+    p = tmp_path / "case.json"
+    p.write_text(json.dumps(d))
+    out_dir = tmp_path / "ens"
+    out = run("ensemble", p, out_dir, "--systems", 512, "--steps", 200, "--silent", env={"PB200_HISTORY_SLOTS": "3"})
+    t, last_hist, n_snap = 0.0, -1.0, 0   # whfast.rs:237-253 on the accumulated clock
+    for _ in range(200):
+        first = last_hist < 0.0
+        if first or last_hist + 0.8 <= t:
+            n_snap += 1
+            last_hist = 0.0 if first else last_hist + 0.8
+        t += 0.08
+    assert n_snap > 3
+    assert "ensemble of 512 systems x 200 steps: 512 running" in out and "%d snapshot(s) per system" % n_snap in out
+    hist = np.fromfile(out_dir / "ensemble_history.bin", dtype=HISTORY_DTYPE)
+    assert len(hist) == 512 * 2 * n_snap
 
 
 def test_ensemble_subcommand(tmp_path):

@@ -537,6 +537,52 @@ def test_device_built_ensemble_equals_host_recipe(E):
                 assert np.allclose(hp, np.array(got.bodies[i].inertial_position[:]) - np.array(got.bodies[0].inertial_position[:]), rtol=0, atol=0)
 
 
+def test_sharded_device_built_ensemble_is_the_unsharded_one(E):
+    """pb200_ensemble_create_perturbed_range: the shards that the ranks of a multi-GPU run build (contiguous member ranges of
+    ONE global ensemble) are, put together, the unsharded ensemble bit for bit — before and after integrating."""
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.shard import shard_range
+    case, tables = case_from_dict(config_case("c4_trappist1"))
+    n_total = 1000
+    with E.Ensemble.perturbed(case, tables, n_total, 20261021, 1e-3) as whole:
+        whole.initialize_physical_values()
+        whole.iterate(150)
+        want = whole.download(("position", "velocity", "angular_momentum"))
+    for world in (3, 8):
+        for rank in range(world):
+            first, last = shard_range(n_total, rank, world)
+            with E.Ensemble.perturbed(case, tables, last - first, 20261021, 1e-3, first_member=first) as part:
+                part.initialize_physical_values()
+                part.iterate(150)
+                got = part.download(("position", "velocity", "angular_momentum"))
+            for k in want:
+                assert np.array_equal(got[k], want[k][..., first:last]), (world, rank, k)
+
+
+def test_history_counting_survives_an_upload_of_the_clock(E):
+    """pb200_ensemble_upload / run_host with current_time in the view rewinds the device clock: the host mirror that guards
+    the history buffer is re-read, so the snapshots of the re-run steps are neither dropped nor refused."""
+    from posidonius_b200.case import case_from_dict
+    d = config_case("c2_case3")
+    d["historic_snapshot_period"] = 0.8   # every ~10 steps
+    case, tables = case_from_dict(d)
+    with E.Ensemble(case, tables, n_systems=8) as ens:
+        ens.initialize_physical_values()
+        start = ens.download()
+        ens.iterate(100)
+        first = ens.history_drain()
+        buf = {k: v.copy() for k, v in start.items()}
+        ens.upload({"current_time": buf["current_time"]})   # clock back to t = 0; last_historic_snapshot_time stays
+        ens.iterate(100)
+        again = ens.history_drain()
+        st, w, _ = ens.status()
+        assert np.all(w == 0)
+        assert first.shape[1] >= 10 and again.shape[1] == 0   # nothing falls due until the clock passes the last snapshot again
+        ens.iterate(100)
+        more = ens.history_drain()
+        assert 0 < more.shape[1] <= first.shape[1]
+
+
 def test_mixed_fates_inside_one_ensemble(E):
     """Members that are destroyed, ejected or completed early share warps with members that keep running: every member's
     status, event iteration and state equals the oracle's for that member (no cross-talk, dead systems frozen)."""

@@ -99,3 +99,20 @@ def test_no_device_reports_error_not_fallback():
     case, tables = case_from_dict(config_case("c1_example"))
     with pytest.raises(EnsembleError):
         Ensemble(case, tables)
+
+
+def test_validate_rejects_out_of_range_and_duplicate_particle_ids():
+    """A malformed recovery image must not index the flattened pair-dependent-factor map out of bounds (pb200_ensemble_create)."""
+    from posidonius_b200.ensemble import validate_case
+    case, tables = case_from_dict(config_case("c4_trappist1"))
+    case.bodies[3].id = 10
+    with pytest.raises(InvalidCaseError):
+        validate_case(case, tables)
+    case.bodies[3].id = -1
+    with pytest.raises(InvalidCaseError):
+        validate_case(case, tables)
+    case.bodies[3].id = 2
+    with pytest.raises(InvalidCaseError):
+        validate_case(case, tables)
+    case.bodies[3].id = 3
+    validate_case(case, tables)
