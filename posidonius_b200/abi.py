@@ -32,7 +32,7 @@ EVOLUTION_TYPES_INV = {v: k for k, v in EVOLUTION_TYPES.items()}
 EVO_NONEVOLVING = 6
 
 STATUS_OK, STATUS_COMPLETED, STATUS_ROCHE_DESTROYED, STATUS_COLLISION, STATUS_EJECTED, STATUS_ZERO_INERTIA = range(6)
-WARN_MIDPOINT_NOT_CONVERGED, WARN_TIMESTEP_GT_PERIOD = 1, 2
+WARN_MIDPOINT_NOT_CONVERGED, WARN_TIMESTEP_GT_PERIOD, WARN_HISTORY_DROPPED = 1, 2, 4
 
 _d3 = C.c_double * 3
 

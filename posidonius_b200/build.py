@@ -27,6 +27,7 @@ UNITS = [
     ("k_generic_strict", "kernels_tu.cu", ["PB_TU_GENERIC=1"]),
     ("k_generic_hybrid", "kernels_tu.cu", ["PB_TU_GENERIC=2"]),
     ("k_n8", "kernels_tu.cu", ["PB_TU_FIXED=8"]),
+    ("k_n8w", "kernels_tu.cu", ["PB_TU_FIXED=8", "PB_TU_WIDE=1"]),
     ("k_n2", "kernels_tu.cu", ["PB_TU_FIXED=2"]),
     ("k_n3", "kernels_tu.cu", ["PB_TU_FIXED=3"]),
     ("k_n2t", "kernels_tu.cu", ["PB_TU_FIXED=20"]),

@@ -33,6 +33,7 @@ struct pb200_ensemble {
     int arithmetic = PB200_ARITH_HYBRID;
     int sm_count = 0;
     bool perturbed = false;       // built by pb200_ensemble_create_perturbed: heliocentric fields of the image are per member
+    bool narrow_blocks = false;   // PB200_NARROW_BLOCKS=1: never use the 384-thread build of the 8-body kernel (A/B tests)
     bool force_generic = false;   // PB200_FORCE_GENERIC=1 in the environment: bypass the compile-time geometry builds (A/B tests)
     // host mirror of the ensemble clock (exact snapshot counting without a device round trip); invalid after an upload of
     // current_time (uniform_clock = false: the device is asked instead)
@@ -62,9 +63,11 @@ inline unsigned pb200_plan_pieces(unsigned grid, unsigned slots, unsigned long l
     return 1;
 }
 
+// `threads` = systems x lanes per system; `block` = the CTA size the kernel was compiled for (PB_BLOCK of its translation unit).
 template <class K>
-inline cudaError_t pb200_launch_sliced(pb200_ensemble* e, K kernel, size_t smem_bytes, int& configured_device, int& blocks_per_sm,
-                                       unsigned grid, unsigned long long n) {
+inline cudaError_t pb200_launch_sliced(pb200_ensemble* e, K kernel, size_t smem_bytes, int block, int& configured_device, int& blocks_per_sm,
+                                       size_t threads, unsigned long long n) {
+    const unsigned grid = (unsigned)((threads + (size_t)block - 1) / (size_t)block);
     // PB200_SMEM_PAD_KB (experiments only): extra dynamic shared memory per CTA, to lower the residency of the same binary
     static const size_t pad = []() { const char* v = getenv("PB200_SMEM_PAD_KB"); return v ? (size_t)atoi(v) * 1024 : (size_t)0; }();
     const size_t smem = smem_bytes + pad;
@@ -72,7 +75,7 @@ inline cudaError_t pb200_launch_sliced(pb200_ensemble* e, K kernel, size_t smem_
         // the cold slots need more than the default 48 KB of dynamic shared memory
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, PB_BLOCK, smem);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, block, smem);
         if (err != cudaSuccess) return err;
         configured_device = e->device;
     }
@@ -83,18 +86,19 @@ inline cudaError_t pb200_launch_sliced(pb200_ensemble* e, K kernel, size_t smem_
         cudaError_t err = cudaMemsetAsync(e->P.sched, 0, (size_t)(grid + 1) * sizeof(unsigned int), e->stream);
         if (err != cudaSuccess) return err;
     }
-    kernel<<<grid * e->P.n_pieces, PB_BLOCK, smem, e->stream>>>(e->P, n);
+    kernel<<<grid * e->P.n_pieces, block, smem, e->stream>>>(e->P, n);
     return cudaGetLastError();
 }
 
 // One entry per translation unit of kernels_tu.cu. The run-time-geometry entries (one per arithmetic mode) dispatch on
 // e->coord / e->gr; the compile-time geometry entries dispatch on e->arithmetic (the caller, pb200_ensemble_step, checks
 // that the ensemble has the build's geometry and effect set).
-cudaError_t pb200_launch_generic_fast(pb200_ensemble* e, unsigned grid, unsigned long long n);
-cudaError_t pb200_launch_generic_strict(pb200_ensemble* e, unsigned grid, unsigned long long n);
-cudaError_t pb200_launch_generic_hybrid(pb200_ensemble* e, unsigned grid, unsigned long long n);
-cudaError_t pb200_launch_n8(pb200_ensemble* e, unsigned grid, unsigned long long n);        // 8 bodies, DH, tides + flattening + Kidder
-cudaError_t pb200_launch_n2(pb200_ensemble* e, unsigned grid, unsigned long long n);        // 2 bodies, DH, tides + flattening + Kidder
-cudaError_t pb200_launch_n3(pb200_ensemble* e, unsigned grid, unsigned long long n);        // 3 bodies, DH, tides + flattening + Kidder
-cudaError_t pb200_launch_n2t(pb200_ensemble* e, unsigned grid, unsigned long long n);       // 2 bodies, DH, tides only
-cudaError_t pb200_launch_n3e(pb200_ensemble* e, unsigned grid, unsigned long long n);       // 3 bodies, DH or Jacobi, all effects + evolution
+cudaError_t pb200_launch_generic_fast(pb200_ensemble* e, size_t threads, unsigned long long n);
+cudaError_t pb200_launch_generic_strict(pb200_ensemble* e, size_t threads, unsigned long long n);
+cudaError_t pb200_launch_generic_hybrid(pb200_ensemble* e, size_t threads, unsigned long long n);
+cudaError_t pb200_launch_n8(pb200_ensemble* e, size_t threads, unsigned long long n);        // 8 bodies, DH, tides + flattening + Kidder
+cudaError_t pb200_launch_n8w(pb200_ensemble* e, size_t threads, unsigned long long n);       // the same in 384-thread CTAs (one per SM)
+cudaError_t pb200_launch_n2(pb200_ensemble* e, size_t threads, unsigned long long n);        // 2 bodies, DH, tides + flattening + Kidder
+cudaError_t pb200_launch_n3(pb200_ensemble* e, size_t threads, unsigned long long n);        // 3 bodies, DH, tides + flattening + Kidder
+cudaError_t pb200_launch_n2t(pb200_ensemble* e, size_t threads, unsigned long long n);       // 2 bodies, DH, tides only
+cudaError_t pb200_launch_n3e(pb200_ensemble* e, size_t threads, unsigned long long n);       // 3 bodies, DH or Jacobi, all effects + evolution

@@ -415,6 +415,7 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     e->recovery_snapshot_period = c0.recovery_snapshot_period;
     e->clock_t = c0.current_time; e->clock_last_hist = c0.last_historic_snapshot_time;
     { const char* fg = getenv("PB200_FORCE_GENERIC"); e->force_generic = fg && fg[0] == '1'; }
+    { const char* nb = getenv("PB200_NARROW_BLOCKS"); e->narrow_blocks = nb && nb[0] == '1'; }
     if (cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) e->sm_count = 0;
     for (size_t s = 1; s < n_cases; s++)
         if (cases[s].current_time != c0.current_time || cases[s].last_historic_snapshot_time != c0.last_historic_snapshot_time) e->uniform_clock = false;
@@ -497,7 +498,7 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     TRY(dev_alloc(e, &P.hist_count, ns));
     TRY(dev_alloc(e, &P.tide_scratch, (size_t)PB_TIDE_SCRATCH * nb * ns));
     TRY(dev_alloc(e, &e->d_energy, ns)); TRY(dev_alloc(e, &e->d_angmom, ns));
-    TRY(dev_alloc(e, &P.sched, (ns * (size_t)P.W + PB_BLOCK - 1) / PB_BLOCK + 1));
+    TRY(dev_alloc(e, &P.sched, (ns * (size_t)P.W + 63) / 64 + 1));   // one flag per CTA of the smallest build (64 threads) + the ticket counter
     P.n_groups = 0; P.n_pieces = 1;
     if (P.flags & FLAG_WIND) { TRY(dev_alloc(e, &e->d_wind_k, nb * ns)); TRY(dev_alloc(e, &e->d_wind_sat, nb * ns)); }
     if (P.flags & FLAG_DYN) {
@@ -688,7 +689,6 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
     if (n_steps == 0) return PB200_OK;
     CUDA_TRY(cudaSetDevice(e->device));
     const size_t threads = e->n_sys * (size_t)e->P.W;
-    const unsigned grid = (unsigned)((threads + PB_BLOCK - 1) / PB_BLOCK);
     // The history planes hold hist_capacity snapshots; refuse a call that could overflow them (the caller drains and
     // steps in smaller calls: pb200_ensemble_history_capacity). The count is exact when the ensemble shares one clock
     // (host mirror, advanced with the kernel's own roundings), else a bound from a device query.
@@ -725,15 +725,17 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
         const bool fixed_ok = e->P.host == 0 && !e->force_generic;
         const bool dh = e->coord == PB200_COORD_DEMOCRATIC_HELIOCENTRIC, kidder = e->gr == PB200_GR_KIDDER1995;
         const int tfg = FLAG_TIDES | FLAG_FLAT | FLAG_GR;
-        if (fixed_ok && e->n_bodies == 8 && dh && kidder && e->P.flags == tfg) err = pb200_launch_n8(e, grid, n_steps);
-        else if (fixed_ok && e->n_bodies == 2 && dh && kidder && e->P.flags == tfg) err = pb200_launch_n2(e, grid, n_steps);
-        else if (fixed_ok && e->n_bodies == 3 && dh && kidder && e->P.flags == tfg) err = pb200_launch_n3(e, grid, n_steps);
-        else if (fixed_ok && e->n_bodies == 2 && dh && e->gr == PB200_GR_DISABLED && e->P.flags == FLAG_TIDES) err = pb200_launch_n2t(e, grid, n_steps);
+        // 8 bodies: 384-thread CTAs once there is at least one of them per SM (below that the 64-thread build spreads the work over more SMs)
+        if (fixed_ok && e->n_bodies == 8 && dh && kidder && e->P.flags == tfg)
+            err = (threads >= (size_t)384 * (size_t)e->sm_count && !e->narrow_blocks) ? pb200_launch_n8w(e, threads, n_steps) : pb200_launch_n8(e, threads, n_steps);
+        else if (fixed_ok && e->n_bodies == 2 && dh && kidder && e->P.flags == tfg) err = pb200_launch_n2(e, threads, n_steps);
+        else if (fixed_ok && e->n_bodies == 3 && dh && kidder && e->P.flags == tfg) err = pb200_launch_n3(e, threads, n_steps);
+        else if (fixed_ok && e->n_bodies == 2 && dh && e->gr == PB200_GR_DISABLED && e->P.flags == FLAG_TIDES) err = pb200_launch_n2t(e, threads, n_steps);
         else if (fixed_ok && e->n_bodies == 3 && (dh || e->coord == PB200_COORD_JACOBI) && kidder && e->P.flags == (tfg | FLAG_EVO))
-            err = pb200_launch_n3e(e, grid, n_steps);
-        else if (e->arithmetic == PB200_ARITH_FAST) err = pb200_launch_generic_fast(e, grid, n_steps);
-        else if (e->arithmetic == PB200_ARITH_STRICT) err = pb200_launch_generic_strict(e, grid, n_steps);
-        else err = pb200_launch_generic_hybrid(e, grid, n_steps);
+            err = pb200_launch_n3e(e, threads, n_steps);
+        else if (e->arithmetic == PB200_ARITH_FAST) err = pb200_launch_generic_fast(e, threads, n_steps);
+        else if (e->arithmetic == PB200_ARITH_STRICT) err = pb200_launch_generic_strict(e, threads, n_steps);
+        else err = pb200_launch_generic_hybrid(e, threads, n_steps);
         e->launches++;
         if (err != cudaSuccess) return set_error(PB200_E_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(err));
     }

@@ -155,7 +155,9 @@ static __constant__ double kInvFactorial[12] = {1. / 6227020800., 1. / 479001600
                                          1. / 5040., 1. / 720., 1. / 120., 1. / 24., 1. / 6., 1. / 2.};
 __device__ __forceinline__ void stumpff_cs3(sd z, sd& c0, sd& c1, sd& c2, sd& c3) {
     int n = 0;
-    while (fabs(z.v) > 0.1) { z = z * sd(0.25); n++; }   // z / 4 (exact scaling, same value)
+    // z / 4 (exact scaling, same value). Bounded (deviation D3): the reference's loop never ends for an infinite z
+    // (a blown-up state) and a kernel must not hang; finite doubles need at most 515 trips.
+    while (fabs(z.v) > 0.1 && n < 600) { z = z * sd(0.25); n++; }
     const double* F = kInvFactorial;
     sd c_odd = sd(F[0]);    // 1/13!
     sd c_even = sd(F[1]);   // 1/12!

@@ -134,7 +134,12 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
     bool converged = false;
 #pragma unroll 1
     for (int it = 0; it < 10; it++) {
+#if PB_PHASE_BARRIER
+        // block-uniform exit: the barrier keeps the warps of the CTA inside the same stretch of code (instruction cache)
+        if (!__syncthreads_or(!done)) break;
+#else
         if (!__any_sync(FULL, !done)) break;
+#endif
         if (evolution && it == 0 && (PB_FLAGS(P) & FLAG_EVO)) {
             // once per step in evolving configurations: re-derive the constants unconditionally (warp-uniform control flow
             // around the shuffles inside make_consts)
@@ -349,6 +354,9 @@ __device__ __forceinline__ S3 gravity_n8_dh(const KParams& P, const Roles& ro, c
 #ifndef PB_STEP_BARRIER
 #define PB_STEP_BARRIER 0   // a block-wide barrier per step paid +2 % at 3 250 FP64 instructions per warp-step, costs 3 % at 2 700 (profiles/r1_variants.md)
 #endif
+#ifndef PB_PHASE_BARRIER
+#define PB_PHASE_BARRIER 0   // block-wide barriers before every force evaluation, Kepler drift and gravity evaluation (instruction cache)
+#endif
 #ifndef PB_MIN_BLOCKS
 #define PB_MIN_BLOCKS 5   // code-generation hint only: <= 168 registers/thread, no spills; six CTAs (12 warps) are resident (profiles/r1_variants.md)
 #endif
@@ -493,7 +501,7 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
 
 #pragma unroll 1
     for (unsigned long long step = step_begin; step < step_end; step++) {
-#if PB_STEP_BARRIER
+#if PB_STEP_BARRIER || PB_PHASE_BARRIER
         // one block-wide barrier per step keeps the warps of a block in the same region of the (large) loop body, so that
         // they share instruction-cache lines; it also makes the loop exit block-uniform
         if (!__syncthreads_or(alive)) break;
@@ -660,7 +668,17 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                     // ---- jump (whfast.rs:495-556): before the Kepler drift in the second half, after it in the first
                     for (int jump_slot = 0; jump_slot < 2; jump_slot++) {
                         if (jump_slot == 1) {
+#if PB_PHASE_BARRIER
+                            __syncthreads();
+#endif
                             kepler_step(kwork, apos, avel, sd(cold.get(K_KMU)), hdt_s, st.tswarn, st.warnings);
+                            {
+                                // WHFast.timestep_warning and the warning itself belong to the system, not to the planet whose
+                                // drift raised it (whfast.rs:702-707): share them in the group (the host lane stores them)
+                                unsigned int wv = st.warnings | (st.tswarn ? 0x80000000u : 0u);
+                                for (int off = W >> 1; off > 0; off >>= 1) wv |= __shfl_xor_sync(FULL, wv, off);
+                                st.warnings = wv & 0x7fffffffu; st.tswarn = (wv >> 31) != 0u;
+                            }
                             if (DIST) { if (b < 3) my_com = my_com + hdt_s * my_sv; }
                             else spos = spos + hdt_s * svel;
                         }
@@ -746,7 +764,11 @@ __global__ void PB_KERNEL_ATTR whfast_steps_kernel(const __grid_constant__ KPara
                         // ---- gravity (whfast.rs:281)
                         int fail;
                         cold.set3(E_R, plain(q.r));
+#if PB_PHASE_BARRIER
+                        __syncthreads();
+#else
                         __syncwarp();
+#endif
                         int code;
 #if PB_FIXED_N == 8
                         if (COORD == PB200_COORD_DEMOCRATIC_HELIOCENTRIC) {
