@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v",
 ]
 # (object name, source, extra defines)
-UNITS = [
+UNITS = [  # "k_s*": the lane = planet kernel of the 2- and 3-body configurations (kernels_small_tu.cu)
     ("api", "pb200_api.cu", []),
     ("case_io", "host/case_io.cpp", []),
     ("k_generic_fast", "kernels_tu.cu", ["PB_TU_GENERIC=0"]),
@@ -28,10 +28,11 @@ UNITS = [
     ("k_generic_hybrid", "kernels_tu.cu", ["PB_TU_GENERIC=2"]),
     ("k_n8", "kernels_tu.cu", ["PB_TU_FIXED=8"]),
     ("k_n8w", "kernels_tu.cu", ["PB_TU_FIXED=8", "PB_TU_WIDE=1"]),
-    ("k_n2", "kernels_tu.cu", ["PB_TU_FIXED=2"]),
-    ("k_n3", "kernels_tu.cu", ["PB_TU_FIXED=3"]),
-    ("k_n2t", "kernels_tu.cu", ["PB_TU_FIXED=20"]),
-    ("k_n3e", "kernels_tu.cu", ["PB_TU_FIXED=30"]),
+    ("k_s2", "kernels_small_tu.cu", ["PB_TU_SMALL=2"]),
+    ("k_s2t", "kernels_small_tu.cu", ["PB_TU_SMALL=20"]),
+    ("k_s3", "kernels_small_tu.cu", ["PB_TU_SMALL=3"]),
+    ("k_s3e", "kernels_small_tu.cu", ["PB_TU_SMALL=30"]),
+    ("k_s3j", "kernels_small_tu.cu", ["PB_TU_SMALL=31"]),
 ]
 
 

@@ -98,7 +98,9 @@ cudaError_t pb200_launch_generic_strict(pb200_ensemble* e, size_t threads, unsig
 cudaError_t pb200_launch_generic_hybrid(pb200_ensemble* e, size_t threads, unsigned long long n);
 cudaError_t pb200_launch_n8(pb200_ensemble* e, size_t threads, unsigned long long n);        // 8 bodies, DH, tides + flattening + Kidder
 cudaError_t pb200_launch_n8w(pb200_ensemble* e, size_t threads, unsigned long long n);       // the same in 384-thread CTAs (one per SM)
-cudaError_t pb200_launch_n2(pb200_ensemble* e, size_t threads, unsigned long long n);        // 2 bodies, DH, tides + flattening + Kidder
-cudaError_t pb200_launch_n3(pb200_ensemble* e, size_t threads, unsigned long long n);        // 3 bodies, DH, tides + flattening + Kidder
-cudaError_t pb200_launch_n2t(pb200_ensemble* e, size_t threads, unsigned long long n);       // 2 bodies, DH, tides only
-cudaError_t pb200_launch_n3e(pb200_ensemble* e, size_t threads, unsigned long long n);       // 3 bodies, DH or Jacobi, all effects + evolution
+// lane = planet builds (small_step.cuh, kernels_small_tu.cu): N - 1 lanes per system, the host body replicated in every lane
+cudaError_t pb200_launch_s2(pb200_ensemble* e, unsigned long long n);    // 2 bodies, DH, tides + flattening + Kidder          (config 1)
+cudaError_t pb200_launch_s2t(pb200_ensemble* e, unsigned long long n);   // 2 bodies, DH, tides only                            (config 2)
+cudaError_t pb200_launch_s3(pb200_ensemble* e, unsigned long long n);    // 3 bodies, DH, tides + flattening + Kidder          (config 3)
+cudaError_t pb200_launch_s3e(pb200_ensemble* e, unsigned long long n);   // 3 bodies, DH, the same + evolution                 (config 3 evolving)
+cudaError_t pb200_launch_s3j(pb200_ensemble* e, unsigned long long n);   // 3 bodies, Jacobi, the same + evolution             (config 5)

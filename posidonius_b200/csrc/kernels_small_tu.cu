@@ -1,0 +1,63 @@
+// kernels_small_tu.cu — one translation unit per build of the lane = planet step kernel (small_step.cuh) for the 2- and
+// 3-body BASELINE configurations. build.py compiles this file once per -DPB_TU_SMALL=<id>, all three arithmetic modes each:
+//   2   2 bodies, democratic heliocentric, tides + flattening + GR Kidder1995              (config 1)
+//   20  2 bodies, democratic heliocentric, tides only                                      (config 2)
+//   3   3 bodies, democratic heliocentric, tides + flattening + GR Kidder1995              (config 3)
+//   30  3 bodies, democratic heliocentric, the same + evolution tables                     (config 3 evolving)
+//   31  3 bodies, Jacobi, the same + evolution tables                                      (config 5)
+#if PB_TU_SMALL == 2
+#define PB_NS pbs2
+#define PB_S_N 2
+#define PB_S_COORD PB200_COORD_DEMOCRATIC_HELIOCENTRIC
+#define PB_S_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
+#define PB_S_ENTRY pb200_launch_s2
+#elif PB_TU_SMALL == 20
+#define PB_NS pbs2t
+#define PB_S_N 2
+#define PB_S_COORD PB200_COORD_DEMOCRATIC_HELIOCENTRIC
+#define PB_S_FLAGS (pb200::FLAG_TIDES)
+#define PB_S_ENTRY pb200_launch_s2t
+#elif PB_TU_SMALL == 3
+#define PB_NS pbs3
+#define PB_S_N 3
+#define PB_S_COORD PB200_COORD_DEMOCRATIC_HELIOCENTRIC
+#define PB_S_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
+#define PB_S_ENTRY pb200_launch_s3
+#elif PB_TU_SMALL == 30
+#define PB_NS pbs3e
+#define PB_S_N 3
+#define PB_S_COORD PB200_COORD_DEMOCRATIC_HELIOCENTRIC
+#define PB_S_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR | pb200::FLAG_EVO)
+#define PB_S_ENTRY pb200_launch_s3e
+#elif PB_TU_SMALL == 31
+#define PB_NS pbs3j
+#define PB_S_N 3
+#define PB_S_COORD PB200_COORD_JACOBI
+#define PB_S_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR | pb200::FLAG_EVO)
+#define PB_S_ENTRY pb200_launch_s3j
+#else
+#error "kernels_small_tu.cu: define PB_TU_SMALL=<2|20|3|30|31>"
+#endif
+#include "ensemble_host.hpp"
+#include "small_step.cuh"
+
+namespace {
+
+template <int ARITH>
+cudaError_t launch_one(pb200_ensemble* e, unsigned long long n) {
+    static thread_local int configured_device = -1, blocks_per_sm = 0;
+    // lane = planet: N - 1 lanes per system
+    const size_t threads = e->n_sys * (size_t)(PB_S_N - 1);
+    return pb200_launch_sliced(e, PB_NS::small_steps_kernel<PB_S_N, PB_S_COORD, PB_S_FLAGS, ARITH>, PB_NS::small_smem_bytes<PB_S_COORD>(), PB_SBLOCK,
+                               configured_device, blocks_per_sm, threads, n);
+}
+
+}  // namespace
+
+cudaError_t PB_S_ENTRY(pb200_ensemble* e, unsigned long long n) {
+    switch (e->arithmetic) {
+        case PB200_ARITH_FAST: return launch_one<PB200_ARITH_FAST>(e, n);
+        case PB200_ARITH_STRICT: return launch_one<PB200_ARITH_STRICT>(e, n);
+        default: return launch_one<PB200_ARITH_HYBRID>(e, n);
+    }
+}

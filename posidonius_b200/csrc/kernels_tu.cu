@@ -1,11 +1,9 @@
 // kernels_tu.cu — one translation unit per build of the step kernel. build.py compiles this file several times in parallel:
 //   -DPB_TU_GENERIC=<arith>            run-time geometry (any bodies / host / coordinates / GR variant), one arithmetic mode
-//   -DPB_TU_FIXED=<8|2|3|20|30>        compile-time geometry builds, all three arithmetic modes each:
-//        8  8 bodies, host 0, tides + flattening + GR Kidder1995, democratic heliocentric   (config 4, TRAPPIST-1)
-//        2  2 bodies, the same effect set                                                    (config 1)
-//        3  3 bodies, the same effect set                                                    (config 3 as shipped)
-//       20  2 bodies, tides only                                                             (config 2)
-//       30  3 bodies, all effects + evolution tables, democratic heliocentric and Jacobi     (configs 3-evolving and 5)
+//   -DPB_TU_FIXED=8 [-DPB_TU_WIDE=1]    compile-time geometry build, all three arithmetic modes: 8 bodies, host 0, tides +
+//                                       flattening + GR Kidder1995, democratic heliocentric (config 4, TRAPPIST-1), in 64- or
+//                                       384-thread CTAs
+// (the 2- and 3-body configurations have their own lane = planet kernel: kernels_small_tu.cu)
 #if defined(PB_TU_GENERIC)
 #define PB_NS pbgen
 #define PB_FIXED_N 0
@@ -26,32 +24,8 @@
 #define PB_FIXED_W 8
 #define PB_FIXED_SHIFT 3
 #define PB_FIXED_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
-#elif PB_TU_FIXED == 2
-#define PB_NS pbn2
-#define PB_FIXED_N 2
-#define PB_FIXED_W 2
-#define PB_FIXED_SHIFT 1
-#define PB_FIXED_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
-#elif PB_TU_FIXED == 3
-#define PB_NS pbn3
-#define PB_FIXED_N 3
-#define PB_FIXED_W 4
-#define PB_FIXED_SHIFT 2
-#define PB_FIXED_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR)
-#elif PB_TU_FIXED == 20
-#define PB_NS pbn2t
-#define PB_FIXED_N 2
-#define PB_FIXED_W 2
-#define PB_FIXED_SHIFT 1
-#define PB_FIXED_FLAGS (pb200::FLAG_TIDES)
-#elif PB_TU_FIXED == 30
-#define PB_NS pbn3e
-#define PB_FIXED_N 3
-#define PB_FIXED_W 4
-#define PB_FIXED_SHIFT 2
-#define PB_FIXED_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR | pb200::FLAG_EVO)
 #else
-#error "kernels_tu.cu: define PB_TU_GENERIC=<arith> or PB_TU_FIXED=<build>"
+#error "kernels_tu.cu: define PB_TU_GENERIC=<arith> or PB_TU_FIXED=8"
 #endif
 #include "ensemble_host.hpp"
 #include "whfast_step.cuh"
@@ -108,23 +82,6 @@ cudaError_t pb200_launch_n8w(pb200_ensemble* e, size_t threads, unsigned long lo
 #else
 cudaError_t pb200_launch_n8(pb200_ensemble* e, size_t threads, unsigned long long n) {
 #endif
-    return launch_arith<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995>(e, threads, n);
-}
-#elif PB_TU_FIXED == 2
-cudaError_t pb200_launch_n2(pb200_ensemble* e, size_t threads, unsigned long long n) {
-    return launch_arith<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995>(e, threads, n);
-}
-#elif PB_TU_FIXED == 3
-cudaError_t pb200_launch_n3(pb200_ensemble* e, size_t threads, unsigned long long n) {
-    return launch_arith<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995>(e, threads, n);
-}
-#elif PB_TU_FIXED == 20
-cudaError_t pb200_launch_n2t(pb200_ensemble* e, size_t threads, unsigned long long n) {
-    return launch_arith<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_DISABLED>(e, threads, n);
-}
-#elif PB_TU_FIXED == 30
-cudaError_t pb200_launch_n3e(pb200_ensemble* e, size_t threads, unsigned long long n) {
-    if (e->coord == PB200_COORD_JACOBI) return launch_arith<PB200_COORD_JACOBI, PB200_GR_KIDDER1995>(e, threads, n);
     return launch_arith<PB200_COORD_DEMOCRATIC_HELIOCENTRIC, PB200_GR_KIDDER1995>(e, threads, n);
 }
 #endif

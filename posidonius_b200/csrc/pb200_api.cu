@@ -498,7 +498,7 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     TRY(dev_alloc(e, &P.hist_count, ns));
     TRY(dev_alloc(e, &P.tide_scratch, (size_t)PB_TIDE_SCRATCH * nb * ns));
     TRY(dev_alloc(e, &e->d_energy, ns)); TRY(dev_alloc(e, &e->d_angmom, ns));
-    TRY(dev_alloc(e, &P.sched, (ns * (size_t)P.W + 63) / 64 + 1));   // one flag per CTA of the smallest build (64 threads) + the ticket counter
+    TRY(dev_alloc(e, &P.sched, (ns * (size_t)P.W + 31) / 32 + 2));   // one flag per CTA of the smallest build (32 threads) + the ticket counter
     P.n_groups = 0; P.n_pieces = 1;
     if (P.flags & FLAG_WIND) { TRY(dev_alloc(e, &e->d_wind_k, nb * ns)); TRY(dev_alloc(e, &e->d_wind_sat, nb * ns)); }
     if (P.flags & FLAG_DYN) {
@@ -730,11 +730,13 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
             // (the all-exact arithmetic gains nothing from them: 2.36e8 against 2.49e8 system-steps/s)
             err = (threads >= (size_t)384 * (size_t)e->sm_count && !e->narrow_blocks && e->arithmetic != PB200_ARITH_STRICT)
                       ? pb200_launch_n8w(e, threads, n_steps) : pb200_launch_n8(e, threads, n_steps);
-        else if (fixed_ok && e->n_bodies == 2 && dh && kidder && e->P.flags == tfg) err = pb200_launch_n2(e, threads, n_steps);
-        else if (fixed_ok && e->n_bodies == 3 && dh && kidder && e->P.flags == tfg) err = pb200_launch_n3(e, threads, n_steps);
-        else if (fixed_ok && e->n_bodies == 2 && dh && e->gr == PB200_GR_DISABLED && e->P.flags == FLAG_TIDES) err = pb200_launch_n2t(e, threads, n_steps);
-        else if (fixed_ok && e->n_bodies == 3 && (dh || e->coord == PB200_COORD_JACOBI) && kidder && e->P.flags == (tfg | FLAG_EVO))
-            err = pb200_launch_n3e(e, threads, n_steps);
+        // 2 and 3 bodies (BASELINE configs 1, 2, 3, 3-evolving, 5): lane = planet (small_step.cuh); PB200_FORCE_GENERIC=1 gives the lane = body kernel
+        else if (fixed_ok && e->P.spin_on && e->n_bodies == 2 && dh && kidder && e->P.flags == tfg) err = pb200_launch_s2(e, n_steps);
+        else if (fixed_ok && e->P.spin_on && e->n_bodies == 2 && dh && e->gr == PB200_GR_DISABLED && e->P.flags == FLAG_TIDES) err = pb200_launch_s2t(e, n_steps);
+        else if (fixed_ok && e->P.spin_on && e->n_bodies == 3 && dh && kidder && e->P.flags == tfg) err = pb200_launch_s3(e, n_steps);
+        else if (fixed_ok && e->P.spin_on && e->n_bodies == 3 && dh && kidder && e->P.flags == (tfg | FLAG_EVO)) err = pb200_launch_s3e(e, n_steps);
+        else if (fixed_ok && e->P.spin_on && e->n_bodies == 3 && e->coord == PB200_COORD_JACOBI && kidder && e->P.flags == (tfg | FLAG_EVO))
+            err = pb200_launch_s3j(e, n_steps);
         else if (e->arithmetic == PB200_ARITH_FAST) err = pb200_launch_generic_fast(e, threads, n_steps);
         else if (e->arithmetic == PB200_ARITH_STRICT) err = pb200_launch_generic_strict(e, threads, n_steps);
         else err = pb200_launch_generic_hybrid(e, threads, n_steps);

@@ -14,8 +14,10 @@ from posidonius_b200.case import case_from_dict  # noqa: E402
 from posidonius_b200.ensemble import Ensemble, measure_fp64_peak  # noqa: E402
 from posidonius_b200.perturb import make_ensemble_cases  # noqa: E402
 
-CONFIGS = [("c1_example", 65536), ("c2_case3", 4096), ("c2_case3", 65536), ("c3_case7", 16384), ("c3_case7_evolving", 16384),
+CONFIGS = [("c1_example", 65536), ("c2_case3", 4096), ("c2_case3", 65536), ("c3_case7", 16384), ("c3_case7", 65536), ("c3_case7_evolving", 16384),
            ("c3_case7_evolving", 65536), ("c4_trappist1", 65536), ("c5_circumbinary", 65536)]
+if os.environ.get("PB200_CONFIGS"):   # e.g. PB200_CONFIGS=c1_example:65536,c2_case3:4096
+    CONFIGS = [(c.split(":")[0], int(c.split(":")[1])) for c in os.environ["PB200_CONFIGS"].split(",")]
 
 
 def main():
