@@ -70,7 +70,9 @@ def build(force=False, verbose=False, out=None, defines=(), only=None):
     objdir = OBJ if out is None else OBJ + "_" + os.path.basename(out)
     os.makedirs(objdir, exist_ok=True)
     log_lines = []
-    units = [u for u in UNITS if only is None or u[0] in only or not os.path.exists(os.path.join(objdir, u[0] + ".o"))]
+    # a variant build (out != None) with `only`: the other units are the product objects
+    reuse = out is not None and only is not None
+    units = [u for u in UNITS if only is None or u[0] in only or (not reuse and not os.path.exists(os.path.join(objdir, u[0] + ".o")))]
     workers = int(os.environ.get("PB200_BUILD_JOBS", str(os.cpu_count() or 4)))
     with ThreadPoolExecutor(max_workers=workers) as pool:
         futures = [pool.submit(_compile, nvcc, name, src, list(defs) + list(defines), objdir, log_lines) for name, src, defs in units]
@@ -81,7 +83,7 @@ def build(force=False, verbose=False, out=None, defines=(), only=None):
             except Exception as exc:  # collect every failing unit before raising
                 errors.append(str(exc))
     log = os.path.join(HERE, "build.log" if out is None else os.path.basename(out) + ".log")
-    objs = [os.path.join(objdir, name + ".o") for name, _, _ in UNITS]
+    objs = [os.path.join(OBJ if reuse and name not in only else objdir, name + ".o") for name, _, _ in UNITS]
     if not errors:
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target] + objs
         proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

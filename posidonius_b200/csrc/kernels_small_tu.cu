@@ -43,13 +43,25 @@
 
 namespace {
 
+// CTA size: one CTA of 8 warps (3 bodies) or two of 4 warps (2 bodies) per SM once the ensemble fills three quarters of the
+// GPU that way (warps that start together share instruction-cache lines), else single-warp CTAs that spread over every SM.
+// PB200_SMALL_BLOCK=32 in the environment forces the small CTAs (A/B runs).
+constexpr int kBigBlock = PB_S_N == 3 ? 256 : 128;
+
+template <int ARITH, int BLK>
+cudaError_t launch_blk(pb200_ensemble* e, size_t threads, unsigned long long n) {
+    static thread_local int configured_device = -1, blocks_per_sm = 0;
+    return pb200_launch_sliced(e, PB_NS::small_steps_kernel<PB_S_N, PB_S_COORD, PB_S_FLAGS, ARITH, BLK>, PB_NS::small_smem_bytes<PB_S_COORD, BLK>(), BLK,
+                               configured_device, blocks_per_sm, threads, n);
+}
+
 template <int ARITH>
 cudaError_t launch_one(pb200_ensemble* e, unsigned long long n) {
-    static thread_local int configured_device = -1, blocks_per_sm = 0;
     // lane = planet: N - 1 lanes per system
     const size_t threads = e->n_sys * (size_t)(PB_S_N - 1);
-    return pb200_launch_sliced(e, PB_NS::small_steps_kernel<PB_S_N, PB_S_COORD, PB_S_FLAGS, ARITH>, PB_NS::small_smem_bytes<PB_S_COORD>(), PB_SBLOCK,
-                               configured_device, blocks_per_sm, threads, n);
+    static const bool force_small = []() { const char* v = getenv("PB200_SMALL_BLOCK"); return v && atoi(v) == 32; }();
+    const bool big = !force_small && 4 * threads >= 3 * (size_t)kBigBlock * (size_t)e->sm_count * (size_t)(256 / kBigBlock);
+    return big ? launch_blk<ARITH, kBigBlock>(e, threads, n) : launch_blk<ARITH, 32>(e, threads, n);
 }
 
 }  // namespace

@@ -26,12 +26,10 @@ using namespace pb200;
 
 extern __shared__ __align__(16) double pb_smem[];
 
-#ifndef PB_SBLOCK
-#define PB_SBLOCK 32
-#endif
-#ifndef PB_SMIN_BLOCKS
-#define PB_SMIN_BLOCKS 8
-#endif
+// CTA size BLK (template parameter): 8 warps are resident per SM either way (<= 255 registers, ~100 slots per thread). Small
+// ensembles take 32-thread CTAs (they spread over all SMs); large ones take one CTA of 8 warps per SM (N = 3) or two of 4
+// (N = 2): warps that start together stay loosely in phase and share the instruction-cache lines of the ~100 KB loop
+// body (N = 3: + 8-10 %, profiles/r2_small_variants.md).
 #define PB_HIST_FIELDS 17
 #define PB_TIDE_SCRATCH 13
 
@@ -57,14 +55,15 @@ enum SmallSlot : int {
     J_EI1 = N_SMALL_SLOTS_DH, J_PME1, J_EI2, J_PME2, J_MI, J_ET1, J_BEI1, J_ET0, J_BMI, J_ETAK,
     N_SMALL_SLOTS_JACOBI
 };
-template <int COORD> constexpr size_t small_smem_bytes() {
-    return (size_t)(COORD == PB200_COORD_JACOBI ? N_SMALL_SLOTS_JACOBI : N_SMALL_SLOTS_DH) * PB_SBLOCK * sizeof(double);
+template <int COORD, int BLK> constexpr size_t small_smem_bytes() {
+    return (size_t)(COORD == PB200_COORD_JACOBI ? N_SMALL_SLOTS_JACOBI : N_SMALL_SLOTS_DH) * BLK * sizeof(double);
 }
 
-struct Sl {
+template <int BLK>
+struct SlT {
     volatile double* base;
-    __device__ __forceinline__ double get(int i) const { return base[i * PB_SBLOCK]; }
-    __device__ __forceinline__ void set(int i, double v) const { base[i * PB_SBLOCK] = v; }
+    __device__ __forceinline__ double get(int i) const { return base[i * BLK]; }
+    __device__ __forceinline__ void set(int i, double v) const { base[i * BLK] = v; }
     __device__ __forceinline__ V3 get3(int i) const { return v3(get(i), get(i + 1), get(i + 2)); }
     __device__ __forceinline__ void set3(int i, V3 v) const { set(i, v.x); set(i + 1, v.y); set(i + 2, v.z); }
     __device__ __forceinline__ srcp rcp(int val, int y) const { srcp r; r.b = get(val); r.y = get(y); return r; }
@@ -96,7 +95,7 @@ struct SmallRoles { bool t_on, f_on, g_on; };
 
 // ---- constants (launch start and whenever a radius evolves). What the exact forces read is computed with `sd` in the
 // reference's association order (see exact_effects.cuh / forces_fast.cuh::make_consts: the same expressions).
-template <int N, int COORD, int FLAGS>
+template <int N, int COORD, int FLAGS, class Sl>
 __device__ __forceinline__ void small_consts(const KParams& P, const Sl& sl, const SmallRoles& ro, bool valid, int b, size_t sys) {
     const size_t ns = (size_t)P.n_sys;
     double sigma = 0., k2t = 0., k2f = 0., mg = 1., sig_h = 0., k2t_h = 0., k2f_h = 0., Mg = 1.;
@@ -164,7 +163,7 @@ __device__ __forceinline__ void small_consts(const KParams& P, const Sl& sl, con
 // ---- Universe::calculate_additional_effects for one planet and its share of the host sums, fast arithmetic
 // (forces_fast.cuh::additional_effects with the host's quantities held by the lane itself).
 // Out: acceleration and dL/dt of the planet; a_h / dl_h = this planet's contributions to the host's.
-template <int FLAGS, bool HYB>
+template <int FLAGS, bool HYB, class Sl>
 __device__ __forceinline__ void small_effects_fast(const KParams& P, const Sl& sl, bool valid, int b, size_t sys, SmallState& q, V3 hr, double inv_d,
                                                    V3 hv, V3& a_p, V3& dl_p, V3& a_h, V3& dl_h, bool tide_save) {
     const double rs_s = q.rs_s, rs_p = q.rs_p;
@@ -261,7 +260,7 @@ __device__ __forceinline__ void small_effects_fast(const KParams& P, const Sl& s
 // ---- The same in the reference's own arithmetic (exact_effects.cuh::additional_effects_exact, operation by operation).
 // Out: the planet's acceleration and dL/dt, and the HOST's (sums over the planets in index order, partner's terms by
 // shuffle): bit-identical in every lane of the group.
-template <int N, int FLAGS>
+template <int N, int FLAGS, class Sl>
 __device__ __forceinline__ void small_effects_exact(const KParams& P, const Sl& sl, const SmallRoles& ro, bool valid, int b, size_t sys, SmallState& q,
                                                     S3 hr, sd dist, S3 hv, S3& a_p, S3& dl_p, S3& a_h, S3& dl_h, bool tide_save) {
     const bool first = b == 1;
@@ -458,6 +457,7 @@ __device__ __forceinline__ void small_effects_exact(const KParams& P, const Sl& 
 }
 
 // effects/evolution.rs:516-546 for one body. R / I live in slots (slot_r, slot_i), rg2 in slot_g. Returns true when something changed.
+template <class Sl>
 __device__ __forceinline__ bool small_evolve(const KParams& P, const Sl& sl, int body, size_t sys, double t, bool commit, bool writer,
                                              int slot_m, int slot_r, int slot_i, int slot_g) {
     if (!commit) return false;
@@ -480,8 +480,8 @@ __device__ __forceinline__ bool small_evolve(const KParams& P, const Sl& sl, int
     return false;
 }
 
-template <int N, int COORD, int FLAGS, int ARITH>
-__global__ void __launch_bounds__(PB_SBLOCK, PB_SMIN_BLOCKS) small_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
+template <int N, int COORD, int FLAGS, int ARITH, int BLK>
+__global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
     constexpr int W = N - 1;
     constexpr bool JAC = COORD == PB200_COORD_JACOBI;
     static_assert(N == 2 || N == 3, "small_steps_kernel: 2 or 3 bodies");
@@ -514,6 +514,7 @@ __global__ void __launch_bounds__(PB_SBLOCK, PB_SMIN_BLOCKS) small_steps_kernel(
     const bool writer = valid && first;  // the lane that stores the host body and the per-system words
     SmallRoles ro;
     ro.t_on = (P.tides_orbiting >> b) & 1u; ro.f_on = (P.flat_orbiting >> b) & 1u; ro.g_on = (P.gr_orbiting >> b) & 1u;
+    typedef SlT<BLK> Sl;
     Sl sl;
     sl.base = pb_smem + threadIdx.x;
     const size_t ns = (size_t)P.n_sys;

@@ -14,15 +14,31 @@ import sys
 import tempfile
 
 
+STEP_FILE = os.environ.get("PB200_STEP_FILE", "whfast_step.cuh")   # small_step.cuh for the lane = planet kernel
+
+
 def main():
     rep, so, kern = sys.argv[1:4]
     warp_steps = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
     focus = sys.argv[5] if len(sys.argv) > 5 else None
     ophist = collections.Counter()
-    tmp = tempfile.mkdtemp()
-    subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
-    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin") and "case_io" not in f][0]
-    dis = subprocess.run(["nvdisasm", "-gi", cubin], stdout=subprocess.PIPE, text=True).stdout
+    # One cubin per translation unit. Units compiled from the same source (kernels_tu.cu, kernels_small_tu.cu with different
+    # -D flags) extract to the same file name from the linked library, so the per-unit objects next to it are searched instead.
+    objdir = os.path.join(os.path.dirname(os.path.abspath(so)), "build" if os.path.basename(so) == "libposidonius_b200.so" else "build_" + os.path.basename(so))
+    objs = sorted(os.path.join(objdir, f) for f in os.listdir(objdir) if f.endswith(".o")) if os.path.isdir(objdir) else []
+    dis = ""
+    for obj in objs + [os.path.abspath(so)]:
+        tmp = tempfile.mkdtemp()
+        subprocess.call(["cuobjdump", "-xelf", "all", obj], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for f in sorted(os.listdir(tmp)):
+            if not f.endswith(".cubin"):
+                continue
+            names = subprocess.run(["cuobjdump", "-elf", os.path.join(tmp, f)], stdout=subprocess.PIPE, text=True).stdout
+            if kern in names:
+                dis = subprocess.run(["nvdisasm", "-gi", os.path.join(tmp, f)], stdout=subprocess.PIPE, text=True).stdout
+                break
+        if dis:
+            break
     addr2 = {}
     in_k = False
     chain = []
@@ -64,7 +80,7 @@ def main():
         op = m.group(2) if m else "?"
         f64 = 1 if op.split(".")[0] in ("DADD", "DMUL", "DFMA", "DSETP", "MUFU") else 0
         # outermost frame that lies in whfast_step.cuh (the kernel body / midpoint / gravity)
-        step_frames = [c for c in ch if c[0] == "whfast_step.cuh"]
+        step_frames = [c for c in ch if c[0] == STEP_FILE]
         o = step_frames[-1] if step_frames else ch[-1]
         o2 = step_frames[0] if step_frames else ch[0]
         outer["%s:%d" % o][f64] += ex

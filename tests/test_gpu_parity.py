@@ -433,16 +433,18 @@ def test_wind_spins_the_star_down(E):
     assert out[0] < out[1]
 
 
-@pytest.mark.parametrize("pieces", ["2", "5"])
-def test_time_sliced_launch_is_bit_identical(E, pieces, monkeypatch):
+@pytest.mark.parametrize("name,pieces", [("c4_trappist1", "2"), ("c4_trappist1", "5"), ("c1_example", "3"), ("c3_case7_evolving", "4"),
+                                         ("c5_circumbinary", "5")])
+def test_time_sliced_launch_is_bit_identical(E, name, pieces, monkeypatch):
     """A launch cut into consecutive pieces per block of systems (wave-quantisation fix, pb200_api.cu plan_pieces) hands
-    the state from CTA to CTA through HBM: results, clocks, iteration counters and history must equal the plain launch."""
+    the state from CTA to CTA through HBM: results, clocks, iteration counters and history must equal the plain launch.
+    Covers the 8-body kernel and the lane = planet kernel of the 2- / 3-body configurations (evolving radii included)."""
     from posidonius_b200.case import case_from_dict
     from posidonius_b200.perturb import make_ensemble_cases
-    d = config_case("c4_trappist1")
-    d["historic_snapshot_period"] = 4.0   # every 50 steps: snapshots fall inside several pieces
+    d = config_case(name)
+    d["historic_snapshot_period"] = 50 * d["time_step"]   # every 50 steps (4 days for TRAPPIST-1): snapshots fall inside several pieces
     case, tables = case_from_dict(d)
-    cases = make_ensemble_cases(case, 3000, 77)   # 375 CTAs: more than one piece boundary per SM
+    cases = make_ensemble_cases(case, 3000, 77)   # 375 CTAs of the 8-body kernel: more than one piece boundary per SM
     out = []
     for k in ("1", pieces):
         monkeypatch.setenv("PB200_PIECES", k)
@@ -459,7 +461,7 @@ def test_time_sliced_launch_is_bit_identical(E, pieces, monkeypatch):
         assert np.array_equal(a[0][key], b[0][key]), key
     assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     assert np.array_equal(a[4], b[4]) and a[4].shape[1] == 7
-    assert a[5:] == b[5:] == (333, 7)
+    assert a[5:] == b[5:] == (333, 7)   # snapshots at steps 0, 50 (or 51: the accumulated clock), ..., 300
 
 
 def test_eight_body_specialisation_matches_generic_kernel(E, monkeypatch):
@@ -623,6 +625,66 @@ def test_mixed_fates_inside_one_ensemble(E):
     assert (~alive).sum() == 9
     for s in np.where(~alive)[0]:
         assert it[s] == oc[s].current_iteration   # the step at which the reference would have panicked
+
+
+@pytest.mark.parametrize("name", ["c1_example", "c3_case7", "c5_circumbinary"])
+def test_mixed_fates_in_small_systems(E, name):
+    """The same for the lane = planet kernel (2 and 3 bodies, democratic heliocentric and Jacobi): host pairs checked by the
+    planet's lane, the planet-planet pair by both lanes, the group-wide verdict = the first failing pair of the reference's
+    loop order; status, event iteration and the survivors' state equal the oracle's, in every arithmetic mode."""
+    from oracle.binding import run_ensemble
+    from posidonius_b200 import abi
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import cases_as_numpy, make_ensemble_cases
+    case, tables = case_from_dict(config_case(name))
+    n = case.n_particles
+    n_sys = 45
+    cases = make_ensemble_cases(case, n_sys, 37)
+    arr = cases_as_numpy(cases)
+    h = case.host_most_massive
+    pos, vel = arr["bodies"]["inertial_position"], arr["bodies"]["inertial_velocity"]
+    moves = [(3, 1, 0.1), (4, n - 1, 2.0e4), (17, 1, 3.0e4), (44, n - 1, 0.05)]
+    for s, body, factor in moves:
+        pos[s, body] = pos[s, h] + factor * (pos[s, body] - pos[s, h])
+    touched = [m[0] for m in moves]
+    if n == 3:
+        # planet 2 next to planet 1 (inside the Roche radius / the summed radii), same velocity
+        for s, gap in ((9, 1.0e-5), (10, 2.0e-4), (26, 3.0e-5)):
+            pos[s, 2] = pos[s, 1] + np.array([gap, 0.0, 0.0])
+            vel[s, 2] = vel[s, 1]
+            touched.append(s)
+        # both fates in one system: planet 1 inside the host's Roche radius AND planet 2 ejected (the lower pair wins)
+        pos[31, 1] = pos[31, h] + 0.1 * (pos[31, 1] - pos[31, h])
+        pos[31, 2] = pos[31, h] + 3.0e4 * (pos[31, 2] - pos[31, h])
+        touched.append(31)
+    steps = 300
+    oc, ost, _ = run_ensemble(cases, n_sys, tables, steps, True, 4)
+    o = oracle_state_of(oc)
+    # (how close is fatal depends on the configuration: the oracle decides; most of the displaced members must not survive)
+    assert (ost != abi.STATUS_OK).sum() >= len(touched) - 1 and len(set(ost.tolist())) >= 3, ost
+    for arithmetic in (abi.ARITH_HYBRID, abi.ARITH_STRICT, abi.ARITH_FAST):
+        with E.Ensemble(cases, tables, arithmetic=arithmetic) as ens:
+            ens.initialize_physical_values()
+            ens.iterate(120)
+            ens.iterate(steps - 120)
+            g = gpu_state_of(ens)
+            st, w, it = ens.status()
+        assert np.array_equal(st, ost), (arithmetic, st, ost)
+        alive = st == abi.STATUS_OK
+        assert alive.sum() == (ost == abi.STATUS_OK).sum()
+        # a member displaced deep inside the star can blow up numerically without tripping a check (the reference's state
+        # is NaN as well): it must be NaN on both sides, and is left out of the comparison of the survivors
+        blown = np.isnan(o["position"]).any(axis=(1, 2))
+        assert np.array_equal(blown, np.isnan(g["position"]).any(axis=(1, 2)))
+        alive &= ~blown
+        for k in ("position", "velocity", "spin", "angular_momentum"):
+            assert rel_err(g[k][alive], o[k][alive]) < TOL_1E3, (arithmetic, k, rel_err(g[k][alive], o[k][alive]))
+        assert np.array_equal(g["current_time"], o["current_time"])
+        for s in np.where(st != abi.STATUS_OK)[0]:
+            assert it[s] == oc[s].current_iteration, (arithmetic, s)
+        if arithmetic == abi.ARITH_STRICT:
+            for k in ("position", "velocity", "spin", "angular_momentum", "acceleration"):
+                assert np.array_equal(g[k][alive], o[k][alive]), k
 
 
 def test_empty_and_invalid_ensembles_are_rejected(E):
