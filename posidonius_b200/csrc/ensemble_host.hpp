@@ -34,6 +34,7 @@ struct pb200_ensemble {
     int sm_count = 0;
     bool perturbed = false;       // built by pb200_ensemble_create_perturbed: heliocentric fields of the image are per member
     bool narrow_blocks = false;   // PB200_NARROW_BLOCKS=1: never use the 384-thread build of the 8-body kernel (A/B tests)
+    bool pair_lanes = false;      // PB200_PAIR_LANES=1: 3-body Jacobi systems always on the two-lane build (A/B tests of the passive-planet build)
     bool force_generic = false;   // PB200_FORCE_GENERIC=1 in the environment: bypass the compile-time geometry builds (A/B tests)
     // host mirror of the ensemble clock (exact snapshot counting without a device round trip); invalid after an upload of
     // current_time (uniform_clock = false: the device is asked instead)
@@ -103,4 +104,5 @@ cudaError_t pb200_launch_s2(pb200_ensemble* e, unsigned long long n);    // 2 bo
 cudaError_t pb200_launch_s2t(pb200_ensemble* e, unsigned long long n);   // 2 bodies, DH, tides only                            (config 2)
 cudaError_t pb200_launch_s3(pb200_ensemble* e, unsigned long long n);    // 3 bodies, DH, tides + flattening + Kidder          (config 3)
 cudaError_t pb200_launch_s3e(pb200_ensemble* e, unsigned long long n);   // 3 bodies, DH, the same + evolution                 (config 3 evolving)
-cudaError_t pb200_launch_s3j(pb200_ensemble* e, unsigned long long n);   // 3 bodies, Jacobi, the same + evolution             (config 5)
+cudaError_t pb200_launch_s3j(pb200_ensemble* e, unsigned long long n);   // 3 bodies, Jacobi, the same + evolution
+cudaError_t pb200_launch_s3p(pb200_ensemble* e, unsigned long long n);   // the same with body 2 outside every effect: thread = system (config 5)

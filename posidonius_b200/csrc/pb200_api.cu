@@ -416,6 +416,7 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     e->clock_t = c0.current_time; e->clock_last_hist = c0.last_historic_snapshot_time;
     { const char* fg = getenv("PB200_FORCE_GENERIC"); e->force_generic = fg && fg[0] == '1'; }
     { const char* nb = getenv("PB200_NARROW_BLOCKS"); e->narrow_blocks = nb && nb[0] == '1'; }
+    { const char* pl = getenv("PB200_PAIR_LANES"); e->pair_lanes = pl && pl[0] == '1'; }
     if (cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) e->sm_count = 0;
     for (size_t s = 1; s < n_cases; s++)
         if (cases[s].current_time != c0.current_time || cases[s].last_historic_snapshot_time != c0.last_historic_snapshot_time) e->uniform_clock = false;
@@ -736,7 +737,11 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
         else if (fixed_ok && e->P.spin_on && e->n_bodies == 3 && dh && kidder && e->P.flags == tfg) err = pb200_launch_s3(e, n_steps);
         else if (fixed_ok && e->P.spin_on && e->n_bodies == 3 && dh && kidder && e->P.flags == (tfg | FLAG_EVO)) err = pb200_launch_s3e(e, n_steps);
         else if (fixed_ok && e->P.spin_on && e->n_bodies == 3 && e->coord == PB200_COORD_JACOBI && kidder && e->P.flags == (tfg | FLAG_EVO))
-            err = pb200_launch_s3j(e, n_steps);
+            // body 2 an OrbitingBody of no effect (the circumbinary planet): it rides in body 1's thread once the ensemble fills the
+            // GPU that way (six warps per SM); a smaller ensemble keeps two lanes per system (twice the warps: 8192 members 4.4e8 vs 4.2e8)
+            err = (((e->P.tides_orbiting | e->P.flat_orbiting | e->P.gr_orbiting) >> 2) & 1u) == 0 && !e->pair_lanes &&
+                          4 * e->n_sys >= 3 * (size_t)192 * (size_t)e->sm_count
+                      ? pb200_launch_s3p(e, n_steps) : pb200_launch_s3j(e, n_steps);
         else if (e->arithmetic == PB200_ARITH_FAST) err = pb200_launch_generic_fast(e, threads, n_steps);
         else if (e->arithmetic == PB200_ARITH_STRICT) err = pb200_launch_generic_strict(e, threads, n_steps);
         else err = pb200_launch_generic_hybrid(e, threads, n_steps);

@@ -53,10 +53,16 @@ enum SmallSlot : int {
     N_SMALL_SLOTS_DH,
     // Jacobi only: the step-invariant scalars of the recurrences (whfast.rs:881-963, 1026-1088)
     J_EI1 = N_SMALL_SLOTS_DH, J_PME1, J_EI2, J_PME2, J_MI, J_ET1, J_BEI1, J_ET0, J_BMI, J_ETAK,
-    N_SMALL_SLOTS_JACOBI
+    N_SMALL_SLOTS_JACOBI,
+    // passive-planet build only (body 2 carried by the thread of body 1): its midpoint working set, base quantities, Kepler
+    // mu, squared collision / Roche distances of the pair (host, body 2)
+    P2_ERR = N_SMALL_SLOTS_JACOBI, P2_ORIG = P2_ERR + 6, P2_INCR = P2_ORIG + 6,
+    K2_M = P2_INCR + 6, K2_R, K2_I, K2_RG2, K2_KMU, K2_RS2H, K2_RR2H,
+    K2_L, K2_LY, K2_LZ, K2_S, K2_SY, K2_SZ,   // its angular momentum and spin (touched once per midpoint)
+    N_SMALL_SLOTS_PASSIVE
 };
-template <int COORD, int BLK> constexpr size_t small_smem_bytes() {
-    return (size_t)(COORD == PB200_COORD_JACOBI ? N_SMALL_SLOTS_JACOBI : N_SMALL_SLOTS_DH) * BLK * sizeof(double);
+template <int COORD, int BLK, bool PASSIVE> constexpr size_t small_smem_bytes() {
+    return (size_t)(PASSIVE ? N_SMALL_SLOTS_PASSIVE : COORD == PB200_COORD_JACOBI ? N_SMALL_SLOTS_JACOBI : N_SMALL_SLOTS_DH) * BLK * sizeof(double);
 }
 
 template <int BLK>
@@ -70,9 +76,9 @@ struct SlT {
 };
 
 // partner lane of the group (N = 3 only; every lane of the warp takes part)
-template <int N> __device__ __forceinline__ double xd(double v) { return N == 3 ? __shfl_xor_sync(FULL, v, 1) : v; }
-template <int N> __device__ __forceinline__ V3 x3(V3 v) { return v3(xd<N>(v.x), xd<N>(v.y), xd<N>(v.z)); }
-template <int N> __device__ __forceinline__ S3 x3(S3 v) { return strict(x3<N>(plain(v))); }
+template <bool PAIR> __device__ __forceinline__ double xd(double v) { return PAIR ? __shfl_xor_sync(FULL, v, 1) : v; }
+template <bool PAIR> __device__ __forceinline__ V3 x3(V3 v) { return v3(xd<PAIR>(v.x), xd<PAIR>(v.y), xd<PAIR>(v.z)); }
+template <bool PAIR> __device__ __forceinline__ S3 x3(S3 v) { return strict(x3<PAIR>(plain(v))); }
 // (planet 1's, planet 2's) from (mine, the partner's)
 __device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a : b; }
 __device__ __forceinline__ S3 sel(bool c, S3 a, S3 b) { return s3(sd(sel(c, a.x.v, b.x.v)), sd(sel(c, a.y.v, b.y.v)), sd(sel(c, a.z.v, b.z.v))); }
@@ -82,6 +88,7 @@ struct SmallState {
     S3 r, v, r0, v0;        // inertial position / velocity of the planet and of the host
     V3 L, s, L0, s0;        // angular momentum and spin (of the previous evaluation)
     double rs_s, rs_p;      // r . w_host, r . w_planet with the spins of the previous evaluation (Q3)
+    S3 r2, v2;              // passive-planet build: body 2 (no effect acts on it; it drifts, is kicked and is checked)
 };
 struct SmallSys {
     double t, last_hist;
@@ -95,7 +102,7 @@ struct SmallRoles { bool t_on, f_on, g_on; };
 
 // ---- constants (launch start and whenever a radius evolves). What the exact forces read is computed with `sd` in the
 // reference's association order (see exact_effects.cuh / forces_fast.cuh::make_consts: the same expressions).
-template <int N, int COORD, int FLAGS, class Sl>
+template <int N, int COORD, int FLAGS, bool PASSIVE, class Sl>
 __device__ __forceinline__ void small_consts(const KParams& P, const Sl& sl, const SmallRoles& ro, bool valid, int b, size_t sys) {
     const size_t ns = (size_t)P.n_sys;
     double sigma = 0., k2t = 0., k2f = 0., mg = 1., sig_h = 0., k2t_h = 0., k2f_h = 0., Mg = 1.;
@@ -154,9 +161,11 @@ __device__ __forceinline__ void small_consts(const KParams& P, const Sl& sl, con
     // collision distance of the pair (host, planet): universe.rs:229-233
     { const double rs = __dadd_rn(Rh, R); sl.set(K_RS2H, __dmul_rn(rs, rs)); }
     if (N == 3) {
-        const double Rp = xd<N>(R);
+        constexpr bool PAIR = !PASSIVE;
+        const double Rp = PASSIVE ? sl.get(K2_R) : xd<PAIR>(R);
         const double rs = b == 1 ? __dadd_rn(R, Rp) : __dadd_rn(Rp, R);
         sl.set(K_RS2P, __dmul_rn(rs, rs));
+        if (PASSIVE) { const double rs2 = __dadd_rn(Rh, Rp); sl.set(K2_RS2H, __dmul_rn(rs2, rs2)); }
     }
 }
 
@@ -260,16 +269,20 @@ __device__ __forceinline__ void small_effects_fast(const KParams& P, const Sl& s
 // ---- The same in the reference's own arithmetic (exact_effects.cuh::additional_effects_exact, operation by operation).
 // Out: the planet's acceleration and dL/dt, and the HOST's (sums over the planets in index order, partner's terms by
 // shuffle): bit-identical in every lane of the group.
-template <int N, int FLAGS, class Sl>
+template <int N, int FLAGS, bool PASSIVE, class Sl>
 __device__ __forceinline__ void small_effects_exact(const KParams& P, const Sl& sl, const SmallRoles& ro, bool valid, int b, size_t sys, SmallState& q,
                                                     S3 hr, sd dist, S3 hv, S3& a_p, S3& dl_p, S3& a_h, S3& dl_h, bool tide_save) {
     const bool first = b == 1;
     const sd zero = sd(0.);
     const S3 zero3 = s3(zero, zero, zero);
     // the host sums of two vectors: 0 + planet 1's + planet 2's (the reference's serial loops)
+    constexpr bool PAIR = N == 3 && !PASSIVE;
     auto host_sums = [&](S3 u, S3 w, S3& su, S3& sw) {
-        if (N == 3) {
-            const S3 uo = x3<N>(u), wo = x3<N>(w);
+        if (PASSIVE) {
+            // body 2 is no OrbitingBody of any effect: its terms are zeros (added like the general kernel adds them)
+            su = (zero3 + u) + zero3; sw = (zero3 + w) + zero3;
+        } else if (N == 3) {
+            const S3 uo = x3<PAIR>(u), wo = x3<PAIR>(w);
             su = (zero3 + sel(first, u, uo)) + sel(first, uo, u);
             sw = (zero3 + sel(first, w, wo)) + sel(first, wo, w);
         } else { su = zero3 + u; sw = zero3 + w; }
@@ -480,12 +493,18 @@ __device__ __forceinline__ bool small_evolve(const KParams& P, const Sl& sl, int
     return false;
 }
 
-template <int N, int COORD, int FLAGS, int ARITH, int BLK>
+// PASSIVE (3 bodies, Jacobi): body 2 is no OrbitingBody of any effect (the circumbinary planet of config 5). In the two-lane
+// mapping its lane would execute every force evaluation next to body 1's lane for nothing, so here ONE thread carries the
+// system: body 1 (with the forces), the host, and body 2, which only drifts (a second pass through the Kepler solver), is
+// kicked and is checked. Half the instructions per system-step, no exchange at all.
+template <int N, int COORD, int FLAGS, int ARITH, int BLK, bool PASSIVE>
 __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __grid_constant__ KParams P, unsigned long long n_steps) {
-    constexpr int W = N - 1;
+    constexpr int W = PASSIVE ? 1 : N - 1;
+    constexpr bool PAIR = W == 2;        // two lanes per system: the partner's terms travel by shuffle
     constexpr bool JAC = COORD == PB200_COORD_JACOBI;
     static_assert(N == 2 || N == 3, "small_steps_kernel: 2 or 3 bodies");
     static_assert(!JAC || N == 3, "Jacobi build: 3 bodies");
+    static_assert(!PASSIVE || JAC, "passive-planet build: 3 bodies, Jacobi coordinates");
     // ---- time slicing (see whfast_step.cuh): ticket -> (piece, group)
     __shared__ unsigned int s_ticket;
     unsigned int piece = 0, group = blockIdx.x;
@@ -529,6 +548,12 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
         q.rs_s = 0.; q.rs_p = 0.;
         sl.set3(P_ERR, ld3(P.verr, b)); sl.set3(P_ERR + 3, ld3(P.lerr, b));
         sl.set3(H_ERR, ld3(P.verr, 0)); sl.set3(H_ERR + 3, ld3(P.lerr, 0));
+        if (PASSIVE) {
+            q.r2 = strict(ld3(P.pos, 2)); q.v2 = strict(ld3(P.vel, 2)); sl.set3(K2_L, ld3(P.L, 2)); sl.set3(K2_S, ld3(P.spin, 2));
+            sl.set3(P2_ERR, ld3(P.verr, 2)); sl.set3(P2_ERR + 3, ld3(P.lerr, 2));
+            const size_t i2 = (size_t)2 * ns + sys;
+            sl.set(K2_M, P.mass[i2]); sl.set(K2_R, ldm(P.radius + i2)); sl.set(K2_I, ldm(P.moi + i2)); sl.set(K2_RG2, ldm(P.rg2 + i2));
+        }
         const size_t i = (size_t)b * ns + sys;
         sl.set(K_M, P.mass[i]); sl.set(K_R, ldm(P.radius + i)); sl.set(K_I, ldm(P.moi + i)); sl.set(K_RG2, ldm(P.rg2 + i));
         sl.set(H_M, P.mass[sys]); sl.set(H_R, ldm(P.radius + sys)); sl.set(H_I, ldm(P.moi + sys)); sl.set(H_RG2, ldm(P.rg2 + sys));
@@ -538,16 +563,18 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
         st.steps_done = 0; st.n_hist_new = 0; st.event_step = 0;
     }
     bool alive = sys_ok && st.status == PB200_STATUS_OK;
-    small_consts<N, COORD, FLAGS>(P, sl, ro, valid, b, sys);
+    small_consts<N, COORD, FLAGS, PASSIVE>(P, sl, ro, valid, b, sys);
     {
         // Roche distances (universe.rs:177-196: filled for lower index < higher index)
         const double rr = __ldg(P.roche + ((size_t)(0 * N + b)) * ns + sys);
         sl.set(K_RR2H, __dmul_rn(rr, rr));
         if (N == 3) { const double rp = __ldg(P.roche + ((size_t)(1 * N + 2)) * ns + sys); sl.set(K_RR2P, __dmul_rn(rp, rp)); }
+        if (PASSIVE) { const double r2h = __ldg(P.roche + ((size_t)(0 * N + 2)) * ns + sys); sl.set(K2_RR2H, __dmul_rn(r2h, r2h)); }
         // constants of the transforms, strict and in the reference's order (whfast_step.cuh, kernel prologue)
         const sd m_s = sd(sl.get(K_M)), M_s = sd(sl.get(H_M));
         const sd mg_s = sd(P.mass_g[(size_t)b * ns + sys]), Mg_s = sd(P.mass_g[sys]);
-        const sd mp_s = sd(xd<N>(m_s.v)), mgp_s = sd(xd<N>(mg_s.v));
+        const sd mp_s = PASSIVE ? sd(sl.get(K2_M)) : sd(xd<PAIR>(m_s.v));
+        const sd mgp_s = PASSIVE ? sd(P.mass_g[(size_t)2 * ns + sys]) : sd(xd<PAIR>(mg_s.v));
         const sd m1 = first ? m_s : mp_s, m2 = first ? mp_s : m_s;        // masses of planets 1 and 2 (N = 3)
         const sd mg1 = first ? mg_s : mgp_s, mg2 = first ? mgp_s : mg_s;
         sd mtot = JAC ? M_s : sd(0.) + M_s;
@@ -556,6 +583,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
         mtot = mtot + m1; mu = mu + mg1;
         eta_k = mtot; mu_k = mu;
         if (N == 3) { mtot = mtot + m2; mu = mu + mg2; if (!first) { eta_k = mtot; mu_k = mu; } }
+        if (PASSIVE) sl.set(K2_KMU, mu.v);   // body 2's Kepler mu: the cumulative gravitational mass up to and including it
         sl.set(K_KMU, JAC ? mu_k.v : Mg_s.v);
         sl.set(K_BACKW, (m_s / M_s).v);
         sl.set(K_BACKWP, (mp_s / M_s).v);
@@ -579,12 +607,17 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
     const S3 zero3 = s3(zero, zero, zero);
     const sd dt_s = sd(P.dt), hdt_s = sd(P.half_dt);
     S3 anew = zero3, anew0 = zero3;     // Newtonian acceleration of the planet / the host (last gravity evaluation)
+    S3 anew2 = zero3;                   // ... of body 2 (passive-planet build)
 
     auto store_state = [&]() {
         if (!valid) return;
         auto st3 = [&](double* a, int body, V3 x) { const size_t i = (size_t)body * ns + sys; a[i] = x.x; a[i + cs] = x.y; a[i + 2 * cs] = x.z; };
         st3(P.pos, b, plain(q.r)); st3(P.vel, b, plain(q.v)); st3(P.L, b, q.L); st3(P.spin, b, q.s);
         st3(P.verr, b, sl.get3(P_ERR)); st3(P.lerr, b, sl.get3(P_ERR + 3));
+        if (PASSIVE) {
+            st3(P.pos, 2, plain(q.r2)); st3(P.vel, 2, plain(q.v2)); st3(P.L, 2, sl.get3(K2_L)); st3(P.spin, 2, sl.get3(K2_S));
+            st3(P.verr, 2, sl.get3(P2_ERR)); st3(P.lerr, 2, sl.get3(P2_ERR + 3));
+        }
         if (writer) {
             st3(P.pos, 0, plain(q.r0)); st3(P.vel, 0, plain(q.v0)); st3(P.L, 0, q.L0); st3(P.spin, 0, q.s0);
             st3(P.verr, 0, sl.get3(H_ERR)); st3(P.lerr, 0, sl.get3(H_ERR + 3));
@@ -601,7 +634,8 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
         // the planet by its lane, the host by every lane of the group (one of them stores)
         bool ch = small_evolve(P, sl, b, sys, t, commit && valid, valid, K_M, K_R, K_I, K_RG2);
         ch |= small_evolve(P, sl, 0, sys, t, commit && valid, writer, H_M, H_R, H_I, H_RG2);
-        if (__any_sync(FULL, ch)) small_consts<N, COORD, FLAGS>(P, sl, ro, valid, b, sys);
+        if (PASSIVE) ch |= small_evolve(P, sl, 2, sys, t, commit && valid, valid, K2_M, K2_R, K2_I, K2_RG2);
+        if (__any_sync(FULL, ch)) small_consts<N, COORD, FLAGS, PASSIVE>(P, sl, ro, valid, b, sys);
     };
 
 #pragma unroll 1
@@ -618,6 +652,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                     // spin = L / I (universe.rs:305-316, common.rs:9-11): it changes the live state too
                     q.s = plain(strict(q.L) / sd(sl.get(K_I)));
                     q.s0 = plain(strict(q.L0) / sd(sl.get(H_I)));
+                    if (PASSIVE) sl.set3(K2_S, plain(strict(sl.get3(K2_L)) / sd(sl.get(K2_I))));
                 }
                 if (snap && valid && st.hist_count < P.hist_capacity) {
                     auto record = [&](int body, V3 r_, V3 s_, V3 v_, int sm, int sr, int sg, double denergy) {
@@ -648,6 +683,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                     }
                     record(b, plain(q.r), q.s, plain(q.v), K_M, K_R, K_RG2, denergy);
                     if (writer) record(0, plain(q.r0), q.s0, plain(q.v0), H_M, H_R, H_RG2, 0.);
+                    if (PASSIVE) record(2, plain(q.r2), sl.get3(K2_S), plain(q.v2), K2_M, K2_R, K2_RG2, 0.);
                 }
                 if (snap) {
                     if (!first_snap) st.last_hist = __dadd_rn(st.last_hist, P.hist_period); else st.last_hist = 0.;
@@ -671,7 +707,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                 S3 spos, svel;                                     // centre of mass
                 // ---- inertial -> alternative (whfast.rs:881-1023)
                 if (JAC) {
-                    const S3 ro_ = x3<N>(q.r), vo_ = x3<N>(q.v);
+                    const S3 ro_ = PASSIVE ? q.r2 : x3<PAIR>(q.r), vo_ = PASSIVE ? q.v2 : x3<PAIR>(q.v);
                     const S3 r1 = sel(first, q.r, ro_), r2 = sel(first, ro_, q.r), v1 = sel(first, q.v, vo_), v2 = sel(first, vo_, q.v);
                     const sd ei1 = sd(sl.get(J_EI1)), pme1 = sd(sl.get(J_PME1)), ei2 = sd(sl.get(J_EI2)), pme2 = sd(sl.get(J_PME2)), mi = sd(sl.get(J_MI));
                     S3 s = M_s * q.r0, sv = M_s * q.v0;
@@ -687,7 +723,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                     const S3 mr = q.r * m_s, mv = q.v * m_s;
                     S3 sr = zero3 + q.r0 * M_s, sv = zero3 + q.v0 * M_s;
                     if (N == 3) {
-                        const S3 mro = x3<N>(mr), mvo = x3<N>(mv);
+                        const S3 mro = x3<PAIR>(mr), mvo = x3<PAIR>(mv);
                         sr = (sr + sel(first, mr, mro)) + sel(first, mro, mr);
                         sv = (sv + sel(first, mv, mvo)) + sel(first, mvo, mv);
                     } else { sr = sr + mr; sv = sv + mv; }
@@ -701,7 +737,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                         // ---- kick (whfast.rs:558-625)
                         if (JAC) {
                             // inertial_to_jacobi_acc (whfast.rs:935-963) + jacobi_interaction_step (:566-592)
-                            const S3 ao = x3<N>(anew);
+                            const S3 ao = PASSIVE ? anew2 : x3<PAIR>(anew);
                             const S3 a1 = sel(first, anew, ao), a2 = sel(first, ao, anew);
                             const sd ei1 = sd(sl.get(J_EI1)), pme1 = sd(sl.get(J_PME1)), ei2 = sd(sl.get(J_EI2));
                             S3 sa = M_s * anew0;
@@ -715,6 +751,14 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                             const sd rj3im = rji * rj2i * sd(kG) * sd(sl.get(J_ETAK));
                             const sd prefac = dt_s * rj3im;
                             if (!first) avel = avel + prefac * apos;
+                            if (PASSIVE) {
+                                // body 2 in the same thread: its Jacobi kick and the extra term (eta_2 = the total mass)
+                                avel_o = avel_o + dt_s * c2;
+                                const sd q2i = sd(1.) / (apos_o.x * apos_o.x + apos_o.y * apos_o.y + apos_o.z * apos_o.z + sd(1e-12));
+                                const sd qi = ssqrt(q2i);
+                                const sd q3im = qi * q2i * sd(kG) * sd(sl.get(K_MTOT));
+                                avel_o = avel_o + (dt_s * q3im) * apos_o;
+                            }
                         } else {
                             avel = avel + dt_s * anew;
                         }
@@ -723,13 +767,18 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                     auto jump = [&]() {
                         S3 psum = zero3;
                         const S3 mine = m_s * avel;
-                        if (N == 3) { const S3 other = x3<N>(mine); psum = (psum + sel(first, mine, other)) + sel(first, other, mine); }
+                        if (N == 3) { const S3 other = x3<PAIR>(mine); psum = (psum + sel(first, mine, other)) + sel(first, other, mine); }
                         else psum = psum + mine;
                         apos = s3(apos.x + hdt_s * psum.x / rM, apos.y + hdt_s * psum.y / rM, apos.z + hdt_s * psum.z / rM);
                     };
                     if (!JAC && phase == 1) jump();
-                    kepler_step(alive, apos, avel, sd(sl.get(K_KMU)), hdt_s, st.tswarn, st.warnings);
-                    if (N == 3) {
+                    // (passive-planet build: a second pass through the same code drifts body 2; the coordinates swap places twice)
+#pragma unroll 1
+                    for (int kb = 0; kb < (PASSIVE ? 2 : 1); kb++) {
+                        kepler_step(alive, apos, avel, sd(sl.get(kb ? K2_KMU : K_KMU)), hdt_s, st.tswarn, st.warnings);
+                        if (PASSIVE) { const S3 tp = apos, tv = avel; apos = apos_o; avel = avel_o; apos_o = tp; avel_o = tv; }
+                    }
+                    if (PAIR) {
                         // the warning belongs to the system (whfast.rs:702-707)
                         unsigned int wv = st.warnings | (st.tswarn ? 0x80000000u : 0u);
                         wv |= __shfl_xor_sync(FULL, wv, 1);
@@ -740,8 +789,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                     // ---- alternative -> inertial (whfast.rs:1026-1155)
                     S3 nr, nr0, nv = q.v, nv0 = q.v0, nr_o = zero3;
                     if (JAC) {
-                        apos_o = x3<N>(apos);
-                        if (phase == 1) avel_o = x3<N>(avel);
+                        if (PAIR) { apos_o = x3<PAIR>(apos); if (phase == 1) avel_o = x3<PAIR>(avel); }
                         const S3 p1 = sel(first, apos, apos_o), p2 = sel(first, apos_o, apos), w1 = sel(first, avel, avel_o), w2 = sel(first, avel_o, avel);
                         const sd mtot = sd(sl.get(K_MTOT)), bei2 = sd(sl.get(J_MI)), et1 = sd(sl.get(J_ET1)), bei1 = sd(sl.get(J_BEI1)), et0 = sd(sl.get(J_ET0)),
                                  bmi = sd(sl.get(J_BMI));
@@ -755,15 +803,16 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                         nr0 = s * bmi; nv0 = sv * bmi;
                         nr = sel(first, r1, r2); nr_o = sel(first, r2, r1);
                         if (phase == 1) nv = sel(first, v1, v2);
+                        if (PASSIVE && alive) { q.r2 = r2; if (phase == 1) q.v2 = v2; }
                     } else {
                         const S3 term = (apos * m_s) / rT;
                         const S3 vterm = avel * sd(sl.get(K_BACKW));
                         S3 star_r = spos, star_v = svel;
                         if (N == 3) {
-                            const S3 to = x3<N>(term);
+                            const S3 to = x3<PAIR>(term);
                             star_r = (star_r - sel(first, term, to)) - sel(first, to, term);
-                            if (phase == 1) { const S3 vo_ = x3<N>(vterm); star_v = (star_v - sel(first, vterm, vo_)) - sel(first, vo_, vterm); }
-                            apos_o = x3<N>(apos);
+                            if (phase == 1) { const S3 vo_ = x3<PAIR>(vterm); star_v = (star_v - sel(first, vterm, vo_)) - sel(first, vo_, vterm); }
+                            apos_o = x3<PAIR>(apos);
                             nr_o = apos_o + star_r;
                         } else {
                             star_r = star_r - term;
@@ -787,7 +836,24 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                         const sd dh2 = dh.x * dh.x + dh.y * dh.y + dh.z * dh.z;
                         check(0, b, dh2.v, K_RR2H, K_RS2H, true);
                         S3 acc = zero3, acc0 = zero3;
-                        if (N == 3) {
+                        if (PASSIVE) {
+                            // the three pairs in one thread (Jacobi: the pair (host, body 1) is ignored, universe.rs:240-250)
+                            const S3 d02 = q.r2 - q.r0, d12 = q.r2 - q.r;     // r_2 - r_0, r_2 - r_1
+                            const sd d02s = d02.x * d02.x + d02.y * d02.y + d02.z * d02.z, d12s = d12.x * d12.x + d12.y * d12.y + d12.z * d12.z;
+                            check(0, 2, d02s.v, K2_RR2H, K2_RS2H, true);
+                            check(1, 2, d12s.v, K_RR2P, K_RS2P, false);
+                            const sd di02 = ssqrt(d02s), di12 = ssqrt(d12s);
+                            const sd g02 = sd(-kG) / (di02 * di02 * di02), g12 = sd(-kG) / (di12 * di12 * di12);
+                            const sd pre02 = g02 * mp_s;           // host <- body 2, d = r_0 - r_2
+                            acc0 = s3(acc0.x + pre02 * (-d02.x), acc0.y + pre02 * (-d02.y), acc0.z + pre02 * (-d02.z));
+                            const sd pre12 = g12 * mp_s;           // body 1 <- body 2, d = r_1 - r_2
+                            acc = s3(acc.x + pre12 * (-d12.x), acc.y + pre12 * (-d12.y), acc.z + pre12 * (-d12.z));
+                            const sd pre20 = g02 * M_s, pre21 = g12 * m_s;   // body 2 <- host, then <- body 1
+                            S3 a2 = zero3;
+                            a2 = s3(a2.x + pre20 * d02.x, a2.y + pre20 * d02.y, a2.z + pre20 * d02.z);
+                            a2 = s3(a2.x + pre21 * d12.x, a2.y + pre21 * d12.y, a2.z + pre21 * d12.z);
+                            anew2 = a2;
+                        } else if (N == 3) {
                             const S3 d = q.r - nr_o;     // r_b - r_partner
                             const sd d2 = d.x * d.x + d.y * d.y + d.z * d.z;
                             check(1, 2, d2.v, K_RR2P, K_RS2P, false);
@@ -798,7 +864,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                                 const sd disth = ssqrt(dh2);
                                 const sd gh = sd(-kG) / (disth * disth * disth);     // pair (host, this planet)
                                 // planet 2's (host, 2) factor, needed by the host's acceleration in both lanes
-                                const double gh_x = xd<N>(gh.v);
+                                const double gh_x = xd<PAIR>(gh.v);
                                 const sd gh2 = sd(first ? gh_x : gh.v);
                                 const S3 dh_2 = first ? (nr_o - q.r0) : dh;          // r_2 - r_0
                                 const sd pre02 = gh2 * m2;                            // host's term from planet 2: -G / d^3 * m_2, d = r_0 - r_2
@@ -823,6 +889,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                             const size_t i = (size_t)b * ns + sys;
                             P.acc[i] = anew.x.v; P.acc[i + cs] = anew.y.v; P.acc[i + 2 * cs] = anew.z.v;
                             if (writer) { P.acc[sys] = anew0.x.v; P.acc[sys + cs] = anew0.y.v; P.acc[sys + 2 * cs] = anew0.z.v; }
+                            if (PASSIVE) { const size_t i2 = (size_t)2 * ns + sys; P.acc[i2] = anew2.x.v; P.acc[i2 + cs] = anew2.y.v; P.acc[i2 + 2 * cs] = anew2.z.v; }
                         }
                         if (died) {
                             st.status = code & 15; st.event_step = st.steps_done; alive = false;
@@ -839,6 +906,10 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                 sl.set3(H_ORIG, plain(q.v0)); sl.set3(H_ORIG + 3, q.L0);
                 sl.set3(P_INCR, v3(0., 0., 0.)); sl.set3(P_INCR + 3, v3(0., 0., 0.));
                 sl.set3(H_INCR, v3(0., 0., 0.)); sl.set3(H_INCR + 3, v3(0., 0., 0.));
+                if (PASSIVE) {
+                    sl.set3(P2_ORIG, plain(q.v2)); sl.set3(P2_ORIG + 3, sl.get3(K2_L));
+                    sl.set3(P2_INCR, v3(0., 0., 0.)); sl.set3(P2_INCR + 3, v3(0., 0., 0.));
+                }
                 const S3 hr_s = q.r - q.r0;
                 const V3 hr = plain(hr_s);
                 const double inv_d = ARITH == 1 ? 0. : rsqrt(dot(hr, hr));
@@ -851,17 +922,20 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                 for (int it = 0; it < 10; it++) {
                     if (!__any_sync(FULL, !done)) break;
                     if ((FLAGS & FLAG_EVO) && evolution && it == 0) evolve_all(st.t, alive);
+                    // calculate_spin of body 2 (every evaluation refreshes every particle's spin, common.rs:3-15): L_2 never
+                    // changes, so once per midpoint, after the inertia may have evolved
+                    if (PASSIVE && it == 0 && !done) sl.set3(K2_S, plain(strict(sl.get3(K2_L)) / sd(sl.get(K2_I))));
                     const S3 hv_s = q.v - q.v0;
                     const bool save_now = save_t && !done;
                     const bool exact_now = ARITH == 1 || (ARITH == 2 && it >= 2);
                     S3 a_p, dl_p, a_h, dl_h;    // (plain doubles inside `sd` when they come from the fast forces)
                     if (exact_now) {
-                        small_effects_exact<N, FLAGS>(P, sl, ro, valid, b, sys, q, hr_s, dist_s, hv_s, a_p, dl_p, a_h, dl_h, save_now);
+                        small_effects_exact<N, FLAGS, PASSIVE>(P, sl, ro, valid, b, sys, q, hr_s, dist_s, hv_s, a_p, dl_p, a_h, dl_h, save_now);
                     } else {
                         V3 fa_p, fdl_p, fa_h, fdl_h;
                         small_effects_fast<FLAGS, ARITH == 2>(P, sl, valid, b, sys, q, hr, inv_d, plain(hv_s), fa_p, fdl_p, fa_h, fdl_h, save_now);
-                        if (N == 3) {
-                            const V3 oa = x3<N>(fa_h), od = x3<N>(fdl_h);
+                        if (PAIR) {
+                            const V3 oa = x3<PAIR>(fa_h), od = x3<PAIR>(fdl_h);
                             fa_h = sel(first, fa_h, oa) + sel(first, oa, fa_h);
                             fdl_h = sel(first, fdl_h, od) + sel(first, od, fdl_h);
                         }
@@ -875,6 +949,15 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                     const S3 ndv0 = s3(hdt_s * a_h.x - ev0.x, hdt_s * a_h.y - ev0.y, hdt_s * a_h.z - ev0.z);
                     const S3 ndl0 = s3(hdt_s * dl_h.x - el0.x, hdt_s * dl_h.y - el0.y, hdt_s * dl_h.z - el0.z);
                     const S3 vf = vo + ndv, Lf = Lo + ndl, vf0 = vo0 + ndv0, Lf0 = Lo0 + ndl0;
+                    // passive-planet build: body 2 feels no additional effect — zero acceleration and torque through the same update
+                    S3 vo2 = zero3, Lo2 = zero3, ndv2 = zero3, ndl2 = zero3, vf2 = zero3, Lf2 = zero3;
+                    if (PASSIVE) {
+                        vo2 = strict(sl.get3(P2_ORIG)); Lo2 = strict(sl.get3(P2_ORIG + 3));
+                        const S3 ev2 = strict(sl.get3(P2_ERR)), el2 = strict(sl.get3(P2_ERR + 3));
+                        ndv2 = s3(hdt_s * zero - ev2.x, hdt_s * zero - ev2.y, hdt_s * zero - ev2.z);
+                        ndl2 = s3(hdt_s * zero - el2.x, hdt_s * zero - el2.y, hdt_s * zero - el2.z);
+                        vf2 = vo2 + ndv2; Lf2 = Lo2 + ndl2;
+                    }
                     bool conv_now = false;
                     if (it >= 2) {
                         // whfast.rs:424-451: sum(delta^2) / sum(total^2) < eps^2 decided as sum(delta_i^2 - eps^2 total_i^2) < 0
@@ -884,7 +967,13 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                         const V3 vfp = plain(vf), Lfp = plain(Lf), vf0p = plain(vf0), Lf0p = plain(Lf0);
                         double c_v = valid ? dot(ddv, ddv) - kEps2 * dot(vfp, vfp) : 0.;
                         double c_l = valid ? dot(ddl, ddl) - kEps2 * dot(Lfp, Lfp) : 0.;
-                        if (N == 3) { c_v += xd<N>(c_v); c_l += xd<N>(c_l); }
+                        if (PAIR) { c_v += xd<PAIR>(c_v); c_l += xd<PAIR>(c_l); }
+                        if (PASSIVE) {
+                            const S3 vf2_old = vo2 + strict(sl.get3(P2_INCR)), Lf2_old = Lo2 + strict(sl.get3(P2_INCR + 3));
+                            const V3 ddv2 = plain(vf2 - vf2_old), ddl2 = plain(Lf2 - Lf2_old), vf2p = plain(vf2), Lf2p = plain(Lf2);
+                            c_v += dot(ddv2, ddv2) - kEps2 * dot(vf2p, vf2p);
+                            c_l += dot(ddl2, ddl2) - kEps2 * dot(Lf2p, Lf2p);
+                        }
                         c_v += dot(ddv0, ddv0) - kEps2 * dot(vf0p, vf0p);
                         c_l += dot(ddl0, ddl0) - kEps2 * dot(Lf0p, Lf0p);
                         conv_now = c_v < 0. && c_l < 0.;
@@ -893,6 +982,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                         if (it > 0) {
                             sl.set3(P_INCR, plain(ndv)); sl.set3(P_INCR + 3, plain(ndl));
                             sl.set3(H_INCR, plain(ndv0)); sl.set3(H_INCR + 3, plain(ndl0));
+                            if (PASSIVE) { sl.set3(P2_INCR, plain(ndv2)); sl.set3(P2_INCR + 3, plain(ndl2)); }
                         }
                         if (conv_now) { done = true; converged = true; }
                         else {
@@ -902,6 +992,10 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                             q.v0 = s3(h * (vo0.x + vf0.x), h * (vo0.y + vf0.y), h * (vo0.z + vf0.z));
                             q.L = plain(s3(h * (Lo.x + Lf.x), h * (Lo.y + Lf.y), h * (Lo.z + Lf.z)));
                             q.L0 = plain(s3(h * (Lo0.x + Lf0.x), h * (Lo0.y + Lf0.y), h * (Lo0.z + Lf0.z)));
+                            if (PASSIVE) {
+                                q.v2 = s3(h * (vo2.x + vf2.x), h * (vo2.y + vf2.y), h * (vo2.z + vf2.z));
+                                sl.set3(K2_L, plain(s3(h * (Lo2.x + Lf2.x), h * (Lo2.y + Lf2.y), h * (Lo2.z + Lf2.z))));
+                            }
                         }
                     }
                 }
@@ -917,6 +1011,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                     };
                     commit(P_ORIG, P_INCR, P_ERR, q.v, q.L);
                     commit(H_ORIG, H_INCR, H_ERR, q.v0, q.L0);
+                    if (PASSIVE) { V3 L2n; commit(P2_ORIG, P2_INCR, P2_ERR, q.v2, L2n); sl.set3(K2_L, L2n); }
                 }
             }
         }

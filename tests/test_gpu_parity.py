@@ -512,6 +512,45 @@ def test_small_system_specialisations_match_generic_kernel(E, monkeypatch, name)
         assert rel_err(a[key], b[key]) < 1e-13, key
 
 
+def test_passive_planet_build_equals_two_lane_build(E, monkeypatch):
+    """Config 5 (Jacobi, the circumbinary planet an OrbitingBody of no effect) on an ensemble large enough for the one-thread-
+    per-system build (small_step.cuh, PASSIVE) against the two-lanes-per-system build (PB200_PAIR_LANES=1) and the oracle:
+    strict mode bit for bit in every array, hybrid mode bit for bit in r and v; historic records equal."""
+    from oracle.binding import run_ensemble
+    from posidonius_b200 import abi
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import make_ensemble_cases
+    d = config_case("c5_circumbinary")
+    d["historic_snapshot_period"] = 40 * d["time_step"]
+    case, tables = case_from_dict(d)
+    n_sys, steps = 22500, 130    # > 3/4 x 192 x 148 lanes: the dispatcher takes the passive-planet build
+    cases = make_ensemble_cases(case, n_sys, 91)
+    sample = np.r_[0:40, n_sys - 40:n_sys]
+    sub = (abi.Case * len(sample))()
+    for k, i in enumerate(sample):
+        sub[k] = cases[int(i)]
+    oc, ost, _ = run_ensemble(sub, len(sample), tables, steps, True, os.cpu_count() or 1)
+    o = oracle_state_of(oc)
+    for arithmetic in (abi.ARITH_STRICT, abi.ARITH_HYBRID):
+        out = []
+        for flag in ("0", "1"):
+            monkeypatch.setenv("PB200_PAIR_LANES", flag)
+            with E.Ensemble(cases, tables, arithmetic=arithmetic) as ens:
+                ens.initialize_physical_values()
+                ens.iterate(steps)
+                out.append((gpu_state_of(ens), ens.history_drain(), ens.status()[0]))
+        (a, ha, sa), (b, hb, sb) = out
+        assert np.array_equal(sa, sb) and (sa == 0).all()
+        keys = a.keys() if arithmetic == abi.ARITH_STRICT else ("position", "velocity", "acceleration", "current_time")
+        for k in keys:
+            assert np.array_equal(a[k], b[k]), (arithmetic, k)
+        for k in ("position", "velocity") + (("spin", "angular_momentum", "velocity_errors", "angular_momentum_errors") if arithmetic == abi.ARITH_STRICT else ()):
+            assert np.array_equal(a[k][sample], o[k]), (arithmetic, k)
+        assert ha.shape[1] == 4
+        if arithmetic == abi.ARITH_STRICT:
+            assert np.array_equal(ha, hb)
+
+
 def test_device_built_ensemble_equals_host_recipe(E):
     """pb200_ensemble_create_perturbed builds the members on the device: initial state bit-identical to
     the host statement of the same SplitMix64 recipe, and the same trajectories afterwards; get_case gives a member's image."""
