@@ -336,16 +336,20 @@ def test_maximum_size_system_ten_bodies(E, arithmetic):
             assert rel_err(g[k], o[k]) < (TOL_1E3 if arithmetic == 0 else 1e-13), (k, rel_err(g[k], o[k]))
 
 
-def test_full_size_ensemble_properties(E):
-    """BASELINE size (65536 TRAPPIST-1 systems): size-independent properties instead of an oracle run.
-    (1) replicas of one case stay bit-identical to each other and to a 1-system run (no cross-talk between groups/warps);
+@pytest.mark.parametrize("name,n_sys", [("c4_trappist1", 65536), ("c1_example", 65536), ("c2_case3", 4096), ("c3_case7", 16384),
+                                        ("c3_case7_evolving", 16384), ("c5_circumbinary", 65536)])
+def test_full_size_ensemble_properties(E, name, n_sys):
+    """Every BASELINE configuration at its BASELINE ensemble size: size-independent properties instead of an oracle run.
+    (1) replicas of one case stay bit-identical to each other and to a 1-system run (no cross-talk between groups/warps;
+        the 1-system run takes another CTA size and, for config 5, the two-lane instead of the passive-planet build);
     (2) two launches of n steps equal one launch of 2n steps (state round-trips through HBM exactly);
     (3) the reference's (heliocentric, hence only approximately conserved) energy and angular momentum diagnostics of
-        every member of a perturbed ensemble stay inside the symplectic oscillation band over 2000 steps (no drift, no NaN)."""
+        every member of a perturbed ensemble stay finite and inside the symplectic oscillation band over 2000 steps (no
+        drift, no NaN, no status or warning word); the band is asserted for TRAPPIST-1, where it was measured."""
     from posidonius_b200.case import case_from_dict
     from posidonius_b200.perturb import make_ensemble_cases
-    case, tables = case_from_dict(config_case("c4_trappist1"))
-    with E.Ensemble(case, tables, n_systems=65536) as big, E.Ensemble(case, tables, n_systems=1) as one:
+    case, tables = case_from_dict(config_case(name))
+    with E.Ensemble(case, tables, n_systems=n_sys) as big, E.Ensemble(case, tables, n_systems=1) as one:
         for ens in (big, one):
             ens.initialize_physical_values()
         big.iterate(300)
@@ -356,7 +360,7 @@ def test_full_size_ensemble_properties(E):
         for k in a:
             assert np.all(a[k] == a[k][..., :1]), k           # all replicas identical
             assert np.array_equal(a[k][..., 0], b[k][..., 0]), k  # and equal to the single-system run in one launch
-    cases = make_ensemble_cases(case, 65536, 20261021)
+    cases = make_ensemble_cases(case, n_sys, 20261021)
     with E.Ensemble(cases, tables) as ens:
         ens.initialize_physical_values()
         e0, l0 = ens.summary()
@@ -365,8 +369,11 @@ def test_full_size_ensemble_properties(E):
         st, w, _ = ens.status()
         assert np.all(st == 0) and np.all(w == 0)
         assert np.all(np.isfinite(e1)) and np.all(np.isfinite(l1))
-        assert np.max(np.abs((e1 - e0) / e0)) < 1e-3
-        assert np.max(np.abs((l1 - l0) / l0)) < 1e-4
+        if name == "c4_trappist1":
+            assert np.max(np.abs((e1 - e0) / e0)) < 1e-3
+            assert np.max(np.abs((l1 - l0) / l0)) < 1e-4
+        else:
+            assert np.max(np.abs((e1 - e0) / e0)) < 0.1 and np.max(np.abs((l1 - l0) / l0)) < 0.1
 
 
 # ---- stellar wind (wind.rs) and dynamical tides (constant_time_lag.rs:20-165): solar-like fixtures of the reference
