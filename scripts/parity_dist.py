@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Distribution of the GPU-vs-oracle relative error after N steps, per configuration and arithmetic mode.
 
-    python scripts/parity_dist.py [--members 1024] [--steps 10000] [--modes hybrid,fast]
+    python scripts/parity_dist.py [--members 1024] [--steps 10000] [--modes hybrid,fast] [--configs c5_circumbinary,...]
 
 Per member: max over bodies of |x_gpu - x_oracle| / |x_oracle| (vector norms; the 1e-10 criterion of BASELINE.json).
 Prints median / 99th percentile / max over the members for r, v, spin, and the fraction of members bit-identical in r and v.
@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--members", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=10000)
     ap.add_argument("--modes", default="hybrid,fast")
+    ap.add_argument("--configs", default="", help="comma-separated subset of the configuration names")
     args = ap.parse_args()
     from oracle.binding import run_ensemble
     from posidonius_b200 import abi
@@ -42,6 +43,8 @@ def main():
     modes = {"fast": abi.ARITH_FAST, "strict": abi.ARITH_STRICT, "hybrid": abi.ARITH_HYBRID}
     print("members %d  steps %d  (per member: max over bodies of the relative error; median / p99 / max over members)" % (args.members, args.steps))
     for idx, name in enumerate(CONFIG_NAMES):
+        if args.configs and name not in args.configs.split(","):
+            continue
         case, tables = case_from_dict(config_case(name))
         cases = make_ensemble_cases(case, args.members, 20261017 + idx)
         t0 = time.time()
