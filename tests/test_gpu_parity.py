@@ -522,7 +522,8 @@ def test_small_system_specialisations_match_generic_kernel(E, monkeypatch, name)
 def test_passive_planet_build_equals_two_lane_build(E, monkeypatch):
     """Config 5 (Jacobi, the circumbinary planet an OrbitingBody of no effect) on an ensemble large enough for the one-thread-
     per-system build (small_step.cuh, PASSIVE) against the two-lanes-per-system build (PB200_PAIR_LANES=1) and the oracle:
-    strict mode bit for bit in every array, hybrid mode bit for bit in r and v; historic records equal."""
+    strict mode bit for bit in every array, hybrid mode bit for bit in r and v; historic records equal (the passive-planet
+    run cut into three time slices, with snapshots inside the slices)."""
     from oracle.binding import run_ensemble
     from posidonius_b200 import abi
     from posidonius_b200.case import case_from_dict
@@ -542,6 +543,7 @@ def test_passive_planet_build_equals_two_lane_build(E, monkeypatch):
         out = []
         for flag in ("0", "1"):
             monkeypatch.setenv("PB200_PAIR_LANES", flag)
+            monkeypatch.setenv("PB200_PIECES", "3" if flag == "0" else "1")   # the passive-planet build time-sliced as well
             with E.Ensemble(cases, tables, arithmetic=arithmetic) as ens:
                 ens.initialize_physical_values()
                 ens.iterate(steps)
