@@ -206,11 +206,12 @@ def other_workloads(device, fp64_peak, arithmetic, skip):
                 ens.initialize_physical_values()
                 ms = time_launches(ens, 1000, 2)
                 st, _, _ = ens.status()
+                build = ens.last_kernel()
             rate = n_sys * 1000 / (ms * 1e-3)
             out["%s_x%d" % (name, n_sys)] = {
                 "value": rate, "bodies": case.n_particles, "systems": n_sys, "flops_per_system_step": flops,
                 "tflops": rate * flops / 1e12, "frac": rate * flops / fp64_peak if fp64_peak else None,
-                "systems_alive": int((st == 0).sum())}
+                "systems_alive": int((st == 0).sum()), "kernel_build": build}
     return out
 
 
@@ -325,6 +326,7 @@ def main():
     wall = time.perf_counter() - t0
     launches = ens.launch_count() - launches0
     pieces = ens.last_pieces()
+    kernel_name = ens.last_kernel()
     hist_timed = hist_bytes[0]
     clocks = sampler.summary()
     st, warn, _ = ens.status()
@@ -379,7 +381,7 @@ def main():
                         "general_relativity": bool(case.consider_general_relativity), "evolution": bool(case.consider_evolution)},
             "coordinates": ["Jacobi", "DemocraticHeliocentric", "WHDS"][case.coordinates_type],
             "parallelism": "one global ensemble sharded by contiguous ranges over %d GPU(s), no collective on the hot path" % world,
-            "time_slices_per_launch": int(pieces),
+            "time_slices_per_launch": int(pieces), "kernel_build": kernel_name,
             "l2": ("inputs larger than L2: %.0f MB of state per GPU; it crosses HBM once per time slice and stays in registers / "
                    "shared memory in between" % (io_bytes / 1e6)) if io_bytes > 126e6 / 2 else
                   ("state %.0f MB per GPU; the kernel keeps it in registers / shared memory for all the steps of a launch and "

@@ -275,6 +275,11 @@ int pb200_ensemble_last_step_ms(pb200_ensemble_t* e, float* ms);
 uint64_t pb200_ensemble_launch_count(const pb200_ensemble_t* e);
 /* Time slices of the last step launch (1 = every block of systems ran its steps in one piece). */
 unsigned pb200_ensemble_last_pieces(const pb200_ensemble_t* e);
+/* Name of the step-kernel build that ran the last pb200_ensemble_step ("" before the first one): "generic" (lane = body, any
+ * geometry), "n8" / "n8w" (8 bodies, 64- / 384-thread CTAs), "s2", "s2t", "s3", "s3e", "s3j", "s3p" (lane = planet, compile-time
+ * effect sets), "s2any", "s3any", "s3jany" (lane = planet, effect set read at run time). Diagnostics: every build computes the
+ * same step. The string is static storage. */
+const char* pb200_ensemble_last_kernel(const pb200_ensemble_t* e);
 
 /* Per-system status (PB200_STATUS_*), warning bits and the iteration index of the event. */
 int pb200_ensemble_status(pb200_ensemble_t* e, int32_t* status, uint32_t* warnings,

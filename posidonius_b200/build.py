@@ -34,6 +34,9 @@ UNITS = [  # "k_s*": the lane = planet kernel of the 2- and 3-body configuration
     ("k_s3e", "kernels_small_tu.cu", ["PB_TU_SMALL=30"]),
     ("k_s3j", "kernels_small_tu.cu", ["PB_TU_SMALL=31"]),
     ("k_s3p", "kernels_small_tu.cu", ["PB_TU_SMALL=32"]),
+    ("k_s2any", "kernels_small_tu.cu", ["PB_TU_SMALL=29"]),
+    ("k_s3any", "kernels_small_tu.cu", ["PB_TU_SMALL=39"]),
+    ("k_s3jany", "kernels_small_tu.cu", ["PB_TU_SMALL=38"]),
 ]
 
 

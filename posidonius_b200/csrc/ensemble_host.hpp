@@ -43,6 +43,7 @@ struct pb200_ensemble {
     double clock_t = 0., clock_last_hist = -1.;
     size_t hist_pending_host = 0;
     unsigned last_pieces = 1;     // time slices of the last step launch (diagnostics)
+    const char* last_kernel = "";  // build that ran the last step launch (diagnostics)
 };
 
 // Wave quantisation: `grid` CTAs of equal length on `slots` resident CTAs leave the last wave partly empty (65536
@@ -105,4 +106,7 @@ cudaError_t pb200_launch_s2t(pb200_ensemble* e, unsigned long long n);   // 2 bo
 cudaError_t pb200_launch_s3(pb200_ensemble* e, unsigned long long n);    // 3 bodies, DH, tides + flattening + Kidder          (config 3)
 cudaError_t pb200_launch_s3e(pb200_ensemble* e, unsigned long long n);   // 3 bodies, DH, the same + evolution                 (config 3 evolving)
 cudaError_t pb200_launch_s3j(pb200_ensemble* e, unsigned long long n);   // 3 bodies, Jacobi, the same + evolution
+cudaError_t pb200_launch_s2any(pb200_ensemble* e, unsigned long long n);   // 2 bodies, DH, any subset of tides / flattening / Kidder / evolution (run-time flags)
+cudaError_t pb200_launch_s3any(pb200_ensemble* e, unsigned long long n);   // 3 bodies, DH, the same
+cudaError_t pb200_launch_s3jany(pb200_ensemble* e, unsigned long long n);  // 3 bodies, Jacobi, the same
 cudaError_t pb200_launch_s3p(pb200_ensemble* e, unsigned long long n);   // the same with body 2 outside every effect: thread = system (config 5)

@@ -6,6 +6,8 @@
 //   30  3 bodies, democratic heliocentric, the same + evolution tables                     (config 3 evolving)
 //   31  3 bodies, Jacobi, the same + evolution tables, two lanes per system
 //   32  the same with body 2 outside every effect: one thread per system                   (config 5)
+//   29 / 39 / 38   catch-all builds (2 bodies DH / 3 bodies DH / 3 bodies Jacobi): every effect compiled in, the ensemble's
+//       flag word selects at run time — any subset of tides, flattening, GR Kidder1995, evolution tables
 #if PB_TU_SMALL == 2
 #define PB_NS pbs2
 #define PB_S_N 2
@@ -36,6 +38,24 @@
 #define PB_S_COORD PB200_COORD_JACOBI
 #define PB_S_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR | pb200::FLAG_EVO)
 #define PB_S_ENTRY pb200_launch_s3j
+#elif PB_TU_SMALL == 29
+#define PB_NS pbs2any
+#define PB_S_N 2
+#define PB_S_COORD PB200_COORD_DEMOCRATIC_HELIOCENTRIC
+#define PB_S_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR | pb200::FLAG_EVO | PB_NS::SMALL_RT)
+#define PB_S_ENTRY pb200_launch_s2any
+#elif PB_TU_SMALL == 39
+#define PB_NS pbs3any
+#define PB_S_N 3
+#define PB_S_COORD PB200_COORD_DEMOCRATIC_HELIOCENTRIC
+#define PB_S_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR | pb200::FLAG_EVO | PB_NS::SMALL_RT)
+#define PB_S_ENTRY pb200_launch_s3any
+#elif PB_TU_SMALL == 38
+#define PB_NS pbs3jany
+#define PB_S_N 3
+#define PB_S_COORD PB200_COORD_JACOBI
+#define PB_S_FLAGS (pb200::FLAG_TIDES | pb200::FLAG_FLAT | pb200::FLAG_GR | pb200::FLAG_EVO | PB_NS::SMALL_RT)
+#define PB_S_ENTRY pb200_launch_s3jany
 #elif PB_TU_SMALL == 32
 #define PB_NS pbs3p
 #define PB_S_N 3
@@ -44,7 +64,7 @@
 #define PB_S_PASSIVE true
 #define PB_S_ENTRY pb200_launch_s3p
 #else
-#error "kernels_small_tu.cu: define PB_TU_SMALL=<2|20|3|30|31|32>"
+#error "kernels_small_tu.cu: define PB_TU_SMALL=<2|20|3|30|31|32|29|39|38>"
 #endif
 #ifndef PB_S_PASSIVE
 #define PB_S_PASSIVE false

@@ -725,26 +725,33 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
         // compile-time geometry builds (kernels_tu.cu): host at index 0 and one of the effect sets of the BASELINE configurations
         const bool fixed_ok = e->P.host == 0 && !e->force_generic;
         const bool dh = e->coord == PB200_COORD_DEMOCRATIC_HELIOCENTRIC, kidder = e->gr == PB200_GR_KIDDER1995;
-        const int tfg = FLAG_TIDES | FLAG_FLAT | FLAG_GR;
+        const int tfg = FLAG_TIDES | FLAG_FLAT | FLAG_GR, flags = e->P.flags;
+        const bool small_ok = fixed_ok && e->P.spin_on && (flags & ~(tfg | FLAG_EVO)) == 0 && (!(flags & FLAG_GR) || kidder);
         // 8 bodies: 384-thread CTAs once there is at least one of them per SM (below that the 64-thread build spreads the work over more SMs)
         if (fixed_ok && e->n_bodies == 8 && dh && kidder && e->P.flags == tfg)
             // (the all-exact arithmetic gains nothing from them: 2.36e8 against 2.49e8 system-steps/s)
             err = (threads >= (size_t)384 * (size_t)e->sm_count && !e->narrow_blocks && e->arithmetic != PB200_ARITH_STRICT)
-                      ? pb200_launch_n8w(e, threads, n_steps) : pb200_launch_n8(e, threads, n_steps);
-        // 2 and 3 bodies (BASELINE configs 1, 2, 3, 3-evolving, 5): lane = planet (small_step.cuh); PB200_FORCE_GENERIC=1 gives the lane = body kernel
-        else if (fixed_ok && e->P.spin_on && e->n_bodies == 2 && dh && kidder && e->P.flags == tfg) err = pb200_launch_s2(e, n_steps);
-        else if (fixed_ok && e->P.spin_on && e->n_bodies == 2 && dh && e->gr == PB200_GR_DISABLED && e->P.flags == FLAG_TIDES) err = pb200_launch_s2t(e, n_steps);
-        else if (fixed_ok && e->P.spin_on && e->n_bodies == 3 && dh && kidder && e->P.flags == tfg) err = pb200_launch_s3(e, n_steps);
-        else if (fixed_ok && e->P.spin_on && e->n_bodies == 3 && dh && kidder && e->P.flags == (tfg | FLAG_EVO)) err = pb200_launch_s3e(e, n_steps);
-        else if (fixed_ok && e->P.spin_on && e->n_bodies == 3 && e->coord == PB200_COORD_JACOBI && kidder && e->P.flags == (tfg | FLAG_EVO))
-            // body 2 an OrbitingBody of no effect (the circumbinary planet): it rides in body 1's thread once the ensemble fills the
-            // GPU that way (six warps per SM); a smaller ensemble keeps two lanes per system (twice the warps: 8192 members 4.4e8 vs 4.2e8)
-            err = (((e->P.tides_orbiting | e->P.flat_orbiting | e->P.gr_orbiting) >> 2) & 1u) == 0 && !e->pair_lanes &&
-                          4 * e->n_sys >= 3 * (size_t)192 * (size_t)e->sm_count
-                      ? pb200_launch_s3p(e, n_steps) : pb200_launch_s3j(e, n_steps);
-        else if (e->arithmetic == PB200_ARITH_FAST) err = pb200_launch_generic_fast(e, threads, n_steps);
-        else if (e->arithmetic == PB200_ARITH_STRICT) err = pb200_launch_generic_strict(e, threads, n_steps);
-        else err = pb200_launch_generic_hybrid(e, threads, n_steps);
+                      ? (e->last_kernel = "n8w", pb200_launch_n8w(e, threads, n_steps)) : (e->last_kernel = "n8", pb200_launch_n8(e, threads, n_steps));
+        // 2 and 3 bodies: lane = planet (small_step.cuh) — host 0, democratic heliocentric (or Jacobi with 3 bodies), spin
+        // integrated, any subset of tides / flattening / GR Kidder1995 / evolution tables, no wind, no dynamical tides. The BASELINE
+        // configurations (1, 2, 3, 3-evolving, 5) have compile-time effect sets; every other subset takes the catch-all build of
+        // its geometry (flag word read at run time). PB200_FORCE_GENERIC=1 gives the lane = body kernel.
+        else if (small_ok && e->n_bodies == 2 && dh)
+            err = flags == tfg ? (e->last_kernel = "s2", pb200_launch_s2(e, n_steps)) : flags == FLAG_TIDES ? (e->last_kernel = "s2t", pb200_launch_s2t(e, n_steps)) : (e->last_kernel = "s2any", pb200_launch_s2any(e, n_steps));
+        else if (small_ok && e->n_bodies == 3 && dh)
+            err = flags == tfg ? (e->last_kernel = "s3", pb200_launch_s3(e, n_steps)) : flags == (tfg | FLAG_EVO) ? (e->last_kernel = "s3e", pb200_launch_s3e(e, n_steps)) : (e->last_kernel = "s3any", pb200_launch_s3any(e, n_steps));
+        else if (small_ok && e->n_bodies == 3 && e->coord == PB200_COORD_JACOBI) {
+            if (flags != (tfg | FLAG_EVO)) err = (e->last_kernel = "s3jany", pb200_launch_s3jany(e, n_steps));
+            else
+                // body 2 an OrbitingBody of no effect (the circumbinary planet): it rides in body 1's thread once the ensemble fills the
+                // GPU that way (six warps per SM); a smaller ensemble keeps two lanes per system (twice the warps: 8192 members 4.4e8 vs 4.2e8)
+                err = (((e->P.tides_orbiting | e->P.flat_orbiting | e->P.gr_orbiting) >> 2) & 1u) == 0 && !e->pair_lanes &&
+                              4 * e->n_sys >= 3 * (size_t)192 * (size_t)e->sm_count
+                          ? (e->last_kernel = "s3p", pb200_launch_s3p(e, n_steps)) : (e->last_kernel = "s3j", pb200_launch_s3j(e, n_steps));
+        }
+        else if (e->arithmetic == PB200_ARITH_FAST) err = (e->last_kernel = "generic", pb200_launch_generic_fast(e, threads, n_steps));
+        else if (e->arithmetic == PB200_ARITH_STRICT) err = (e->last_kernel = "generic", pb200_launch_generic_strict(e, threads, n_steps));
+        else err = (e->last_kernel = "generic", pb200_launch_generic_hybrid(e, threads, n_steps));
         e->launches++;
         if (err != cudaSuccess) return set_error(PB200_E_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(err));
     }
@@ -774,6 +781,7 @@ int pb200_ensemble_last_step_ms(pb200_ensemble_t* e, float* ms) {
 
 uint64_t pb200_ensemble_launch_count(const pb200_ensemble_t* e) { return e ? e->launches : 0; }
 unsigned pb200_ensemble_last_pieces(const pb200_ensemble_t* e) { return e ? e->last_pieces : 0; }
+const char* pb200_ensemble_last_kernel(const pb200_ensemble_t* e) { return e ? e->last_kernel : ""; }
 size_t pb200_ensemble_history_capacity(const pb200_ensemble_t* e) { return e ? (size_t)e->P.hist_capacity : 0; }
 
 int pb200_ensemble_status(pb200_ensemble_t* e, int32_t* status, uint32_t* warnings, uint64_t* iteration_of_event) {

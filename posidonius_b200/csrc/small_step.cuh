@@ -84,6 +84,11 @@ __device__ __forceinline__ double sel(bool c, double a, double b) { return c ? a
 __device__ __forceinline__ S3 sel(bool c, S3 a, S3 b) { return s3(sd(sel(c, a.x.v, b.x.v)), sd(sel(c, a.y.v, b.y.v)), sd(sel(c, a.z.v, b.z.v))); }
 __device__ __forceinline__ V3 sel(bool c, V3 a, V3 b) { return v3(sel(c, a.x, b.x), sel(c, a.y, b.y), sel(c, a.z, b.z)); }
 
+// Effect set: FLAGS names what is compiled in; with SMALL_RT set the ensemble's own flag word selects among it at run time
+// (uniform branches) — the catch-all builds for effect sets that have no compile-time build of their own.
+enum : int { SMALL_RT = 1 << 10 };
+template <int FLAGS> __device__ __forceinline__ bool has(const KParams& P, int f) { return (FLAGS & f) && (!(FLAGS & SMALL_RT) || (P.flags & f)); }
+
 struct SmallState {
     S3 r, v, r0, v0;        // inertial position / velocity of the planet and of the host
     V3 L, s, L0, s0;        // angular momentum and spin (of the previous evaluation)
@@ -191,7 +196,7 @@ __device__ __forceinline__ void small_effects_fast(const KParams& P, const Sl& s
     double Kr = 0., Kv = 0., Pcp = 0., Hcs = 0.;
     V3 F = v3(0., 0., 0.);
     dl_p = v3(0., 0., 0.); dl_h = v3(0., 0., 0.);
-    if (FLAGS & FLAG_TIDES) {
+    if (has<FLAGS>(P, FLAG_TIDES)) {
         const double inv_d6 = inv_d4 * inv_d2, inv_d7 = inv_d6 * inv_d;
         const double FodS = sl.get(C_AS) * inv_d6, FodP = sl.get(C_AP) * inv_d6;
         const double Fos = FodS * inv_d, Fop = FodP * inv_d;
@@ -214,7 +219,7 @@ __device__ __forceinline__ void small_effects_fast(const KParams& P, const Sl& s
             ts[10 * cs_] = dl_p.x; ts[11 * cs_] = dl_p.y; ts[12 * cs_] = dl_p.z;
         }
     }
-    if (FLAGS & FLAG_FLAT) {
+    if (has<FLAGS>(P, FLAG_FLAT)) {
         const double inv_d5 = inv_d4 * inv_d;
         const double k_s = sl.get(C_KS), k_p = sl.get(C_KP);
         const double KsRs = k_s * rs_s, KpRp = k_p * rs_p;
@@ -225,7 +230,7 @@ __device__ __forceinline__ void small_effects_fast(const KParams& P, const Sl& s
         F = v3(F.x + Fop * q.s.x + Fos * sh.x, F.y + Fop * q.s.y + Fos * sh.y, F.z + Fop * q.s.z + Fos * sh.z);
         Pcp = -Fop; Hcs = -Fos;
     }
-    if (FLAGS & FLAG_GR) {
+    if (has<FLAGS>(P, FLAG_GR)) {
         const double v2 = dot(hv, hv);
         const double mgs = sl.get(C_MGS);
         const double A = mgs * inv_d2 * kInvC2;
@@ -306,7 +311,7 @@ __device__ __forceinline__ void small_effects_exact(const KParams& P, const Sl& 
     const sd neg_inv_M = sd(-1.0) * inv_M;
     S3 a = zero3, ah = zero3;
     S3 td = zero3, fd = zero3, gd = zero3, tdh = zero3, fdh = zero3, gdh = zero3;
-    if (FLAGS & FLAG_TIDES) {
+    if (has<FLAGS>(P, FLAG_TIDES)) {
         const sd cs = sd(sl.get(C_AS)), cp = sd(sl.get(C_AP));
         const sd t1 = sd(sl.get(X_T1)), t2 = sd(sl.get(X_T2)), host_k = sd(sl.get(X_HOSTK));
         const sd d8 = d4 * d4;
@@ -353,7 +358,7 @@ __device__ __forceinline__ void small_effects_exact(const KParams& P, const Sl& 
         a = a + t_acc; td = t_dl;
         ah = ah + s3(neg_inv_M * sF.x, neg_inv_M * sF.y, neg_inv_M * sF.z); tdh = sN;
     }
-    if (FLAGS & FLAG_FLAT) {
+    if (has<FLAGS>(P, FLAG_FLAT)) {
         const sd Rh5 = sd(sl.get(H_R5)), R5 = sd(sl.get(K_R5));
         const sd fs0 = sd(sl.get(X_FS0)), fp0 = sd(sl.get(X_FP0));
         const srcp r6 = make_rcp(sd(6.));
@@ -381,7 +386,7 @@ __device__ __forceinline__ void small_effects_exact(const KParams& P, const Sl& 
         a = a + f_acc; fd = f_dl;
         ah = ah + s3(neg_inv_M * sF.x, neg_inv_M * sF.y, neg_inv_M * sF.z); fdh = sN;
     }
-    if (FLAGS & FLAG_GR) {
+    if (has<FLAGS>(P, FLAG_GR)) {
         // general_relativity.rs:177-456 (Kidder1995)
         const sd c2 = sd(kC2);
         const sd mgs = sd(sl.get(C_MGS));
@@ -528,7 +533,9 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
     const bool first = b == 1;
     const size_t sys_raw = W == 2 ? (gtid >> 1) : gtid;
     const bool sys_ok = sys_raw < (size_t)P.n_sys;
-    const size_t sys = sys_ok ? sys_raw : 0;   // padding lanes shadow system 0 (they never store)
+    // padding lanes shadow the LAST system, which this same CTA owns: its loads (kernel start) precede its stores (kernel end /
+    // piece hand-over), so no lane ever reads state that another CTA is writing; padding lanes never store
+    const size_t sys = sys_ok ? sys_raw : (size_t)P.n_sys - 1;
     const bool valid = sys_ok;
     const bool writer = valid && first;  // the lane that stores the host body and the per-system words
     SmallRoles ro;
@@ -647,7 +654,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
             const bool due = __dadd_rn(st.last_hist, P.hist_period) <= st.t;
             const bool snap = alive && (first_snap || due);
             if (__any_sync(FULL, snap)) {
-                if (FLAGS & FLAG_EVO) evolve_all(st.t, snap);
+                if (has<FLAGS>(P, FLAG_EVO)) evolve_all(st.t, snap);
                 if (snap) {
                     // spin = L / I (universe.rs:305-316, common.rs:9-11): it changes the live state too
                     q.s = plain(strict(q.L) / sd(sl.get(K_I)));
@@ -667,7 +674,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
                         h[16 * cs] = 0.;
                     };
                     double denergy = 0.;
-                    if ((FLAGS & FLAG_TIDES) && ro.t_on) {
+                    if (has<FLAGS>(P, FLAG_TIDES) && ro.t_on) {
                         // tides/common.rs:263-279 with the internals left by the last evaluation and the fresh spin
                         const size_t i = (size_t)b * ns + sys;
                         double ts[PB_TIDE_SCRATCH];
@@ -921,7 +928,7 @@ __global__ void __launch_bounds__(BLK, 256 / BLK) small_steps_kernel(const __gri
 #pragma unroll 1
                 for (int it = 0; it < 10; it++) {
                     if (!__any_sync(FULL, !done)) break;
-                    if ((FLAGS & FLAG_EVO) && evolution && it == 0) evolve_all(st.t, alive);
+                    if (has<FLAGS>(P, FLAG_EVO) && evolution && it == 0) evolve_all(st.t, alive);
                     // calculate_spin of body 2 (every evaluation refreshes every particle's spin, common.rs:3-15): L_2 never
                     // changes, so once per midpoint, after the inertia may have evolved
                     if (PASSIVE && it == 0 && !done) sl.set3(K2_S, plain(strict(sl.get3(K2_L)) / sd(sl.get(K2_I))));

@@ -135,6 +135,10 @@ class Ensemble:
     def last_pieces(self):
         return lib().pb200_ensemble_last_pieces(self._h)
 
+    def last_kernel(self):
+        """Name of the step-kernel build that ran the last iterate() (diagnostics; include/posidonius_b200.h)."""
+        return lib().pb200_ensemble_last_kernel(self._h).decode()
+
     def history_capacity(self):
         return lib().pb200_ensemble_history_capacity(self._h)
 

@@ -514,9 +514,50 @@ def test_small_system_specialisations_match_generic_kernel(E, monkeypatch, name)
             out.append(gpu_state_of(ens))
             st, _, _ = ens.status()
             assert (st == 0).all() and ens.get_case(332).current_iteration == 300
+            assert ens.last_kernel() == ("generic" if flag == "1" else {"c1_example": "s2", "c2_case3": "s2t", "c3_case7": "s3",
+                                                                        "c3_case7_evolving": "s3e", "c5_circumbinary": "s3j"}[name])
     a, b = out
     for key in ("position", "velocity", "spin", "angular_momentum"):
         assert rel_err(a[key], b[key]) < 1e-13, key
+
+
+@pytest.mark.parametrize("name,off", [("c1_example", ("general_relativity",)), ("c1_example", ("rotational_flattening",)),
+                                      ("c3_case7", ("tides",)), ("c3_case7_evolving", ("rotational_flattening",)),
+                                      ("c3_case7_evolving", ("general_relativity", "rotational_flattening")),
+                                      ("c5_circumbinary", ("general_relativity",)), ("c5_circumbinary", ("tides", "evolution"))])
+def test_catch_all_small_builds_match_generic_kernel_and_oracle(E, monkeypatch, name, off):
+    """Effect sets without a compile-time build of their own (any subset of tides / flattening / GR Kidder1995 / evolution on a
+    2- or 3-body system) take the catch-all lane = planet builds, which read the flag word at run time: strict mode bit for
+    bit equal to the run-time-geometry kernel and to the oracle, hybrid mode within 1e-13 of the run-time-geometry kernel."""
+    from oracle.binding import run_ensemble
+    from posidonius_b200 import abi
+    from posidonius_b200.case import case_from_dict
+    from posidonius_b200.perturb import make_ensemble_cases
+    d = config_case(name)
+    for effect in off:
+        d["universe"]["consider_effects"][effect] = False
+    case, tables = case_from_dict(d)
+    n_sys, steps = 150, 250
+    cases = make_ensemble_cases(case, n_sys, 17)
+    oc, ost, _ = run_ensemble(cases, n_sys, tables, steps, True, os.cpu_count() or 1)
+    o = oracle_state_of(oc)
+    for arithmetic in (abi.ARITH_STRICT, abi.ARITH_HYBRID):
+        out = []
+        for flag in ("0", "1"):
+            monkeypatch.setenv("PB200_FORCE_GENERIC", flag)
+            with E.Ensemble(cases, tables, arithmetic=arithmetic) as ens:
+                ens.initialize_physical_values()
+                ens.iterate(steps)
+                out.append(gpu_state_of(ens))
+                st, _, _ = ens.status()
+                assert np.array_equal(st, ost)
+                assert ens.last_kernel() == ("generic" if flag == "1" else {2: "s2any", 3: "s3jany" if name.startswith("c5") else "s3any"}[case.n_particles])
+        a, b = out
+        for key in ("position", "velocity", "spin", "angular_momentum"):
+            if arithmetic == abi.ARITH_STRICT:
+                assert np.array_equal(a[key], b[key]) and np.array_equal(a[key], o[key]), (name, off, key)
+            else:
+                assert rel_err(a[key], b[key]) < 1e-13, (name, off, key)
 
 
 def test_passive_planet_build_equals_two_lane_build(E, monkeypatch):
@@ -548,6 +589,7 @@ def test_passive_planet_build_equals_two_lane_build(E, monkeypatch):
                 ens.initialize_physical_values()
                 ens.iterate(steps)
                 out.append((gpu_state_of(ens), ens.history_drain(), ens.status()[0]))
+                assert ens.last_kernel() == ("s3p" if flag == "0" else "s3j")
         (a, ha, sa), (b, hb, sb) = out
         assert np.array_equal(sa, sb) and (sa == 0).all()
         keys = a.keys() if arithmetic == abi.ARITH_STRICT else ("position", "velocity", "acceleration", "current_time")
