@@ -1,4 +1,5 @@
-// small_step.cuh — the step kernel for 2- and 3-body systems (BASELINE configs 1, 2, 3, 3-evolving, 5): lane = PLANET.
+// small_step.cuh — the step kernel for 2- and 3-body systems (BASELINE configs 1, 2, 3, 3-evolving, 5 and every other effect
+// subset on such systems): lane = PLANET.
 //
 // The lane = body mapping of whfast_step.cuh leaves the host lane (and the padding lane of a 3-body system) without work in
 // the force evaluations and in the Kepler drift: 1 of 2 lanes (N = 2) or 2 of 4 lanes (N = 3) do the arithmetic, and every
@@ -17,8 +18,11 @@
 // particles/universe.rs:428-614, effects/tides/{common,constant_time_lag}.rs, effects/rotational_flattening/{common,
 // oblate_spheroid}.rs, effects/general_relativity.rs:177-456, effects/evolution.rs:449-546.
 //
-// Compile-time: N (2 | 3), coordinates (democratic heliocentric | Jacobi), effect set (FLAG_* mask; GR = Kidder1995),
-// arithmetic mode. Host at index 0, spin integrated (every effect set of the BASELINE configurations has tides).
+// Compile-time: N (2 | 3), coordinates (democratic heliocentric | Jacobi), effect set (FLAG_* mask; GR = Kidder1995; with
+// SMALL_RT the ensemble's flag word selects among the compiled-in effects at run time), arithmetic mode, CTA size, and the
+// passive-planet mapping (3 bodies, Jacobi, body 2 outside every effect: one thread per system). Host at index 0, spin
+// integrated (at least one effect enabled). The force formulas are the ones of forces_fast.cuh / exact_effects.cuh with the
+// host's quantities and the per-planet products held by the lane itself instead of being read from the host's column.
 #include "whfast_kernel.cuh"
 
 namespace PB_NS {
