@@ -280,6 +280,9 @@ unsigned pb200_ensemble_last_pieces(const pb200_ensemble_t* e);
  * effect sets), "s2any", "s3any", "s3jany" (lane = planet, effect set read at run time). Diagnostics: every build computes the
  * same step. The string is static storage. */
 const char* pb200_ensemble_last_kernel(const pb200_ensemble_t* e);
+/* The same name for a case that has not been uploaded: which build would integrate an ensemble of n_systems copies /
+ * perturbed members of `c` on a GPU with sm_count SMs in the given arithmetic. Needs no device. "" for a null / malformed case. */
+const char* pb200_case_step_kernel(const pb200_case_t* c, size_t n_systems, int sm_count, int arithmetic);
 
 /* Per-system status (PB200_STATUS_*), warning bits and the iteration index of the event. */
 int pb200_ensemble_status(pb200_ensemble_t* e, int32_t* status, uint32_t* warnings,

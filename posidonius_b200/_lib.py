@@ -41,6 +41,7 @@ _SIGNATURES = {
     "pb200_ensemble_launch_count": (C.c_uint64, [C.c_void_p]),
     "pb200_ensemble_last_pieces": (C.c_uint, [C.c_void_p]),
     "pb200_ensemble_last_kernel": (C.c_char_p, [C.c_void_p]),
+    "pb200_case_step_kernel": (C.c_char_p, [C.POINTER(abi.Case), C.c_size_t, C.c_int, C.c_int]),
     "pb200_ensemble_history_capacity": (C.c_size_t, [C.c_void_p]),
     "pb200_ensemble_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "pb200_ensemble_download": (C.c_int, [C.c_void_p, C.POINTER(abi.StateView)]),

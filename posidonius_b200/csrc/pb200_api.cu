@@ -386,6 +386,42 @@ void pb200_ensemble_destroy(pb200_ensemble_t* e) {
     delete e;
 }
 
+// Everything of KParams that is uniform across the ensemble and known from the case alone (no device involved): geometry,
+// effect flags, per-body role masks. Shared by pb200_ensemble_create and pb200_case_step_kernel.
+static void fill_uniform_params(KParams& P, const pb200_case_t& c0, size_t n_systems) {
+    const int n = c0.n_particles;
+    P.n_sys = (int)n_systems; P.n_bodies = n;
+    int W = 2; while (W < n) W <<= 1;
+    P.W = W; P.shift = 0; while ((1 << P.shift) < W) P.shift++;
+    P.host = c0.host_most_massive;
+    P.flags = (c0.consider_tides ? FLAG_TIDES : 0) | (c0.consider_rotational_flattening ? FLAG_FLAT : 0) |
+              (c0.consider_general_relativity ? FLAG_GR : 0) | (c0.consider_evolution ? FLAG_EVO : 0);
+    P.spin_on = c0.consider_tides || c0.consider_rotational_flattening || c0.consider_evolution ||
+                (c0.consider_general_relativity && c0.general_relativity_implementation == PB200_GR_KIDDER1995);
+    P.dt = c0.time_step; P.half_dt = c0.half_time_step; P.time_limit = c0.time_limit; P.hist_period = c0.historic_snapshot_period;
+    P.tides_orbiting = P.flat_orbiting = P.gr_orbiting = P.gr_enabled = 0;
+    for (int i = 0; i < n; i++) {
+        const pb200_body_t& b = c0.bodies[i];
+        if (b.tides_role == PB200_ROLE_ORBITING) P.tides_orbiting |= 1u << i;
+        if (b.flattening_role == PB200_ROLE_ORBITING) P.flat_orbiting |= 1u << i;
+        if (b.general_relativity_role == PB200_ROLE_ORBITING) P.gr_orbiting |= 1u << i;
+        if (b.general_relativity_role != PB200_ROLE_DISABLED) P.gr_enabled |= 1u << i;
+        P.evo_table[i] = (c0.consider_evolution && b.evolution_type != PB200_EVO_NONEVOLVING) ? b.evolution_table : -1;
+    }
+    for (int i = n; i < PB200_MAX_PARTICLES; i++) P.evo_table[i] = -1;
+    P.wind_on = P.dyn_evo = 0;
+    for (int i = 0; i < n; i++) {
+        const pb200_body_t& b = c0.bodies[i];
+        if (c0.consider_wind && b.wind_role == 0) P.wind_on |= 1u << i;
+        // the reference matches on Particle.evolution whatever consider_effects.evolution says (constant_time_lag.rs:27, 96)
+        if (c0.consider_tides && is_dynamical_tide_evolution(b) && (i == P.host || b.tides_role == PB200_ROLE_ORBITING)) P.dyn_evo |= 1u << i;
+    }
+    if (P.wind_on) P.flags |= FLAG_WIND;
+    if (P.dyn_evo) P.flags |= FLAG_DYN;
+    P.tides_host_central = c0.bodies[P.host].tides_role == PB200_ROLE_CENTRAL;
+    P.flat_host_central = c0.bodies[P.host].flattening_role == PB200_ROLE_CENTRAL;
+}
+
 int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_systems, const pb200_table_t* tables,
                           size_t n_tables, int device, pb200_ensemble_t** out) {
     if (!cases || !out || n_systems == 0) return set_error(PB200_E_INVALID, "null argument or empty ensemble");
@@ -421,36 +457,7 @@ int pb200_ensemble_create(const pb200_case_t* cases, size_t n_cases, size_t n_sy
     for (size_t s = 1; s < n_cases; s++)
         if (cases[s].current_time != c0.current_time || cases[s].last_historic_snapshot_time != c0.last_historic_snapshot_time) e->uniform_clock = false;
     KParams& P = e->P;
-    P.n_sys = (int)n_systems; P.n_bodies = n;
-    int W = 2; while (W < n) W <<= 1;
-    P.W = W; P.shift = 0; while ((1 << P.shift) < W) P.shift++;
-    P.host = c0.host_most_massive;
-    P.flags = (c0.consider_tides ? FLAG_TIDES : 0) | (c0.consider_rotational_flattening ? FLAG_FLAT : 0) |
-              (c0.consider_general_relativity ? FLAG_GR : 0) | (c0.consider_evolution ? FLAG_EVO : 0);
-    P.spin_on = c0.consider_tides || c0.consider_rotational_flattening || c0.consider_evolution ||
-                (c0.consider_general_relativity && c0.general_relativity_implementation == PB200_GR_KIDDER1995);
-    P.dt = c0.time_step; P.half_dt = c0.half_time_step; P.time_limit = c0.time_limit; P.hist_period = c0.historic_snapshot_period;
-    P.tides_orbiting = P.flat_orbiting = P.gr_orbiting = P.gr_enabled = 0;
-    for (int i = 0; i < n; i++) {
-        const pb200_body_t& b = c0.bodies[i];
-        if (b.tides_role == PB200_ROLE_ORBITING) P.tides_orbiting |= 1u << i;
-        if (b.flattening_role == PB200_ROLE_ORBITING) P.flat_orbiting |= 1u << i;
-        if (b.general_relativity_role == PB200_ROLE_ORBITING) P.gr_orbiting |= 1u << i;
-        if (b.general_relativity_role != PB200_ROLE_DISABLED) P.gr_enabled |= 1u << i;
-        P.evo_table[i] = (c0.consider_evolution && b.evolution_type != PB200_EVO_NONEVOLVING) ? b.evolution_table : -1;
-    }
-    for (int i = n; i < PB200_MAX_PARTICLES; i++) P.evo_table[i] = -1;
-    P.wind_on = P.dyn_evo = 0;
-    for (int i = 0; i < n; i++) {
-        const pb200_body_t& b = c0.bodies[i];
-        if (c0.consider_wind && b.wind_role == 0) P.wind_on |= 1u << i;
-        // the reference matches on Particle.evolution whatever consider_effects.evolution says (constant_time_lag.rs:27, 96)
-        if (c0.consider_tides && is_dynamical_tide_evolution(b) && (i == P.host || b.tides_role == PB200_ROLE_ORBITING)) P.dyn_evo |= 1u << i;
-    }
-    if (P.wind_on) P.flags |= FLAG_WIND;
-    if (P.dyn_evo) P.flags |= FLAG_DYN;
-    P.tides_host_central = c0.bodies[P.host].tides_role == PB200_ROLE_CENTRAL;
-    P.flat_host_central = c0.bodies[P.host].flattening_role == PB200_ROLE_CENTRAL;
+    fill_uniform_params(P, c0, n_systems);
 
 #define TRY(x) do { int _r = (x); if (_r != PB200_OK) { pb200_ensemble_destroy(e); return _r; } } while (0)
 #define CUDA_TRY_E(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { pb200_ensemble_destroy(e); return set_error(PB200_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
@@ -685,6 +692,50 @@ static int refresh_clock_mirror(pb200_ensemble* e) {
     return PB200_OK;
 }
 
+// ---- Which build of the step kernel integrates an ensemble (geometry builds). A pure function of the case's
+// uniform parameters, the ensemble size and the SM count, so that it can be asked without a device (pb200_case_step_kernel).
+enum StepBuild { BUILD_GENERIC, BUILD_N8, BUILD_N8W, BUILD_S2, BUILD_S2T, BUILD_S2ANY, BUILD_S3, BUILD_S3E, BUILD_S3ANY, BUILD_S3J, BUILD_S3P, BUILD_S3JANY };
+static const char* build_name(StepBuild b) {
+    static const char* const names[] = {"generic", "n8", "n8w", "s2", "s2t", "s2any", "s3", "s3e", "s3any", "s3j", "s3p", "s3jany"};
+    return names[b];
+}
+static StepBuild select_build(const KParams& P, int coord, int gr, int arithmetic, size_t n_sys, int sm_count, bool force_generic, bool narrow_blocks,
+                              bool pair_lanes) {
+    // compile-time geometry builds: host at index 0
+    const bool fixed_ok = P.host == 0 && !force_generic;
+    const bool dh = coord == PB200_COORD_DEMOCRATIC_HELIOCENTRIC, kidder = gr == PB200_GR_KIDDER1995;
+    const int tfg = FLAG_TIDES | FLAG_FLAT | FLAG_GR, flags = P.flags;
+    // 8 bodies, tides + flattening + Kidder1995, democratic heliocentric (config 4): 384-thread CTAs once there is at least one of
+    // them per SM (below that the 64-thread build spreads the work over more SMs; the all-exact arithmetic gains nothing from
+    // them: 2.36e8 against 2.49e8 system-steps/s)
+    if (fixed_ok && P.n_bodies == 8 && dh && kidder && flags == tfg)
+        return (n_sys * 8 >= (size_t)384 * (size_t)sm_count && !narrow_blocks && arithmetic != PB200_ARITH_STRICT) ? BUILD_N8W : BUILD_N8;
+    // 2 and 3 bodies: lane = planet (small_step.cuh) — host 0, democratic heliocentric (or Jacobi with 3 bodies), spin
+    // integrated, any subset of tides / flattening / GR Kidder1995 / evolution tables, no wind, no dynamical tides. The BASELINE
+    // configurations (1, 2, 3, 3-evolving, 5) have compile-time effect sets; every other subset takes the catch-all build of
+    // its geometry (flag word read at run time). PB200_FORCE_GENERIC=1 gives the lane = body kernel.
+    const bool small_ok = fixed_ok && P.spin_on && (flags & ~(tfg | FLAG_EVO)) == 0 && (!(flags & FLAG_GR) || kidder);
+    if (small_ok && P.n_bodies == 2 && dh) return flags == tfg ? BUILD_S2 : flags == FLAG_TIDES ? BUILD_S2T : BUILD_S2ANY;
+    if (small_ok && P.n_bodies == 3 && dh) return flags == tfg ? BUILD_S3 : flags == (tfg | FLAG_EVO) ? BUILD_S3E : BUILD_S3ANY;
+    if (small_ok && P.n_bodies == 3 && coord == PB200_COORD_JACOBI) {
+        if (flags != (tfg | FLAG_EVO)) return BUILD_S3JANY;
+        // body 2 an OrbitingBody of no effect (the circumbinary planet of config 5): it rides in body 1's thread once the ensemble
+        // fills the GPU that way (six warps per SM as one 192-thread CTA); a smaller ensemble keeps two lanes per system (twice the
+        // warps: 8192 members 4.4e8 against 4.2e8 system-steps/s)
+        const bool passive = (((P.tides_orbiting | P.flat_orbiting | P.gr_orbiting) >> 2) & 1u) == 0;
+        return passive && !pair_lanes && 4 * n_sys >= 3 * (size_t)192 * (size_t)sm_count ? BUILD_S3P : BUILD_S3J;
+    }
+    return BUILD_GENERIC;
+}
+
+const char* pb200_case_step_kernel(const pb200_case_t* c, size_t n_systems, int sm_count, int arithmetic) {
+    if (!c || c->n_particles < 2 || c->n_particles > PB200_MAX_PARTICLES) return "";
+    KParams P{};
+    fill_uniform_params(P, *c, n_systems);
+    const int gr = c->consider_general_relativity ? c->general_relativity_implementation : PB200_GR_DISABLED;
+    return build_name(select_build(P, c->coordinates_type, gr, arithmetic, n_systems, sm_count, false, false, false));
+}
+
 int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
     if (!e) return set_error(PB200_E_INVALID, "null ensemble");
     if (n_steps == 0) return PB200_OK;
@@ -721,37 +772,25 @@ int pb200_ensemble_step(pb200_ensemble_t* e, uint64_t n_steps) {
     }
     CUDA_TRY(cudaEventRecord(e->ev0, e->stream));
     {
+        const StepBuild build = select_build(e->P, e->coord, e->gr, e->arithmetic, e->n_sys, e->sm_count, e->force_generic, e->narrow_blocks, e->pair_lanes);
+        e->last_kernel = build_name(build);
         cudaError_t err;
-        // compile-time geometry builds (kernels_tu.cu): host at index 0 and one of the effect sets of the BASELINE configurations
-        const bool fixed_ok = e->P.host == 0 && !e->force_generic;
-        const bool dh = e->coord == PB200_COORD_DEMOCRATIC_HELIOCENTRIC, kidder = e->gr == PB200_GR_KIDDER1995;
-        const int tfg = FLAG_TIDES | FLAG_FLAT | FLAG_GR, flags = e->P.flags;
-        const bool small_ok = fixed_ok && e->P.spin_on && (flags & ~(tfg | FLAG_EVO)) == 0 && (!(flags & FLAG_GR) || kidder);
-        // 8 bodies: 384-thread CTAs once there is at least one of them per SM (below that the 64-thread build spreads the work over more SMs)
-        if (fixed_ok && e->n_bodies == 8 && dh && kidder && e->P.flags == tfg)
-            // (the all-exact arithmetic gains nothing from them: 2.36e8 against 2.49e8 system-steps/s)
-            err = (threads >= (size_t)384 * (size_t)e->sm_count && !e->narrow_blocks && e->arithmetic != PB200_ARITH_STRICT)
-                      ? (e->last_kernel = "n8w", pb200_launch_n8w(e, threads, n_steps)) : (e->last_kernel = "n8", pb200_launch_n8(e, threads, n_steps));
-        // 2 and 3 bodies: lane = planet (small_step.cuh) — host 0, democratic heliocentric (or Jacobi with 3 bodies), spin
-        // integrated, any subset of tides / flattening / GR Kidder1995 / evolution tables, no wind, no dynamical tides. The BASELINE
-        // configurations (1, 2, 3, 3-evolving, 5) have compile-time effect sets; every other subset takes the catch-all build of
-        // its geometry (flag word read at run time). PB200_FORCE_GENERIC=1 gives the lane = body kernel.
-        else if (small_ok && e->n_bodies == 2 && dh)
-            err = flags == tfg ? (e->last_kernel = "s2", pb200_launch_s2(e, n_steps)) : flags == FLAG_TIDES ? (e->last_kernel = "s2t", pb200_launch_s2t(e, n_steps)) : (e->last_kernel = "s2any", pb200_launch_s2any(e, n_steps));
-        else if (small_ok && e->n_bodies == 3 && dh)
-            err = flags == tfg ? (e->last_kernel = "s3", pb200_launch_s3(e, n_steps)) : flags == (tfg | FLAG_EVO) ? (e->last_kernel = "s3e", pb200_launch_s3e(e, n_steps)) : (e->last_kernel = "s3any", pb200_launch_s3any(e, n_steps));
-        else if (small_ok && e->n_bodies == 3 && e->coord == PB200_COORD_JACOBI) {
-            if (flags != (tfg | FLAG_EVO)) err = (e->last_kernel = "s3jany", pb200_launch_s3jany(e, n_steps));
-            else
-                // body 2 an OrbitingBody of no effect (the circumbinary planet): it rides in body 1's thread once the ensemble fills the
-                // GPU that way (six warps per SM); a smaller ensemble keeps two lanes per system (twice the warps: 8192 members 4.4e8 vs 4.2e8)
-                err = (((e->P.tides_orbiting | e->P.flat_orbiting | e->P.gr_orbiting) >> 2) & 1u) == 0 && !e->pair_lanes &&
-                              4 * e->n_sys >= 3 * (size_t)192 * (size_t)e->sm_count
-                          ? (e->last_kernel = "s3p", pb200_launch_s3p(e, n_steps)) : (e->last_kernel = "s3j", pb200_launch_s3j(e, n_steps));
+        switch (build) {
+            case BUILD_N8W: err = pb200_launch_n8w(e, threads, n_steps); break;
+            case BUILD_N8: err = pb200_launch_n8(e, threads, n_steps); break;
+            case BUILD_S2: err = pb200_launch_s2(e, n_steps); break;
+            case BUILD_S2T: err = pb200_launch_s2t(e, n_steps); break;
+            case BUILD_S2ANY: err = pb200_launch_s2any(e, n_steps); break;
+            case BUILD_S3: err = pb200_launch_s3(e, n_steps); break;
+            case BUILD_S3E: err = pb200_launch_s3e(e, n_steps); break;
+            case BUILD_S3ANY: err = pb200_launch_s3any(e, n_steps); break;
+            case BUILD_S3J: err = pb200_launch_s3j(e, n_steps); break;
+            case BUILD_S3P: err = pb200_launch_s3p(e, n_steps); break;
+            case BUILD_S3JANY: err = pb200_launch_s3jany(e, n_steps); break;
+            default:
+                err = e->arithmetic == PB200_ARITH_FAST ? pb200_launch_generic_fast(e, threads, n_steps)
+                      : e->arithmetic == PB200_ARITH_STRICT ? pb200_launch_generic_strict(e, threads, n_steps) : pb200_launch_generic_hybrid(e, threads, n_steps);
         }
-        else if (e->arithmetic == PB200_ARITH_FAST) err = (e->last_kernel = "generic", pb200_launch_generic_fast(e, threads, n_steps));
-        else if (e->arithmetic == PB200_ARITH_STRICT) err = (e->last_kernel = "generic", pb200_launch_generic_strict(e, threads, n_steps));
-        else err = (e->last_kernel = "generic", pb200_launch_generic_hybrid(e, threads, n_steps));
         e->launches++;
         if (err != cudaSuccess) return set_error(PB200_E_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(err));
     }

@@ -218,6 +218,13 @@ class Ensemble:
         return e, l
 
 
+def step_kernel_for(case, n_systems, sm_count=148, arithmetic=abi.ARITH_HYBRID):
+    """Name of the step-kernel build that would integrate an ensemble of `n_systems` members of `case` on a GPU with
+    `sm_count` SMs (pb200_case_step_kernel; needs no device): "generic", "n8" / "n8w", "s2", "s2t", "s3", "s3e", "s3j", "s3p",
+    "s2any", "s3any", "s3jany" — DESIGN.md §3, geometry builds."""
+    return lib().pb200_case_step_kernel(C.byref(case), int(n_systems), int(sm_count), int(arithmetic)).decode()
+
+
 def measure_fp64_peak(device=0, ms_target=50.0):
     v = C.c_double()
     _check(lib().pb200_measure_fp64_peak(device, ms_target, C.byref(v)))

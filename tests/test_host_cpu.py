@@ -116,3 +116,48 @@ def test_validate_rejects_out_of_range_and_duplicate_particle_ids():
         validate_case(case, tables)
     case.bodies[3].id = 3
     validate_case(case, tables)
+
+
+def test_step_kernel_selection_is_a_pure_function_of_the_case():
+    """Which build of the step kernel integrates a case (pb200_case_step_kernel, no device needed): every BASELINE configuration
+    at its BASELINE ensemble size lands on its own compile-time build; other effect subsets of 2- / 3-body systems on the
+    catch-all lane = planet builds; everything else (other body counts, WHDS, host not at index 0, Anderson / Newhall GR, pure
+    gravity) on the run-time-geometry kernel."""
+    from posidonius_b200.ensemble import step_kernel_for
+
+    def kernel(name, n_sys, edit=None, **kw):
+        d = config_case(name)
+        if edit:
+            edit(d)
+        case, _ = case_from_dict(d)
+        return step_kernel_for(case, n_sys, **kw)
+
+    assert kernel("c1_example", 65536) == "s2"
+    assert kernel("c2_case3", 4096) == "s2t"
+    assert kernel("c3_case7", 16384) == "s3"
+    assert kernel("c3_case7_evolving", 16384) == "s3e"
+    assert kernel("c4_trappist1", 65536) == "n8w"
+    assert kernel("c4_trappist1", 8192) == "n8w"                                  # the 8-GPU shard: 171 CTAs of 384 threads, time-sliced
+    assert kernel("c4_trappist1", 4096) == "n8"                                   # fewer than one 384-thread CTA per SM: 64-thread CTAs
+    assert kernel("c4_trappist1", 65536, arithmetic=abi.ARITH_STRICT) == "n8"
+    assert kernel("c5_circumbinary", 65536) == "s3p"                              # passive planet, one thread per system
+    assert kernel("c5_circumbinary", 8192) == "s3j"                               # small shard: two lanes per system
+    off = lambda *effects: (lambda d: [d["universe"]["consider_effects"].__setitem__(e, False) for e in effects])
+    assert kernel("c1_example", 1000, off("general_relativity")) == "s2any"
+    assert kernel("c3_case7_evolving", 1000, off("rotational_flattening")) == "s3any"
+    assert kernel("c5_circumbinary", 65536, off("general_relativity")) == "s3jany"
+    assert kernel("c1_example", 1000, off("tides", "rotational_flattening", "general_relativity")) == "generic"   # pure gravity: no spin to integrate
+
+    def whds(d):
+        d["alternative_coordinates_type"] = "WHDS"
+    assert kernel("c1_example", 1000, whds) == "generic"
+
+    def anderson(d):
+        d["universe"]["general_relativity_implementation"] = "Anderson1975"
+    assert kernel("c3_case7", 1000, anderson) == "generic"
+    # the 5-body golden fixtures of the reference: run-time geometry
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "manifest.json")) as f:
+        fx = json.load(f)["fixtures"]["test_integrator-whfast_jacobi"]
+    case, _ = case_from_dict(load_json_gz(fx["case"]))
+    assert case.n_particles == 5 and step_kernel_for(case, 1000) == "generic"
