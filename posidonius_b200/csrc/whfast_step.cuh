@@ -130,6 +130,9 @@ __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, cons
     // Q3: previous spins, new position
     if (ARITH) { q.rs_s = sdot(hr_s, strict(cold.getk3(PB_HOST(P), E_S))).v; q.rs_p = sdot(hr_s, strict(q.s)).v; }
     else { q.rs_s = dot(hr, cold.getk3(PB_HOST(P), E_S)); q.rs_p = dot(hr, q.s); }
+    // the first evaluation rewrites E_S with the fresh spins: every lane's read above comes first (the vote at the top of the
+    // loop already keeps the lanes together; the barrier also orders the shared-memory accesses — compute-sanitizer racecheck)
+    __syncwarp();
     bool done = !alive;  // group-uniform
     bool converged = false;
 #pragma unroll 1
