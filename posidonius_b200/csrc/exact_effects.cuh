@@ -29,6 +29,8 @@ using namespace pb200;
 // (the host is not part of the sum), which only the host itself rewrites in the next round.
 __device__ __forceinline__ void host_sums6(const KParams& P, const Cold& cold, int b, S3 u, S3 w, S3& su, S3& sw) {
 #if PB_DIST
+    // (the previous round's totals sit in the host's term cells, which the host rewrites now: every lane has read them first)
+    __syncwarp();
     dist_put3(cold, M_0, 0, plain(u)); dist_put3(cold, M_0, 3, plain(w));
     __syncwarp();
     if (b < 6) {
