@@ -25,8 +25,8 @@ using namespace pb200;
 // Host sums of two vectors over the non-host bodies in index order — the same additions in the same order as the
 // reference's serial loops over the particles. Every lane passes its terms (zero unless it is an OrbitingBody of the
 // effect); on return the HOST lane holds the sums (the other lanes get unspecified finite values).
-// Two warp barriers per round: the cell that receives the total of scalar c is the host's own term cell of that scalar
-// (the host is not part of the sum), which only the host itself rewrites in the next round.
+// Three warp barriers per round (before the terms are published, before the walk, before the totals are read): the cell
+// that receives the total of scalar c is the host's own term cell of that scalar (the host is not part of the sum).
 __device__ __forceinline__ void host_sums6(const KParams& P, const Cold& cold, int b, S3 u, S3 w, S3& su, S3& sw) {
 #if PB_DIST
     // (the previous round's totals sit in the host's term cells, which the host rewrites now: every lane has read them first)
