@@ -107,8 +107,9 @@ __device__ __forceinline__ S3 ordered_diff_others(const Cold& cold, S3 init, int
 //     increment, hence the new v, L and their Kahan residuals, carry the reference's roundings whenever the two uncommitted
 //     iterates rounded to the same doubles as the reference's, which they do except with probability ~ |dv| / |v| per
 //     component (the iterates enter the exact evaluation only through v_orig + dv / 2, and a relative error of 1e-15 in a
-//     dv of relative size 1e-8 .. 1e-6 rarely moves that sum across a rounding boundary). Nothing accumulates: the
-//     residuals are exact again after every committed evaluation.
+//     dv of relative size 1e-8 .. 1e-6 rarely moves that sum across a rounding boundary; the angular momenta move faster
+//     — dL / L up to 1e-5 per step — so the spin entering the exact evaluation is an ulp off now and then, which shows in
+//     the Kahan residuals first and in r, v only much later: profiles/r2_hybrid_decay.txt).
 template <int COORD, int GR, int ARITH>
 __device__ __forceinline__ void midpoint(const KParams& P, const Roles& ro, const Cold& cold, int gb, int hl, int b, bool alive, Lane& q,
                                          double t, bool evolution, unsigned int& warnings, bool save_tides, size_t sys) {
